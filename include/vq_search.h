@@ -1,0 +1,145 @@
+/*
+ * vq_search.h — C-ABI of the B200-native frame-embedding search engine.
+ *
+ * This is the drop-in boundary for the query hot path of adhney/video-quierer.  The
+ * reference is pure Python and has no FFI of its own, so each entry
+ * point below cites the reference *code* it replaces; the ctypes binding a maintainer
+ * adds on the reference side is shown in INTEGRATION.md.
+ *
+ * Conventions
+ *   - plain `extern "C"`, pointers + sizes only; no torch / C++ types cross the boundary;
+ *   - every function returns 0 on success or a negative VQ_E* code; `vq_last_error()`
+ *     returns a thread-local human-readable message for the last failure;
+ *   - all pointers are DEVICE pointers unless the name ends in `_host`;
+ *   - the caller owns all memory (torch allocates; the library borrows for the call);
+ *   - all work is enqueued on `stream` (a cudaStream_t passed as void*); nothing
+ *     synchronises the device unless stated;
+ *   - rows of a store are `ld` elements apart (`ld >= dim`, padding must be zero;
+ *     `ld % 32 == 0` for fp32 stores, `ld % 64 == 0` for bf16 stores);
+ *   - result order everywhere: score descending, ties by ascending row; missing results
+ *     (k > n, NaN scores) have row = -1 and score = -inf.
+ */
+#ifndef VQ_SEARCH_H_
+#define VQ_SEARCH_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VQ_ABI_VERSION 1
+
+/* element types of a frame-embedding store */
+#define VQ_F32  0
+#define VQ_BF16 1
+
+/* error codes */
+#define VQ_OK            0
+#define VQ_EINVAL       -1   /* bad argument (message says which) */
+#define VQ_ECUDA        -2   /* a CUDA call / launch failed */
+#define VQ_EWORKSPACE   -3   /* workspace too small */
+#define VQ_EUNSUPPORTED -4   /* shape not supported by the requested path */
+
+/* query normalisation applied inside vq_scan_topk / vq_hnsw_search */
+#define VQ_NORM_NONE   0     /* queries are used as given */
+#define VQ_NORM_EPS    1     /* q / (|q| + 1e-10)  — video_search_overhaul.py:49-50 */
+#define VQ_NORM_PLAIN  2     /* q / |q|            — src/indexes/hnsw.py:250,499 */
+
+/* scan path selection */
+#define VQ_SCAN_AUTO   0     /* pick by batch size and store dtype */
+#define VQ_SCAN_FMA    1     /* fp32-FMA HBM-streaming path ("GEMV" path), any store dtype */
+#define VQ_SCAN_MMA    2     /* tcgen05/TMEM tile-GEMM path (bf16 store: kind::f16; fp32 store: kind::tf32) */
+
+int         vq_abi_version(void);
+const char* vq_last_error(void);
+/* Name of the scan kernel the last vq_scan_topk call on this thread dispatched to and how
+ * many kernels it launched (for bench.py's gpu_launches accounting). */
+const char* vq_last_scan_path(void);
+int         vq_last_launch_count(void);
+
+/* (a) L2-normalisation of embeddings, in place.                       [kernel: l2norm_rows]
+ * Replaces: `embedding / embedding.norm()` video_search_overhaul.py:226,289;
+ *           `vector / np.linalg.norm(vector)` src/indexes/hnsw.py:157.
+ * x: [rows, ld] fp32; eps_mode is VQ_NORM_EPS or VQ_NORM_PLAIN. */
+int vq_l2_normalize(float* x, int64_t rows, int dim, int ld, int eps_mode, void* stream);
+
+/* Store ingest: copy `rows` fp32 embeddings (src: [rows, src_ld]) into a store of dtype
+ * `dst_dtype` (dst: [rows, dst_ld], zero-padding columns dim..dst_ld), optionally
+ * normalising each row first (norm_mode = VQ_NORM_*).               [kernel: ingest_rows]
+ * Replaces: `self.embeddings.append(embedding.astype(np.float32))` video_search_overhaul.py:33
+ * and the per-query `np.vstack(self.embeddings)` (:46) — the matrix is built once. */
+int vq_ingest_rows(const float* src, int64_t rows, int dim, int src_ld,
+                   void* dst, int dst_dtype, int dst_ld, int norm_mode, void* stream);
+
+/* (b)+(c) exact batched query x frame inner-product scan with fused per-query top-k.
+ * Replaces: SimpleVideoIndex.search, video_search_overhaul.py:40-64 (normalise :49-50,
+ * np.dot :53, argsort top-k :56) and the sequential batch loop src/api/routes.py:627-634.
+ *   store      [n, ld] of store_dtype, rows assumed unit-norm (never re-normalised, :53)
+ *   queries    [b, dim] fp32 (dense, row stride = dim)
+ *   out_scores [b, k] fp32, out_rows [b, k] int32  (best first)
+ *   workspace  >= vq_scan_workspace_bytes(...) bytes, 256-byte aligned
+ * Scores never round-trip to HBM: only per-CTA top-k candidate lists are written. */
+size_t vq_scan_workspace_bytes(int64_t n, int dim, int ld, int store_dtype, int b, int k, int path);
+int vq_scan_topk(const void* store, int64_t n, int dim, int ld, int store_dtype,
+                 const float* queries, int b, int k, int query_norm,
+                 float* out_scores, int32_t* out_rows,
+                 void* workspace, size_t workspace_bytes, int path, void* stream);
+
+/* Merge g candidate lists per query into one global top-k_out.        [kernel: topk_merge]
+ * New (the reference is single-process); this is the shard/merge layer of SURVEY.md §8(e).
+ *   scores/rows  [g, b, k_in] (fp32 / int32, local row numbers, row < 0 = empty slot)
+ *   shard_offsets[g] int64 added to local rows (may be NULL = all zero)
+ *   out_scores   [b, k_out] fp32, out_rows [b, k_out] int64 (global rows) */
+int vq_topk_merge(const float* scores, const int32_t* rows, int g, int b, int k_in,
+                  const int64_t* shard_offsets, int k_out,
+                  float* out_scores, int64_t* out_rows, void* stream);
+
+/* Exact fp32 re-score of candidate rows (two-stage mode: bf16 scan selects k_cand, this
+ * re-scores them from the fp32 shadow store and keeps the best k).     [kernel: rescore_rows]
+ *   cand_rows [b, k_cand] int32 (row < 0 ignored); queries [b, ld] fp32 *already normalised*
+ *   and zero padded to the store's ld (i.e. the output of vq_ingest_rows on the queries)
+ *   out_scores [b, k] fp32, out_rows [b, k] int32 */
+int vq_rescore_topk(const float* store_f32, int64_t n, int dim, int ld,
+                    const float* queries, int b, const int32_t* cand_rows, int k_cand, int k,
+                    float* out_scores, int32_t* out_rows, void* stream);
+
+/* (d) HNSW greedy/beam search, one warp per query.                     [kernel: hnsw_search]
+ * Replaces: HNSWIndex.search / OptimizedHNSWIndex.search, src/indexes/hnsw.py:238-280,
+ * :488-528 and _search_layer :76-121 (same stop rule :103 and admit rule :113).
+ *   store      [n, ld] of store_dtype (unit-norm rows)
+ *   levels     [n] int32 top level of each node
+ *   adj0       [n, m0] int32 layer-0 neighbours, -1 padded
+ *   upper_off  [n] int32 first upper-layer slot of a node (-1 if level 0)
+ *   upper_adj  [slots, m] int32: slot(node, lv) = upper_off[node] + lv - 1
+ *   entry / max_level: entry point and its level;  ef = max(ef_search, k) like :264
+ *   out_dist   [b, k] fp32 (1 - dot, ascending), out_rows [b, k] int32
+ *   out_stats  optional [b, 2] uint32: distance evaluations, expanded nodes (roofline) */
+size_t vq_hnsw_workspace_bytes(int b, int dim, int ef);
+int vq_hnsw_search(const void* store, int64_t n, int dim, int ld, int store_dtype,
+                   const int32_t* levels, const int32_t* adj0, int m0,
+                   const int32_t* upper_off, const int32_t* upper_adj, int m,
+                   int32_t entry, int max_level, int ef,
+                   const float* queries, int b, int k, int query_norm,
+                   float* out_dist, int32_t* out_rows, uint32_t* out_stats,
+                   void* workspace, size_t workspace_bytes, void* stream);
+
+/* HNSW construction on the GPU (the reference's per-insert Python build,
+ * src/indexes/hnsw.py:150-229, is ~10 ms/insert and unusable at 1M).   [kernels: knn_*, link_*]
+ * Builds one layer: for every member node, its `m_out` graph neighbours chosen from the
+ * exact `k_cand` nearest members (brute-force scan + fused top-k), then reverse edges are
+ * added and every list is pruned back to `m_out` closest (hnsw.py:197-223 semantics).
+ *   members    [n_members] int32 node ids participating in this layer (NULL = all n rows)
+ *   adj_out    [n_members, m_out] int32 (-1 padded), neighbours as node ids
+ *   diversify  0 = closest-m (reference hnsw.py:123-148), 1 = HNSW diversity heuristic */
+size_t vq_hnsw_layer_workspace_bytes(int64_t n_members, int dim, int ld, int store_dtype, int k_cand, int m_out);
+int vq_hnsw_build_layer(const void* store, int64_t n, int dim, int ld, int store_dtype,
+                        const int32_t* members, int64_t n_members,
+                        int k_cand, int m_out, int diversify,
+                        int32_t* adj_out, void* workspace, size_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VQ_SEARCH_H_ */

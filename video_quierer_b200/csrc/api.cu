@@ -1,0 +1,228 @@
+// C-ABI entry points (include/vq_search.h) for normalise / ingest / exact scan / merge / rescore.
+#include <stdarg.h>
+#include <string.h>
+
+#include "vq_common.cuh"
+
+// ---- kernels implemented in the other translation units
+int vq_scan_fma_tile_rows(int bt);
+size_t vq_scan_fma_smem(int bt, int ld, int k);
+int vq_scan_fma_grid(int n, int bt);
+int vq_scan_fma_launch(const void* store, int n, int ld, int store_dtype, const float* q, int bt, int k,
+                       float* part_scores, int* part_rows, int grid, cudaStream_t stream);
+int vq_topk_merge_launch(const float* scores, const int* rows, int g, int b_stride, int b_out, int k_in,
+                         const long long* offsets, int k_out, float* out_scores, void* out_rows,
+                         int rows64, int negate_out, cudaStream_t stream);
+int vq_ingest_launch(const float* src, long long rows, int dim, int src_ld, void* dst, int dst_dtype,
+                     int dst_ld, int mode, cudaStream_t stream);
+int vq_rescore_launch(const float* store, int ld, const float* queries, int qld, const int* cand, int b,
+                      int k_cand, float* out_scores, cudaStream_t stream);
+// tcgen05 path (scan_mma.cu)
+bool vq_scan_mma_supported(int64_t n, int dim, int ld, int store_dtype, int b, int k);
+size_t vq_scan_mma_workspace(int64_t n, int ld, int store_dtype, int b, int k);
+int vq_scan_mma_run(const void* store, int64_t n, int dim, int ld, int store_dtype, const float* qnorm, int b, int k,
+                    float* out_scores, int32_t* out_rows, void* ws, size_t ws_bytes, cudaStream_t stream,
+                    int* launches);
+
+// ----------------------------------------------------------------------------- error state
+static thread_local char g_err[512] = "";
+static thread_local char g_path[64] = "";
+static thread_local int g_launches = 0;
+
+void vq_set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+void vq_note_launch(const char* path, int launches) {
+    if (path) { strncpy(g_path, path, sizeof(g_path) - 1); g_path[sizeof(g_path) - 1] = 0; }
+    g_launches = launches;
+}
+
+int vq_num_sms() {
+    static int sms[64] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+    if (sms[dev] == 0) {
+        int v = 0;
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
+        sms[dev] = v;
+    }
+    return sms[dev];
+}
+
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+static inline int pow2_at_least(int v) { int p = 1; while (p < v) p <<= 1; return p; }
+
+static int check_store(int64_t n, int dim, int ld, int store_dtype) {
+    VQ_CHECK_ARG(store_dtype == VQ_F32 || store_dtype == VQ_BF16, "store_dtype must be VQ_F32 or VQ_BF16, got %d", store_dtype);
+    VQ_CHECK_ARG(n >= 0 && n < (int64_t)INT_MAX, "n=%lld out of range (shard rows must fit int32)", (long long)n);
+    VQ_CHECK_ARG(dim > 0 && ld >= dim, "need 0 < dim <= ld (dim=%d ld=%d)", dim, ld);
+    const int mult = store_dtype == VQ_BF16 ? 64 : 32;
+    VQ_CHECK_ARG(ld % mult == 0, "ld=%d must be a multiple of %d for this store dtype", ld, mult);
+    return VQ_OK;
+}
+
+struct ScanPlan {
+    int bt;            // FMA query tile
+    int grid;          // FMA grid
+    size_t q_bytes, part_bytes;
+};
+static ScanPlan fma_plan(int64_t n, int ld, int b, int k, int force_bt) {
+    ScanPlan p;
+    p.bt = force_bt ? force_bt : (b >= 16 ? 16 : pow2_at_least(b));
+    // shrink the tile until its shared memory fits
+    while (p.bt > 1 && vq_scan_fma_smem(p.bt, ld, k) > 200 * 1024) p.bt >>= 1;
+    p.grid = vq_scan_fma_grid((int)n, p.bt);
+    const int b_pad = (int)align_up((size_t)b, (size_t)p.bt);
+    p.q_bytes = align_up((size_t)b_pad * ld * 4, 256);
+    p.part_bytes = align_up((size_t)p.grid * p.bt * k * 4, 256);
+    return p;
+}
+
+extern "C" {
+
+int vq_abi_version(void) { return VQ_ABI_VERSION; }
+const char* vq_last_error(void) { return g_err; }
+const char* vq_last_scan_path(void) { return g_path; }
+int vq_last_launch_count(void) { return g_launches; }
+
+int vq_l2_normalize(float* x, int64_t rows, int dim, int ld, int eps_mode, void* stream) {
+    VQ_CHECK_ARG(x != nullptr || rows == 0, "x is NULL");
+    VQ_CHECK_ARG(rows >= 0 && dim > 0 && ld >= dim, "bad shape rows=%lld dim=%d ld=%d", (long long)rows, dim, ld);
+    VQ_CHECK_ARG(eps_mode == VQ_NORM_EPS || eps_mode == VQ_NORM_PLAIN, "eps_mode must be VQ_NORM_EPS or VQ_NORM_PLAIN");
+    const int rc = vq_ingest_launch(x, rows, dim, ld, x, VQ_F32, ld, eps_mode, (cudaStream_t)stream);
+    vq_note_launch("l2norm_rows", rows ? 1 : 0);
+    return rc;
+}
+
+int vq_ingest_rows(const float* src, int64_t rows, int dim, int src_ld, void* dst, int dst_dtype, int dst_ld,
+                   int norm_mode, void* stream) {
+    VQ_CHECK_ARG((src && dst) || rows == 0, "src/dst is NULL");
+    VQ_CHECK_ARG(rows >= 0 && dim > 0 && src_ld >= dim && dst_ld >= dim, "bad shape rows=%lld dim=%d src_ld=%d dst_ld=%d",
+                 (long long)rows, dim, src_ld, dst_ld);
+    VQ_CHECK_ARG(dst_dtype == VQ_F32 || dst_dtype == VQ_BF16, "dst_dtype must be VQ_F32 or VQ_BF16");
+    VQ_CHECK_ARG(norm_mode >= VQ_NORM_NONE && norm_mode <= VQ_NORM_PLAIN, "bad norm_mode %d", norm_mode);
+    const int rc = vq_ingest_launch(src, rows, dim, src_ld, dst, dst_dtype, dst_ld, norm_mode, (cudaStream_t)stream);
+    vq_note_launch("ingest_rows", rows ? 1 : 0);
+    return rc;
+}
+
+size_t vq_scan_workspace_bytes(int64_t n, int dim, int ld, int store_dtype, int b, int k, int path) {
+    (void)dim;
+    if (n <= 0 || b <= 0 || k <= 0) return 256;
+    const ScanPlan p = fma_plan(n, ld, b, k, path == 3 ? 32 : 0);
+    size_t fma = p.q_bytes + 2 * p.part_bytes;
+    size_t mma = 0;
+    if (path != VQ_SCAN_FMA && path != 3) mma = p.q_bytes + vq_scan_mma_workspace(n, ld, store_dtype, b, k);
+    return (fma > mma ? fma : mma) + 256;
+}
+
+int vq_scan_topk(const void* store, int64_t n, int dim, int ld, int store_dtype, const float* queries, int b, int k,
+                 int query_norm, float* out_scores, int32_t* out_rows, void* workspace, size_t workspace_bytes,
+                 int path, void* stream_v) {
+    cudaStream_t stream = (cudaStream_t)stream_v;
+    int rc = check_store(n, dim, ld, store_dtype);
+    if (rc) return rc;
+    VQ_CHECK_ARG(b >= 0 && k > 0 && k <= 1024, "need b >= 0 and 0 < k <= 1024 (b=%d k=%d)", b, k);
+    VQ_CHECK_ARG(query_norm >= VQ_NORM_NONE && query_norm <= VQ_NORM_PLAIN, "bad query_norm %d", query_norm);
+    VQ_CHECK_ARG(path >= 0 && path <= 3, "bad path %d", path);
+    if (b == 0) { vq_note_launch("none", 0); return VQ_OK; }
+    VQ_CHECK_ARG(store && queries && out_scores && out_rows && workspace, "NULL pointer argument");
+    VQ_CHECK_ARG(((uintptr_t)workspace & 255) == 0, "workspace must be 256-byte aligned");
+    VQ_CHECK_ARG(((uintptr_t)store & 15) == 0, "store must be 16-byte aligned");
+    const size_t need = vq_scan_workspace_bytes(n, dim, ld, store_dtype, b, k, path);
+    if (workspace_bytes < need) {
+        vq_set_error("workspace too small: %zu < %zu", workspace_bytes, need);
+        return VQ_EWORKSPACE;
+    }
+    int launches = 0;
+    if (n == 0) {   // empty store: all slots empty (the reference returns [] — video_search_overhaul.py:42-43)
+        VQ_CUDA(cudaMemsetAsync(out_rows, 0xff, (size_t)b * k * 4, stream));
+        VQ_CUDA(cudaMemsetAsync(out_scores, 0xff, (size_t)b * k * 4, stream));   // NaN pattern; rows=-1 is the marker
+        vq_note_launch("empty", 0);
+        return VQ_OK;
+    }
+
+    bool use_mma = false;
+    if (path == VQ_SCAN_MMA) {
+        if (!vq_scan_mma_supported(n, dim, ld, store_dtype, b, k)) {
+            vq_set_error("tcgen05 scan path does not support n=%lld dim=%d ld=%d dtype=%d b=%d k=%d", (long long)n, dim,
+                         ld, store_dtype, b, k);
+            return VQ_EUNSUPPORTED;
+        }
+        use_mma = true;
+    } else if (path == VQ_SCAN_AUTO) {
+        // bf16 store: the tensor path wins as soon as the FMA path stops being HBM-bound.
+        // fp32 store: kind::tf32 would break the 1e-5 score parity, so AUTO never picks it.
+        use_mma = store_dtype == VQ_BF16 && b > 16 && vq_scan_mma_supported(n, dim, ld, store_dtype, b, k);
+    }
+
+    const ScanPlan p = fma_plan(n, ld, b, k, path == 3 ? 32 : 0);
+    unsigned char* ws = (unsigned char*)workspace;
+    float* qn = (float*)ws;                               // [b_pad, ld] normalised, zero padded
+    const int b_pad = (int)align_up((size_t)b, (size_t)p.bt);
+    VQ_CUDA(cudaMemsetAsync(qn, 0, (size_t)b_pad * ld * 4, stream));
+    rc = vq_ingest_launch(queries, b, dim, dim, qn, VQ_F32, ld, query_norm, stream);
+    if (rc) return rc;
+    launches += 1;
+
+    if (use_mma) {
+        int l2 = 0;
+        rc = vq_scan_mma_run(store, n, dim, ld, store_dtype, qn, b, k, out_scores, out_rows, ws + p.q_bytes,
+                             workspace_bytes - p.q_bytes, stream, &l2);
+        if (rc) return rc;
+        vq_note_launch(store_dtype == VQ_BF16 ? "scan_mma_bf16" : "scan_mma_tf32", launches + l2);
+        return VQ_OK;
+    }
+
+    float* part_s = (float*)(ws + p.q_bytes);
+    int* part_r = (int*)(ws + p.q_bytes + p.part_bytes);
+    for (int q0 = 0; q0 < b; q0 += p.bt) {
+        int bt = p.bt;
+        const int left = b - q0;
+        if (left < bt) bt = pow2_at_least(left);            // padded queries are all-zero rows of qn
+        const int grid = vq_scan_fma_grid((int)n, bt);
+        rc = vq_scan_fma_launch(store, (int)n, ld, store_dtype, qn + (size_t)q0 * ld, bt, k, part_s, part_r, grid, stream);
+        if (rc) return rc;
+        rc = vq_topk_merge_launch(part_s, part_r, grid, bt, left < bt ? left : bt, k, nullptr, k,
+                                  out_scores + (size_t)q0 * k, out_rows + (size_t)q0 * k, 0, 0, stream);
+        if (rc) return rc;
+        launches += 2;
+    }
+    vq_note_launch(store_dtype == VQ_BF16 ? "scan_fma_bf16" : "scan_fma_f32", launches);
+    return VQ_OK;
+}
+
+int vq_topk_merge(const float* scores, const int32_t* rows, int g, int b, int k_in, const int64_t* shard_offsets,
+                  int k_out, float* out_scores, int64_t* out_rows, void* stream) {
+    VQ_CHECK_ARG(g > 0 && b >= 0 && k_in > 0 && k_out > 0 && k_out <= 1024, "bad shape g=%d b=%d k_in=%d k_out=%d", g, b, k_in, k_out);
+    if (b == 0) return VQ_OK;
+    VQ_CHECK_ARG(scores && rows && out_scores && out_rows, "NULL pointer argument");
+    const int rc = vq_topk_merge_launch(scores, rows, g, b, b, k_in, (const long long*)shard_offsets, k_out, out_scores,
+                                        out_rows, 1, 0, (cudaStream_t)stream);
+    vq_note_launch("topk_merge", 1);
+    return rc;
+}
+
+int vq_rescore_topk(const float* store_f32, int64_t n, int dim, int ld, const float* queries, int b,
+                    const int32_t* cand_rows, int k_cand, int k, float* out_scores, int32_t* out_rows, void* stream_v) {
+    // The b*k_cand re-scored values live in a small stream-ordered scratch allocation.
+    cudaStream_t stream = (cudaStream_t)stream_v;
+    int rc = check_store(n, dim, ld, VQ_F32);
+    if (rc) return rc;
+    VQ_CHECK_ARG(b >= 0 && k_cand > 0 && k > 0 && k <= k_cand && k <= 1024, "bad shape b=%d k_cand=%d k=%d", b, k_cand, k);
+    if (b == 0) return VQ_OK;
+    VQ_CHECK_ARG(store_f32 && queries && cand_rows && out_scores && out_rows, "NULL pointer argument");
+    float* tmp = nullptr;
+    VQ_CUDA(cudaMallocAsync((void**)&tmp, (size_t)b * k_cand * 4, stream));
+    rc = vq_rescore_launch(store_f32, ld, queries, ld, cand_rows, b, k_cand, tmp, stream);
+    if (rc == VQ_OK)
+        rc = vq_topk_merge_launch(tmp, cand_rows, 1, b, b, k_cand, nullptr, k, out_scores, out_rows, 0, 0, stream);
+    cudaFreeAsync(tmp, stream);
+    vq_note_launch("rescore_rows", 2);
+    return rc;
+}
+
+}  // extern "C"

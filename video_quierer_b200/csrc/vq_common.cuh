@@ -1,0 +1,95 @@
+// Shared device/host helpers for the frame-search kernels (sm_100a only).
+#pragma once
+
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <limits.h>
+#include <math.h>
+
+#include "../../include/vq_search.h"
+
+#define VQ_WARP 32
+#define VQ_NEG_INF (-INFINITY)
+#define VQ_EMPTY_ROW INT_MAX   // sentinel row of an unused top-k slot (sorts last among equal scores)
+
+// ----------------------------------------------------------------------------- host errors
+void vq_set_error(const char* fmt, ...);
+void vq_note_launch(const char* path_or_null, int launches);
+#define VQ_CHECK_ARG(cond, ...)                 \
+    do {                                        \
+        if (!(cond)) {                          \
+            vq_set_error(__VA_ARGS__);          \
+            return VQ_EINVAL;                   \
+        }                                       \
+    } while (0)
+#define VQ_CUDA(call)                                                                     \
+    do {                                                                                  \
+        cudaError_t e__ = (call);                                                         \
+        if (e__ != cudaSuccess) {                                                         \
+            vq_set_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+            return VQ_ECUDA;                                                              \
+        }                                                                                 \
+    } while (0)
+#define VQ_LAUNCH_CHECK(name)                                                             \
+    do {                                                                                  \
+        cudaError_t e__ = cudaGetLastError();                                             \
+        if (e__ != cudaSuccess) {                                                         \
+            vq_set_error("launch of %s failed: %s", name, cudaGetErrorString(e__));       \
+            return VQ_ECUDA;                                                              \
+        }                                                                                 \
+    } while (0)
+
+int vq_num_sms();
+
+// ----------------------------------------------------------------------------- device utils
+// Total order of the engine: higher score first, then lower row.  NaN never beats anything.
+__device__ __forceinline__ bool vq_better(float s, int r, float s2, int r2) {
+    return (s > s2) || (s == s2 && r < r2);
+}
+
+// 128-bit streaming load that does not pollute L1 (the store is read exactly once per pass).
+__device__ __forceinline__ uint4 vq_ldg_stream(const void* p) {
+    uint4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                 : "l"(p));
+    return v;
+}
+
+__device__ __forceinline__ float vq_bf16lo(uint32_t w) { return __uint_as_float(w << 16); }
+__device__ __forceinline__ float vq_bf16hi(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
+
+__device__ __forceinline__ float vq_warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Insert (cs, cr) into a warp-owned descending top-k list held in shared memory
+// (ls/lr: k entries, sentinel-filled).  Must be called by all 32 lanes with uniform args.
+// Cost: O(k/32) warp steps.
+__device__ __forceinline__ void vq_list_insert(float* ls, int* lr, int k, float cs, int cr, int lane) {
+    // position = number of entries strictly better than the candidate
+    int pos = 0;
+    for (int base = 0; base < k; base += 32) {
+        int i = base + lane;
+        bool b = (i < k) && vq_better(ls[i], lr[i], cs, cr);
+        pos += __popc(__ballot_sync(0xffffffffu, b));
+    }
+    if (pos >= k) return;
+    // shift [pos, k-1) up by one, highest chunk first so nothing is overwritten before it is read
+    for (int base = ((k - 1) / 32) * 32; base >= 0; base -= 32) {
+        int i = base + lane;                // destination index
+        float s = 0.f; int r = 0;
+        bool mv = (i < k) && (i > pos);
+        if (mv) { s = ls[i - 1]; r = lr[i - 1]; }
+        __syncwarp();
+        if (mv) { ls[i] = s; lr[i] = r; }
+        __syncwarp();
+        if (base <= pos) break;
+    }
+    if (lane == 0) { ls[pos] = cs; lr[pos] = cr; }
+    __syncwarp();
+}

@@ -1,0 +1,218 @@
+"""Device-side plumbing shared by the index facades: the frame-embedding store (a contiguous
+device matrix with amortised growth) and thin wrappers that hand torch tensors to the C-ABI
+as raw pointers.  torch is used for memory, streams and distributed only — every kernel
+on the search path is ours (libvqsearch.so).
+"""
+
+from __future__ import annotations
+
+import threading
+
+import numpy as np
+import torch
+
+from . import _lib
+
+_DT = {"fp32": _lib.F32, "f32": _lib.F32, "float32": _lib.F32, "bf16": _lib.BF16, "bfloat16": _lib.BF16}
+_PATH = {"auto": _lib.SCAN_AUTO, "fma": _lib.SCAN_FMA, "gemv": _lib.SCAN_FMA, "mma": _lib.SCAN_MMA,
+         "gemm": _lib.SCAN_MMA, "fma32": _lib.SCAN_FMA32}
+
+
+def _require_cuda(device=None) -> torch.device:
+    if not torch.cuda.is_available():
+        raise RuntimeError("video_quierer_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+    return torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def _stream(device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def padded_ld(dim: int, dtype: str = "fp32") -> int:
+    """Row stride of a store: multiple of 64 elements (covers both the fp32 and bf16 rules)."""
+    return (dim + 63) // 64 * 64
+
+
+class Workspace:
+    """A grow-only device scratch buffer (256-byte aligned by the caching allocator)."""
+
+    def __init__(self, device):
+        self.device = device
+        self.buf = None
+
+    def get(self, nbytes: int) -> torch.Tensor:
+        if self.buf is None or self.buf.numel() < nbytes:
+            self.buf = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=self.device)
+        return self.buf
+
+
+class DeviceStore:
+    """Contiguous [capacity, ld] device matrix of frame embeddings (+ optional bf16 twin).
+
+    Replaces the reference's Python list of per-frame arrays that is re-stacked for every
+    query (video_search_overhaul.py:27,46).  Rows are stored as given (the reference never
+    re-normalises stored rows on the exact path) or normalised on ingest for HNSW
+    (hnsw.py:157).
+    """
+
+    def __init__(self, dim: int, device=None, keep_fp32: bool = True, keep_bf16: bool = False,
+                 capacity: int = 0):
+        self.device = _require_cuda(device)
+        self.dim = int(dim)
+        self.ld = padded_ld(dim)
+        self.n = 0
+        self.keep_fp32, self.keep_bf16 = keep_fp32, keep_bf16
+        self.f32 = None
+        self.bf16 = None
+        self.lib = _lib.load()
+        if capacity:
+            self._reserve(capacity)
+
+    # ------------------------------------------------------------------ capacity
+    def capacity(self) -> int:
+        t = self.f32 if self.f32 is not None else self.bf16
+        return 0 if t is None else t.shape[0]
+
+    def _reserve(self, rows: int):
+        cap = self.capacity()
+        if rows <= cap:
+            return
+        new_cap = max(rows, 2 * cap, 1024)
+        with torch.cuda.device(self.device):
+            if self.keep_fp32:
+                t = torch.empty((new_cap, self.ld), dtype=torch.float32, device=self.device)
+                if self.n:
+                    t[: self.n].copy_(self.f32[: self.n])
+                self.f32 = t
+            if self.keep_bf16:
+                t = torch.empty((new_cap, self.ld), dtype=torch.bfloat16, device=self.device)
+                if self.n:
+                    t[: self.n].copy_(self.bf16[: self.n])
+                self.bf16 = t
+
+    # ------------------------------------------------------------------ ingest
+    def append(self, rows, norm: int = _lib.NORM_NONE):
+        """Append fp32 rows ([m, dim] numpy or torch, host or device) through `vq_ingest_rows`."""
+        if isinstance(rows, np.ndarray):
+            src = torch.from_numpy(np.ascontiguousarray(rows, dtype=np.float32))
+        else:
+            src = rows.detach().to(torch.float32).contiguous()
+        if src.dim() == 1:
+            src = src[None, :]
+        if src.shape[1] != self.dim:
+            raise ValueError(f"embedding dimension {src.shape[1]} != store dimension {self.dim}")
+        m = src.shape[0]
+        if m == 0:
+            return
+        self._reserve(self.n + m)
+        with torch.cuda.device(self.device):
+            src = src.to(self.device, non_blocking=False)
+            st = _stream(self.device)
+            if self.keep_fp32:
+                dst = self.f32[self.n: self.n + m]
+                _lib.check(self.lib.vq_ingest_rows(_ptr(src), m, self.dim, self.dim, _ptr(dst), _lib.F32, self.ld,
+                                                   norm, st), "vq_ingest_rows")
+            if self.keep_bf16:
+                dst = self.bf16[self.n: self.n + m]
+                _lib.check(self.lib.vq_ingest_rows(_ptr(src), m, self.dim, self.dim, _ptr(dst), _lib.BF16, self.ld,
+                                                   norm, st), "vq_ingest_rows")
+        self.n += m
+
+    def truncate(self, n: int):
+        self.n = min(self.n, max(0, int(n)))
+
+    def view(self, dtype: str = "fp32") -> torch.Tensor:
+        t = self.f32 if _DT[dtype] == _lib.F32 else self.bf16
+        if t is None:
+            raise RuntimeError(f"store keeps no {dtype} copy")
+        return t[: self.n]
+
+    def rows_to_host(self, start: int = 0, stop: int | None = None) -> np.ndarray:
+        return self.view("fp32")[start:stop, : self.dim].cpu().numpy()
+
+
+class Scanner:
+    """Exact scan + fused top-k through `vq_scan_topk` (and the two-stage bf16 + re-score mode)."""
+
+    def __init__(self, device=None):
+        self.device = _require_cuda(device)
+        self.lib = _lib.load()
+        self.ws = Workspace(self.device)
+        self.lock = threading.Lock()
+        self.last_path = ""
+        self.last_launches = 0
+
+    def scan(self, mat: torch.Tensor, n: int, dim: int, queries: torch.Tensor, k: int,
+             norm: int = _lib.NORM_EPS, path: str = "auto"):
+        """mat: [>=n, ld] fp32 or bf16 device tensor; queries: [b, dim] fp32 device tensor.
+        Returns (scores [b,k] fp32, rows [b,k] int32) device tensors; empty slots have row -1."""
+        dt = _lib.F32 if mat.dtype == torch.float32 else _lib.BF16
+        ld = mat.stride(0)
+        b = queries.shape[0]
+        with torch.cuda.device(self.device):
+            out_s = torch.empty((b, k), dtype=torch.float32, device=self.device)
+            out_r = torch.empty((b, k), dtype=torch.int32, device=self.device)
+            if b == 0:
+                return out_s, out_r
+            p = _PATH[path]
+            need = self.lib.vq_scan_workspace_bytes(n, dim, ld, dt, b, k, p)
+            with self.lock:
+                ws = self.ws.get(need)
+                rc = self.lib.vq_scan_topk(_ptr(mat), n, dim, ld, dt, _ptr(queries), b, k, norm, _ptr(out_s),
+                                           _ptr(out_r), _ptr(ws), ws.numel(), p, _stream(self.device))
+                _lib.check(rc, "vq_scan_topk")
+                self.last_path = _lib.last_scan_path()
+                self.last_launches = _lib.last_launch_count()
+        return out_s, out_r
+
+    def rescore(self, f32: torch.Tensor, n: int, dim: int, queries_norm_padded: torch.Tensor,
+                cand_rows: torch.Tensor, k: int):
+        b, kc = cand_rows.shape
+        with torch.cuda.device(self.device):
+            out_s = torch.empty((b, k), dtype=torch.float32, device=self.device)
+            out_r = torch.empty((b, k), dtype=torch.int32, device=self.device)
+            rc = self.lib.vq_rescore_topk(_ptr(f32), n, dim, f32.stride(0), _ptr(queries_norm_padded), b,
+                                          _ptr(cand_rows), kc, k, _ptr(out_s), _ptr(out_r), _stream(self.device))
+            _lib.check(rc, "vq_rescore_topk")
+            self.last_launches += 2
+        return out_s, out_r
+
+    def normalise_padded(self, queries: torch.Tensor, ld: int, norm: int) -> torch.Tensor:
+        """[b, dim] -> normalised, zero-padded [b, ld] fp32 (vq_ingest_rows on the queries)."""
+        b, dim = queries.shape
+        with torch.cuda.device(self.device):
+            out = torch.empty((b, ld), dtype=torch.float32, device=self.device)
+            _lib.check(self.lib.vq_ingest_rows(_ptr(queries), b, dim, dim, _ptr(out), _lib.F32, ld, norm,
+                                               _stream(self.device)), "vq_ingest_rows")
+            self.last_launches += 1
+        return out
+
+    def merge(self, scores: torch.Tensor, rows: torch.Tensor, offsets, k_out: int):
+        """scores/rows: [g, b, k_in]; offsets: int64 [g] device tensor or None → ([b,k] f32, [b,k] i64)."""
+        g, b, k_in = scores.shape
+        with torch.cuda.device(self.device):
+            out_s = torch.empty((b, k_out), dtype=torch.float32, device=self.device)
+            out_r = torch.empty((b, k_out), dtype=torch.int64, device=self.device)
+            rc = self.lib.vq_topk_merge(_ptr(scores.contiguous()), _ptr(rows.contiguous()), g, b, k_in,
+                                        _ptr(offsets), k_out, _ptr(out_s), _ptr(out_r), _stream(self.device))
+            _lib.check(rc, "vq_topk_merge")
+        return out_s, out_r
+
+
+def as_device_queries(q, dim: int, device) -> torch.Tensor:
+    """Accept numpy / torch, 1-D or 2-D, any float dtype → [b, dim] fp32 device tensor."""
+    if isinstance(q, np.ndarray):
+        t = torch.from_numpy(np.ascontiguousarray(q, dtype=np.float32))
+    elif isinstance(q, torch.Tensor):
+        t = q.detach().to(torch.float32)
+    else:
+        t = torch.from_numpy(np.ascontiguousarray(np.asarray(q), dtype=np.float32))
+    if t.dim() == 1:
+        t = t[None, :]
+    if t.dim() != 2 or t.shape[1] != dim:
+        raise ValueError(f"query shape {tuple(t.shape)} does not match dimension {dim}")
+    return t.to(device).contiguous()

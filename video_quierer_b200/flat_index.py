@@ -1,0 +1,256 @@
+"""B200FlatIndex — drop-in for the reference's live exact index,
+``SimpleVideoIndex`` (reference video_search_overhaul.py:23-106).
+
+Same attribute surface (`embeddings`, `metadata`, `video_hashes`), same methods
+(`add_frame`, `search`, `save_to_disk`, `load_from_disk`), same result dicts and error
+conventions (empty index → ``[]``; k > N → N hits; save/load swallow errors and return a
+bool).  What changes is the engine: the per-query ``np.vstack`` + ``np.dot`` + ``np.argsort``
+(:46-56) becomes one `vq_scan_topk` launch over a device-resident matrix.
+
+The route handlers of the reference reach *through* the index and mutate
+``index.embeddings`` / ``index.metadata`` directly (``pop(i)``, rebind to ``[]``, ``len``;
+src/api/routes.py:754-762,979-981,1014-1016), so `embeddings` is a list subclass that
+records mutations; the device matrix is re-synchronised lazily before the next search
+(append-only changes upload only the new rows).
+"""
+
+from __future__ import annotations
+
+import logging
+import pickle
+import threading
+from pathlib import Path
+from typing import Dict, List
+
+import numpy as np
+import torch
+
+from . import _lib
+from .engine import DeviceStore, Scanner, _require_cuda, as_device_queries
+
+logger = logging.getLogger(__name__)
+
+
+class EmbeddingList(list):
+    """`list` of per-frame float32 arrays that remembers how far the device copy is valid."""
+
+    def __init__(self, *a):
+        super().__init__(*a)
+        self.valid_prefix = 0          # rows [0, valid_prefix) are unchanged since the last sync
+
+    def _touch(self, i: int):
+        n = len(self)
+        if i < 0:
+            i += n
+        self.valid_prefix = max(0, min(self.valid_prefix, i))
+
+    def pop(self, i=-1):
+        self._touch(i if i >= 0 else len(self) + i)
+        return super().pop(i)
+
+    def __delitem__(self, i):
+        self._touch(0 if isinstance(i, slice) else i)
+        super().__delitem__(i)
+
+    def __setitem__(self, i, v):
+        self._touch(0 if isinstance(i, slice) else i)
+        super().__setitem__(i, v)
+
+    def insert(self, i, v):
+        self._touch(i)
+        super().insert(i, v)
+
+    def remove(self, v):
+        self.valid_prefix = 0
+        super().remove(v)
+
+    def clear(self):
+        self.valid_prefix = 0
+        super().clear()
+
+    def sort(self, *a, **k):
+        self.valid_prefix = 0
+        super().sort(*a, **k)
+
+    def reverse(self):
+        self.valid_prefix = 0
+        super().reverse()
+
+    def __iadd__(self, other):
+        super().extend(other)
+        return self
+    # append / extend only add rows past valid_prefix → nothing to record
+
+
+class B200FlatIndex:
+    """Exact cosine search over a device-resident frame-embedding matrix."""
+
+    def __init__(self, device=None, store_dtype: str = "fp32", rescore: bool = True, path: str = "auto"):
+        """store_dtype 'fp32' = parity mode (scores within 1e-5 of the reference);
+        'bf16' = throughput mode: bf16 scan picks candidates, and with `rescore` they are
+        re-scored exactly from an fp32 shadow copy before the final top-k."""
+        self._embeddings = EmbeddingList()
+        self.metadata: List[Dict] = []
+        self.video_hashes: Dict = {}
+        self.device = _require_cuda(device)
+        self.store_dtype = "bf16" if store_dtype in ("bf16", "bfloat16") else "fp32"
+        self.rescore = bool(rescore)
+        self.path = path
+        self._store: DeviceStore | None = None
+        self._scanner = Scanner(self.device)
+        self._lock = threading.RLock()
+        self.search_times: List[float] = []
+
+    # ------------------------------------------------------------------ attribute surface
+    @property
+    def embeddings(self) -> EmbeddingList:
+        return self._embeddings
+
+    @embeddings.setter
+    def embeddings(self, value):
+        # handlers rebind the attribute: `system.index.embeddings = []` (routes.py:979,1014)
+        with self._lock:
+            self._embeddings = value if isinstance(value, EmbeddingList) else EmbeddingList(value)
+            self._embeddings.valid_prefix = 0
+
+    # ------------------------------------------------------------------ ingest
+    def add_frame(self, embedding: np.ndarray, video_name: str, timestamp: float):
+        """video_search_overhaul.py:31-38."""
+        self._embeddings.append(np.asarray(embedding).astype(np.float32))
+        self.metadata.append({
+            'video_name': video_name,
+            'timestamp': timestamp,
+            'frame_id': len(self._embeddings) - 1,
+        })
+
+    def add_frames(self, embeddings: np.ndarray, video_names, timestamps):
+        """Bulk form of `add_frame` (same bookkeeping, one upload)."""
+        embeddings = np.asarray(embeddings, dtype=np.float32)
+        base = len(self._embeddings)
+        self._embeddings.extend(list(embeddings))
+        for i, (vn, ts) in enumerate(zip(video_names, timestamps)):
+            self.metadata.append({'video_name': vn, 'timestamp': ts, 'frame_id': base + i})
+
+    def _sync(self):
+        emb = self._embeddings
+        n = len(emb)
+        if n == 0:
+            if self._store is not None:
+                self._store.truncate(0)
+            emb.valid_prefix = 0
+            return
+        dim = int(np.asarray(emb[0]).shape[-1])
+        if self._store is None or self._store.dim != dim:
+            bf = self.store_dtype == "bf16"
+            self._store = DeviceStore(dim, self.device, keep_fp32=(not bf) or self.rescore, keep_bf16=bf)
+            emb.valid_prefix = 0
+        st = self._store
+        keep = min(emb.valid_prefix, st.n, n)
+        if keep == n and st.n == n:
+            return
+        st.truncate(keep)
+        chunk = 1 << 16
+        for s in range(keep, n, chunk):
+            e = min(n, s + chunk)
+            st.append(np.stack(emb[s:e]).astype(np.float32, copy=False), _lib.NORM_NONE)
+        emb.valid_prefix = n
+
+    # ------------------------------------------------------------------ search
+    def _search_device(self, q_dev: torch.Tensor, k: int):
+        st = self._store
+        if self.store_dtype == "bf16":
+            if self.rescore:
+                kc = min(st.n, max(2 * k, k + 22))
+                _, cand = self._scanner.scan(st.bf16, st.n, st.dim, q_dev, kc, _lib.NORM_EPS, self.path)
+                launches = self._scanner.last_launches
+                qn = self._scanner.normalise_padded(q_dev, st.ld, _lib.NORM_EPS)
+                out = self._scanner.rescore(st.f32, st.n, st.dim, qn, cand, k)
+                self._scanner.last_launches += launches - 0
+                return out
+            return self._scanner.scan(st.bf16, st.n, st.dim, q_dev, k, _lib.NORM_EPS, self.path)
+        return self._scanner.scan(st.f32, st.n, st.dim, q_dev, k, _lib.NORM_EPS, self.path)
+
+    def search_arrays(self, queries, k: int = 5):
+        """Batched search returning ([b,k'] scores float32, [b,k'] rows int32) numpy arrays,
+        k' = min(k, N).  `queries` may be numpy or a torch tensor (host or device)."""
+        with self._lock:
+            self._sync()
+            n = 0 if self._store is None else self._store.n
+            if n == 0:
+                b = 1 if np.ndim(queries) == 1 else len(queries)
+                return np.zeros((b, 0), np.float32), np.zeros((b, 0), np.int32)
+            q = as_device_queries(queries, self._store.dim, self.device)
+            kk = min(int(k), n)
+            s, r = self._search_device(q, kk)
+            return s.cpu().numpy(), r.cpu().numpy()
+
+    def search(self, query_embedding: np.ndarray, k: int = 5) -> List[Dict]:
+        """video_search_overhaul.py:40-64: list of metadata copies + 'score', best first."""
+        if not self._embeddings:
+            return []
+        scores, rows = self.search_arrays(query_embedding, k)
+        results = []
+        for s, r in zip(scores[0], rows[0]):
+            if r < 0:
+                continue
+            md = self.metadata[int(r)].copy()
+            md['score'] = float(s)
+            results.append(md)
+        return results
+
+    def search_batch(self, queries, k: int = 5) -> List[List[Dict]]:
+        """One launch for the whole batch (replaces the per-query loop of routes.py:627-634)."""
+        if not self._embeddings:
+            return [[] for _ in range(len(queries))]
+        scores, rows = self.search_arrays(np.asarray(queries), k)
+        out = []
+        for sb, rb in zip(scores, rows):
+            hits = []
+            for s, r in zip(sb, rb):
+                if r < 0:
+                    continue
+                md = self.metadata[int(r)].copy()
+                md['score'] = float(s)
+                hits.append(md)
+            out.append(hits)
+        return out
+
+    # ------------------------------------------------------------------ persistence
+    def save_to_disk(self, cache_path: Path):
+        """Same pickle as the reference (video_search_overhaul.py:66-85) so caches interchange."""
+        try:
+            cache_data = {
+                'embeddings': [np.asarray(e) for e in self._embeddings],
+                'metadata': self.metadata,
+                'video_hashes': self.video_hashes,
+                'version': '1.0',
+            }
+            with open(cache_path, 'wb') as f:
+                pickle.dump(cache_data, f)
+            logger.info("Saved %d embeddings to %s", len(self._embeddings), cache_path)
+            return True
+        except Exception as e:  # noqa: BLE001 — the reference swallows everything here (:83-85)
+            logger.error("Failed to save cache: %s", e)
+            return False
+
+    def load_from_disk(self, cache_path: Path) -> bool:
+        """video_search_overhaul.py:87-106."""
+        try:
+            cache_path = Path(cache_path)
+            if not cache_path.exists():
+                return False
+            with open(cache_path, 'rb') as f:
+                cache_data = pickle.load(f)
+            self.embeddings = cache_data.get('embeddings', [])
+            self.metadata = cache_data.get('metadata', [])
+            self.video_hashes = cache_data.get('video_hashes', {})
+            logger.info("Loaded %d embeddings from %s", len(self._embeddings), cache_path)
+            return True
+        except Exception as e:  # noqa: BLE001 — (:104-106)
+            logger.error("Failed to load cache: %s", e)
+            return False
+
+    # ------------------------------------------------------------------ introspection
+    @property
+    def last_scan_path(self) -> str:
+        return self._scanner.last_path
