@@ -58,6 +58,11 @@ const char* vq_last_error(void);
  * many kernels it launched (for bench.py's gpu_launches accounting). */
 const char* vq_last_scan_path(void);
 int         vq_last_launch_count(void);
+/* Roofline instrumentation: when enabled, vq_scan_topk / vq_hnsw_search bracket their dominant
+ * kernel with CUDA events on the launch stream; vq_profile_last_kernel_ms() waits for the end
+ * event and returns that kernel's device time in ms (negative if none was recorded). */
+int         vq_profile_enable(int on);
+float       vq_profile_last_kernel_ms(void);
 
 /* (a) L2-normalisation of embeddings, in place.                       [kernel: l2norm_rows]
  * Replaces: `embedding / embedding.norm()` video_search_overhaul.py:226,289;
@@ -89,10 +94,12 @@ int vq_scan_topk(const void* store, int64_t n, int dim, int ld, int store_dtype,
 
 /* Merge g candidate lists per query into one global top-k_out.        [kernel: topk_merge]
  * New (the reference is single-process); this is the shard/merge layer of SURVEY.md §8(e).
- *   scores/rows  [g, b, k_in] (fp32 / int32, local row numbers, row < 0 = empty slot)
+ *   scores/rows  [g, b, k_in] (fp32 / int32, local row numbers, row < 0 = empty slot);
+ *                consecutive shards are g_stride elements apart (0 = dense, b*k_in), so one
+ *                packed all-gather buffer [g][scores|rows] can be merged in place
  *   shard_offsets[g] int64 added to local rows (may be NULL = all zero)
  *   out_scores   [b, k_out] fp32, out_rows [b, k_out] int64 (global rows) */
-int vq_topk_merge(const float* scores, const int32_t* rows, int g, int b, int k_in,
+int vq_topk_merge(const float* scores, const int32_t* rows, int g, int64_t g_stride, int b, int k_in,
                   const int64_t* shard_offsets, int k_out,
                   float* out_scores, int64_t* out_rows, void* stream);
 

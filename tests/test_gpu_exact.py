@@ -1,0 +1,179 @@
+"""GPU parity tests of the exact path, through the C-ABI (ctypes) and the drop-in facade,
+against the oracle and the golden outputs of the unmodified reference."""
+import numpy as np
+import pytest
+
+from oracle import compare, exact
+from video_quierer_b200.utils import synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def eng(built_lib):
+    import torch
+    from video_quierer_b200 import _lib, engine
+    return engine, _lib, torch
+
+
+def _scan(eng, store_np, queries_np, k, dtype="fp32", path="fma", norm=None):
+    engine, _lib, torch = eng
+    st = engine.DeviceStore(store_np.shape[1], keep_fp32=True, keep_bf16=(dtype == "bf16"))
+    st.append(store_np)
+    sc = engine.Scanner()
+    q = engine.as_device_queries(queries_np, store_np.shape[1], st.device)
+    s, r = sc.scan(st.view(dtype), st.n, st.dim, q, k, _lib.NORM_EPS if norm is None else norm, path)
+    torch.cuda.synchronize()
+    return s.cpu().numpy(), r.cpu().numpy(), sc
+
+
+def test_golden_small_all_k(eng, golden):
+    g = golden("exact_small.npz")
+    store = g["store_f16"].astype(np.float32)
+    queries = g["queries_f16"].astype(np.float32)
+    for k in (1, 10, 50):
+        s, r, _ = _scan(eng, store, queries, k)
+        assert compare.check_topk_batch(r, s, g[f"rows_k{k}"], g[f"scores_k{k}"]) == []
+        assert compare.id_match_fraction(r, g[f"rows_k{k}"]) == 1.0   # no ties in this fixture
+
+
+@pytest.mark.parametrize("b", [1, 2, 3, 5, 8, 13, 16, 17, 32, 40])
+def test_batch_sizes_vs_oracle(eng, b):
+    store = synth.gauss(5000, 512, seed=3)
+    queries = np.random.default_rng(4).standard_normal((b, 512), dtype=np.float32)
+    s, r, sc = _scan(eng, store, queries, 10)
+    ro, so = exact.exact_search_batch(store, queries, 10)
+    assert compare.check_topk_batch(r, s, ro, so) == []
+    assert sc.last_path == "scan_fma_f32" and sc.last_launches >= 3
+
+
+@pytest.mark.parametrize("n,dim", [(1, 512), (3, 64), (127, 128), (128, 768), (129, 96), (4097, 512), (10001, 100)])
+def test_ragged_shapes(eng, n, dim):
+    store = synth.gauss(n, dim, seed=5)
+    queries = np.random.default_rng(6).standard_normal((4, dim), dtype=np.float32)
+    k = min(10, n)
+    s, r, _ = _scan(eng, store, queries, k)
+    ro, so = exact.exact_search_batch(store, queries, k)
+    assert compare.check_topk_batch(r, s, ro, so) == []
+
+
+def test_c1_full_config_golden(eng, golden):
+    """BASELINE config 1 against the reference's own outputs."""
+    g = golden("exact_c1.npz")
+    store = synth.gauss(10000, 512, seed=synth.STORE_SEED)
+    queries = np.random.default_rng(synth.QUERY_SEED).standard_normal((100, 512), dtype=np.float32)
+    assert synth.sha256_of(store) == str(g["store_sha"])
+    s, r, _ = _scan(eng, store, queries, 10)
+    assert compare.check_topk_batch(r, s, g["rows"], g["scores"]) == []
+    assert compare.id_match_fraction(r, g["rows"]) == 1.0
+    assert np.max(np.abs(s - g["scores"]) / np.abs(g["scores"])) < 1e-5
+
+
+def test_k100_and_large_k(eng):
+    store = synth.clip_like(20000, 256, seed=7)
+    queries = synth.clip_like(9, 256, seed=8, n_store=20000)
+    for k in (100, 257, 1024):
+        s, r, _ = _scan(eng, store, queries, k)
+        ro, so = exact.exact_search_batch(store, queries, k)
+        assert compare.check_topk_batch(r, s, ro, so) == []
+
+
+def test_ties_deterministic_rule(eng):
+    store = synth.with_ties(4000, 128, seed=9)
+    queries = store[[10, 200, 3999]] + 0.0
+    s, r, _ = _scan(eng, store, queries, 20)
+    ro, so = exact.exact_search_batch(store, queries, 20)
+    assert compare.check_topk_batch(r, s, ro, so) == []
+    # engine rule: equal scores are listed by ascending row
+    for b in range(len(r)):
+        for i in range(19):
+            if s[b, i] == s[b, i + 1]:
+                assert r[b, i] < r[b, i + 1]
+
+
+def test_zero_query_and_k_gt_n(eng):
+    store = synth.gauss(7, 64, seed=10)
+    s, r, _ = _scan(eng, store, np.zeros((1, 64), np.float32), 5)
+    assert np.all(s == 0.0) and list(r[0]) == [0, 1, 2, 3, 4]
+    s, r, _ = _scan(eng, store, store[:2], 50)
+    assert np.all(r[:, :7] >= 0) and np.all(r[:, 7:] == -1)
+
+
+def test_bf16_store_scan_matches_bf16_oracle(eng):
+    """bf16 store, fp32 accumulate: exactly the oracle run on the bf16-rounded rows."""
+    _, _, torch = eng
+    store = synth.clip_like(6000, 512, seed=11)
+    queries = synth.clip_like(6, 512, seed=12, n_store=6000)
+    s, r, sc = _scan(eng, store, queries, 10, dtype="bf16")
+    rounded = torch.from_numpy(store).to(torch.bfloat16).to(torch.float32).numpy()
+    ro, so = exact.exact_search_batch(rounded, queries, 10)
+    assert compare.check_topk_batch(r, s, ro, so) == []
+    assert sc.last_path == "scan_fma_bf16"
+
+
+def test_linearity_property_full_size(eng):
+    """Size-independent property at a BASELINE-scale store: score(q1+q2-normalised) ordering is
+    consistent with an independent recomputation of the returned rows on the host."""
+    n = 200_000
+    store = synth.gauss(n, 512, seed=13)
+    queries = np.random.default_rng(14).standard_normal((3, 512), dtype=np.float32)
+    s, r, _ = _scan(eng, store, queries, 10)
+    qn = queries / (np.linalg.norm(queries, axis=1, keepdims=True) + 1e-10)
+    for b in range(3):
+        host = store[r[b]].astype(np.float64) @ qn[b].astype(np.float64)
+        assert np.allclose(host, s[b], rtol=1e-5, atol=1e-7)
+        assert np.all(np.diff(s[b]) <= 0)
+        # nothing outside the returned set beats the k-th score
+        full = store @ qn[b]
+        assert np.sum(full > s[b, -1] + 1e-6) <= 9
+
+
+def test_facade_matches_reference_dicts(eng, golden):
+    from video_quierer_b200.flat_index import B200FlatIndex
+    g = golden("exact_small.npz")
+    store = g["store_f16"].astype(np.float32)
+    queries = g["queries_f16"].astype(np.float32)
+    idx = B200FlatIndex()
+    assert idx.search(queries[0], 5) == []
+    for i, x in enumerate(store):
+        idx.add_frame(x, f"v{i % 7}.mp4", float(i) * 0.5)
+    res = idx.search(queries[1], 3)
+    assert sorted(res[0].keys()) == list(g["dict_keys"])
+    assert [[x["frame_id"], x["timestamp"]] for x in res] == g["dict_example"].tolist()
+    assert [x["video_name"] for x in res] == list(g["dict_video"])
+    assert isinstance(res[0]["score"], float)
+    # batch = the /api/search/batch loop, one launch
+    batch = idx.search_batch(queries[:8], 10)
+    assert [[h["frame_id"] for h in hits] for hits in batch] == g["rows_k10"][:8].tolist()
+    # mutation through the attribute surface the route handlers use
+    idx.embeddings.pop(int(g["rows_k10"][0][0])); idx.metadata.pop(int(g["rows_k10"][0][0]))
+    res2 = idx.search(queries[0], 1)
+    assert res2[0]["frame_id"] == int(g["rows_k10"][0][1])
+    idx.embeddings = []; idx.metadata = []
+    assert idx.search(queries[0], 5) == []
+
+
+def test_facade_save_load_roundtrip(eng, tmp_path):
+    from video_quierer_b200.flat_index import B200FlatIndex
+    store = synth.gauss(300, 64, seed=15)
+    a = B200FlatIndex()
+    a.add_frames(store, ["a.mp4"] * 300, [float(i) for i in range(300)])
+    a.video_hashes["a.mp4"] = "h"
+    p = tmp_path / "video_search_cache.pkl"
+    assert a.save_to_disk(p) is True
+    b = B200FlatIndex()
+    assert b.load_from_disk(p) is True and b.video_hashes == {"a.mp4": "h"}
+    assert b.load_from_disk(tmp_path / "missing.pkl") is False
+    q = store[17]
+    assert [h["frame_id"] for h in a.search(q, 5)] == [h["frame_id"] for h in b.search(q, 5)]
+
+
+def test_bf16_two_stage_rescore_is_exact(eng):
+    from video_quierer_b200.flat_index import B200FlatIndex
+    store = synth.clip_like(8000, 512, seed=16)
+    queries = synth.clip_like(5, 512, seed=17, n_store=8000)
+    idx = B200FlatIndex(store_dtype="bf16", rescore=True)
+    idx.add_frames(store, ["a.mp4"] * len(store), np.arange(len(store), dtype=float))
+    s, r = idx.search_arrays(queries, 10)
+    ro, so = exact.exact_search_batch(store, queries, 10)
+    assert compare.check_topk_batch(r, s, ro, so) == []

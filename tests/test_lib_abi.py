@@ -1,0 +1,51 @@
+"""CPU-only: the C-ABI library builds, loads and exports every symbol include/vq_search.h declares."""
+import ctypes
+import os
+import re
+
+from video_quierer_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    hdr = open(os.path.join(ROOT, "include", "vq_search.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    return sorted(set(re.findall(r"\b(vq_[a-z0-9_]+)\s*\(", hdr)))
+
+
+def test_header_symbols_exported(built_lib):
+    names = _declared_symbols()
+    assert len(names) >= 12
+    lib = ctypes.CDLL(built_lib)
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in vq_search.h but not exported"
+
+
+def test_binding_covers_header(built_lib):
+    assert sorted(_lib.SIGNATURES) == _declared_symbols()
+    lib = _lib.load()
+    assert lib.vq_abi_version() == 1
+    assert isinstance(lib.vq_last_error(), bytes)
+
+
+def test_argument_validation_without_gpu(built_lib):
+    """Argument errors are reported before any CUDA call, so they are testable on CPU."""
+    lib = _lib.load()
+    rc = lib.vq_scan_topk(None, 10, 512, 500, 0, None, 1, 10, 1, None, None, None, 0, 0, None)
+    assert rc == -1 and b"ld" in lib.vq_last_error()
+    rc = lib.vq_scan_topk(None, 10, 512, 512, 7, None, 1, 10, 1, None, None, None, 0, 0, None)
+    assert rc == -1 and b"store_dtype" in lib.vq_last_error()
+    rc = lib.vq_scan_topk(None, 10, 512, 512, 0, None, 1, 0, 1, None, None, None, 0, 0, None)
+    assert rc == -1
+    assert lib.vq_scan_workspace_bytes(1000000, 512, 512, 0, 32, 10, 0) > 0
+
+
+def test_no_product_import_of_oracle():
+    """The product package must never import the oracle (it is test infrastructure)."""
+    pkg = os.path.join(ROOT, "video_quierer_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f

@@ -28,7 +28,9 @@ SIGNATURES = {
     "vq_ingest_rows": (_i32, [_vp, _i64, _i32, _i32, _vp, _i32, _i32, _i32, _vp]),
     "vq_scan_workspace_bytes": (_sz, [_i64, _i32, _i32, _i32, _i32, _i32, _i32]),
     "vq_scan_topk": (_i32, [_vp, _i64, _i32, _i32, _i32, _vp, _i32, _i32, _i32, _vp, _vp, _vp, _sz, _i32, _vp]),
-    "vq_topk_merge": (_i32, [_vp, _vp, _i32, _i32, _i32, _vp, _i32, _vp, _vp, _vp]),
+    "vq_topk_merge": (_i32, [_vp, _vp, _i32, _i64, _i32, _i32, _vp, _i32, _vp, _vp, _vp]),
+    "vq_profile_enable": (_i32, [_i32]),
+    "vq_profile_last_kernel_ms": (C.c_float, []),
     "vq_rescore_topk": (_i32, [_vp, _i64, _i32, _i32, _vp, _i32, _vp, _i32, _i32, _vp, _vp, _vp]),
     "vq_hnsw_workspace_bytes": (_sz, [_i32, _i32, _i32]),
     "vq_hnsw_search": (_i32, [_vp, _i64, _i32, _i32, _i32, _vp, _vp, _i32, _vp, _vp, _i32, _i32, _i32, _i32,

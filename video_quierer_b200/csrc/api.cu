@@ -10,7 +10,7 @@ size_t vq_scan_fma_smem(int bt, int ld, int k);
 int vq_scan_fma_grid(int n, int bt);
 int vq_scan_fma_launch(const void* store, int n, int ld, int store_dtype, const float* q, int bt, int k,
                        float* part_scores, int* part_rows, int grid, cudaStream_t stream);
-int vq_topk_merge_launch(const float* scores, const int* rows, int g, int b_stride, int b_out, int k_in,
+int vq_topk_merge_launch(const float* scores, const int* rows, int g, long long g_stride, int b_out, int k_in,
                          const long long* offsets, int k_out, float* out_scores, void* out_rows,
                          int rows64, int negate_out, cudaStream_t stream);
 int vq_ingest_launch(const float* src, long long rows, int dim, int src_ld, void* dst, int dst_dtype,
@@ -38,6 +38,22 @@ void vq_set_error(const char* fmt, ...) {
 void vq_note_launch(const char* path, int launches) {
     if (path) { strncpy(g_path, path, sizeof(g_path) - 1); g_path[sizeof(g_path) - 1] = 0; }
     g_launches = launches;
+}
+
+// ---- roofline instrumentation (events around the dominant kernel of the last call)
+static thread_local bool g_prof_on = false;
+static thread_local cudaEvent_t g_ev0 = nullptr, g_ev1 = nullptr;
+static thread_local bool g_ev_valid = false;
+void vq_prof_begin(cudaStream_t s) {
+    if (!g_prof_on) return;
+    if (!g_ev0) { cudaEventCreate(&g_ev0); cudaEventCreate(&g_ev1); }
+    cudaEventRecord(g_ev0, s);
+    g_ev_valid = false;
+}
+void vq_prof_end(cudaStream_t s) {
+    if (!g_prof_on || !g_ev0) return;
+    cudaEventRecord(g_ev1, s);
+    g_ev_valid = true;
 }
 
 int vq_num_sms() {
@@ -87,6 +103,15 @@ int vq_abi_version(void) { return VQ_ABI_VERSION; }
 const char* vq_last_error(void) { return g_err; }
 const char* vq_last_scan_path(void) { return g_path; }
 int vq_last_launch_count(void) { return g_launches; }
+
+int vq_profile_enable(int on) { g_prof_on = on != 0; return VQ_OK; }
+float vq_profile_last_kernel_ms(void) {
+    if (!g_ev_valid) return -1.f;
+    float ms = -1.f;
+    if (cudaEventSynchronize(g_ev1) != cudaSuccess) return -1.f;
+    if (cudaEventElapsedTime(&ms, g_ev0, g_ev1) != cudaSuccess) return -1.f;
+    return ms;
+}
 
 int vq_l2_normalize(float* x, int64_t rows, int dim, int ld, int eps_mode, void* stream) {
     VQ_CHECK_ARG(x != nullptr || rows == 0, "x is NULL");
@@ -184,9 +209,11 @@ int vq_scan_topk(const void* store, int64_t n, int dim, int ld, int store_dtype,
         const int left = b - q0;
         if (left < bt) bt = pow2_at_least(left);            // padded queries are all-zero rows of qn
         const int grid = vq_scan_fma_grid((int)n, bt);
+        if (q0 == 0) vq_prof_begin(stream);
         rc = vq_scan_fma_launch(store, (int)n, ld, store_dtype, qn + (size_t)q0 * ld, bt, k, part_s, part_r, grid, stream);
+        if (q0 == 0) vq_prof_end(stream);
         if (rc) return rc;
-        rc = vq_topk_merge_launch(part_s, part_r, grid, bt, left < bt ? left : bt, k, nullptr, k,
+        rc = vq_topk_merge_launch(part_s, part_r, grid, (long long)bt * k, left < bt ? left : bt, k, nullptr, k,
                                   out_scores + (size_t)q0 * k, out_rows + (size_t)q0 * k, 0, 0, stream);
         if (rc) return rc;
         launches += 2;
@@ -195,12 +222,14 @@ int vq_scan_topk(const void* store, int64_t n, int dim, int ld, int store_dtype,
     return VQ_OK;
 }
 
-int vq_topk_merge(const float* scores, const int32_t* rows, int g, int b, int k_in, const int64_t* shard_offsets,
-                  int k_out, float* out_scores, int64_t* out_rows, void* stream) {
+int vq_topk_merge(const float* scores, const int32_t* rows, int g, int64_t g_stride, int b, int k_in,
+                  const int64_t* shard_offsets, int k_out, float* out_scores, int64_t* out_rows, void* stream) {
+    if (g_stride == 0) g_stride = (int64_t)b * k_in;
+    VQ_CHECK_ARG(g_stride >= (int64_t)b * k_in, "g_stride %lld < b*k_in", (long long)g_stride);
     VQ_CHECK_ARG(g > 0 && b >= 0 && k_in > 0 && k_out > 0 && k_out <= 1024, "bad shape g=%d b=%d k_in=%d k_out=%d", g, b, k_in, k_out);
     if (b == 0) return VQ_OK;
     VQ_CHECK_ARG(scores && rows && out_scores && out_rows, "NULL pointer argument");
-    const int rc = vq_topk_merge_launch(scores, rows, g, b, b, k_in, (const long long*)shard_offsets, k_out, out_scores,
+    const int rc = vq_topk_merge_launch(scores, rows, g, (long long)g_stride, b, k_in, (const long long*)shard_offsets, k_out, out_scores,
                                         out_rows, 1, 0, (cudaStream_t)stream);
     vq_note_launch("topk_merge", 1);
     return rc;
@@ -219,7 +248,7 @@ int vq_rescore_topk(const float* store_f32, int64_t n, int dim, int ld, const fl
     VQ_CUDA(cudaMallocAsync((void**)&tmp, (size_t)b * k_cand * 4, stream));
     rc = vq_rescore_launch(store_f32, ld, queries, ld, cand_rows, b, k_cand, tmp, stream);
     if (rc == VQ_OK)
-        rc = vq_topk_merge_launch(tmp, cand_rows, 1, b, b, k_cand, nullptr, k, out_scores, out_rows, 0, 0, stream);
+        rc = vq_topk_merge_launch(tmp, cand_rows, 1, (long long)b * k_cand, b, k_cand, nullptr, k, out_scores, out_rows, 0, 0, stream);
     cudaFreeAsync(tmp, stream);
     vq_note_launch("rescore_rows", 2);
     return rc;

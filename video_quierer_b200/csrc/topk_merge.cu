@@ -12,7 +12,7 @@ constexpr int kWarps = kThreads / 32;
 // scores/rows: [g, b, k_in]; one CTA per query.
 template <typename OutRow>
 __global__ void __launch_bounds__(kThreads)
-topk_merge_kernel(const float* __restrict__ scores, const int* __restrict__ rows, int g, int b /*query stride*/, int k_in,
+topk_merge_kernel(const float* __restrict__ scores, const int* __restrict__ rows, int g, long long gs /*shard stride*/, int k_in,
                   const long long* __restrict__ offsets, int k_out,
                   float* __restrict__ out_scores, OutRow* __restrict__ out_rows, int negate_out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -31,7 +31,7 @@ topk_merge_kernel(const float* __restrict__ scores, const int* __restrict__ rows
     // only when offsets are absent; with offsets we compare true global rows.
     auto cand_row = [&](int c) -> long long {
         const int sh = c / k_in, j = c - sh * k_in;
-        const int r = rows[((size_t)sh * b + q) * k_in + j];
+        const int r = rows[(size_t)sh * gs + (size_t)q * k_in + j];
         if (r < 0) return -1;
         return (long long)r + (offsets ? offsets[sh] : 0);
     };
@@ -46,7 +46,7 @@ topk_merge_kernel(const float* __restrict__ scores, const int* __restrict__ rows
         long long r = -1;
         if (c < total) {
             const int sh = c / k_in, j = c - sh * k_in;
-            const size_t at = ((size_t)sh * b + q) * k_in + j;
+            const size_t at = (size_t)sh * gs + (size_t)q * k_in + j;
             const int lr_ = rows[at];
             if (lr_ >= 0) { s = scores[at]; r = (long long)lr_ + (offsets ? offsets[sh] : 0); }
         }
@@ -121,16 +121,22 @@ topk_merge_kernel(const float* __restrict__ scores, const int* __restrict__ rows
 
 }  // namespace
 
-// b_stride: number of queries per list block in the input; b_out (<= b_stride) queries are merged.
-int vq_topk_merge_launch(const float* scores, const int* rows, int g, int b_stride, int b_out, int k_in,
+// g_stride: elements between consecutive candidate blocks (>= b_out*k_in); b_out queries are merged.
+int vq_topk_merge_launch(const float* scores, const int* rows, int g, long long g_stride, int b_out, int k_in,
                          const long long* offsets, int k_out, float* out_scores, void* out_rows,
                          int rows64, int negate_out, cudaStream_t stream) {
-    const int b = b_stride;
+    const long long b = g_stride;
     if (b_out <= 0) return VQ_OK;
     const size_t smem = (size_t)kWarps * k_out * 8;
-    if (smem > 48 * 1024) {
+    if (smem > 96 * 1024) {
         vq_set_error("topk_merge: k_out=%d too large", k_out);
         return VQ_EUNSUPPORTED;
+    }
+    static bool attr_done = false;
+    if (!attr_done) {
+        VQ_CUDA(cudaFuncSetAttribute(topk_merge_kernel<long long>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+        VQ_CUDA(cudaFuncSetAttribute(topk_merge_kernel<int>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+        attr_done = true;
     }
     if (rows64)
         topk_merge_kernel<long long><<<b_out, kThreads, smem, stream>>>(scores, rows, g, b, k_in, offsets, k_out,

@@ -42,6 +42,8 @@ void vq_note_launch(const char* path_or_null, int launches);
     } while (0)
 
 int vq_num_sms();
+void vq_prof_begin(cudaStream_t s);
+void vq_prof_end(cudaStream_t s);
 
 // ----------------------------------------------------------------------------- device utils
 // Total order of the engine: higher score first, then lower row.  NaN never beats anything.

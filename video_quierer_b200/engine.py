@@ -191,13 +191,14 @@ class Scanner:
             self.last_launches += 1
         return out
 
-    def merge(self, scores: torch.Tensor, rows: torch.Tensor, offsets, k_out: int):
-        """scores/rows: [g, b, k_in]; offsets: int64 [g] device tensor or None → ([b,k] f32, [b,k] i64)."""
+    def merge(self, scores: torch.Tensor, rows: torch.Tensor, offsets, k_out: int, g_stride: int = 0):
+        """scores/rows: [g, b, k_in] views whose shard stride is `g_stride` elements (0 = dense);
+        offsets: int64 [g] device tensor or None → ([b,k] f32, [b,k] i64)."""
         g, b, k_in = scores.shape
         with torch.cuda.device(self.device):
             out_s = torch.empty((b, k_out), dtype=torch.float32, device=self.device)
             out_r = torch.empty((b, k_out), dtype=torch.int64, device=self.device)
-            rc = self.lib.vq_topk_merge(_ptr(scores.contiguous()), _ptr(rows.contiguous()), g, b, k_in,
+            rc = self.lib.vq_topk_merge(_ptr(scores), _ptr(rows), g, g_stride, b, k_in,
                                         _ptr(offsets), k_out, _ptr(out_s), _ptr(out_r), _stream(self.device))
             _lib.check(rc, "vq_topk_merge")
         return out_s, out_r

@@ -1,0 +1,84 @@
+"""Shard/merge layer — one process per GPU over torch.distributed.
+
+The frame-embedding store is row-sharded: rank r owns the contiguous rows
+``[r*ceil(N/G), min(N, (r+1)*ceil(N/G)))``.  A search is
+  1. every rank scans its shard for a local top-k   (vq_scan_topk / vq_hnsw_search),
+  2. ONE all-gather of the packed ``[scores | rows]`` candidate block (8*b*k bytes per rank,
+     latency-bound on NVSwitch),
+  3. an on-device merge ``g*k -> k`` that adds the shard offsets (vq_topk_merge reads the
+     packed gather buffer in place through its shard stride).
+The reference has no counterpart (single process).  The collective plumbing is independent of
+CUDA so that it can be exercised with the gloo backend on CPU: `local_search` and `merge` are
+injectable; the defaults are the CUDA kernels and raise if no GPU is present.
+"""
+
+from __future__ import annotations
+
+from typing import Callable, Optional
+
+import torch
+import torch.distributed as dist
+
+
+def shard_range(n_total: int, world: int, rank: int):
+    """Contiguous row range of `rank`."""
+    per = -(-n_total // world) if world > 0 else n_total
+    lo = min(n_total, rank * per)
+    hi = min(n_total, (rank + 1) * per)
+    return lo, hi
+
+
+def shard_offsets(n_total: int, world: int):
+    return [shard_range(n_total, world, r)[0] for r in range(world)]
+
+
+def pack_candidates(scores: torch.Tensor, rows: torch.Tensor) -> torch.Tensor:
+    """[b,k] fp32 + [b,k] int32 → one int32 buffer [2, b, k] (scores bit-cast)."""
+    return torch.stack((scores.contiguous().view(torch.int32), rows.contiguous().to(torch.int32)), dim=0)
+
+
+class ShardedSearcher:
+    """Row-sharded exact/ANN search across the ranks of a process group."""
+
+    def __init__(self, local_search: Callable, n_total: int, group=None,
+                 merge: Optional[Callable] = None, device=None):
+        """local_search(queries[b,dim], k) -> (scores [b,k] fp32, rows [b,k] int32) on this
+        rank's shard (local row numbers, -1 = empty slot)."""
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.n_total = int(n_total)
+        self.local_search = local_search
+        self.device = device
+        self._merge = merge
+        self._offsets = None
+        self._scanner = None
+        self._gather_buf = None
+
+    # default merge = the CUDA kernel, reading the packed gather buffer in place
+    def _cuda_merge(self, gathered: torch.Tensor, k_out: int):
+        from .engine import Scanner
+        if self._scanner is None:
+            self._scanner = Scanner(self.device)
+            self._offsets = torch.tensor(shard_offsets(self.n_total, self.world), dtype=torch.int64,
+                                         device=gathered.device)
+        g, _, b, k = gathered.shape
+        scores = gathered[:, 0].view(torch.float32)          # [g, b, k] view, shard stride 2*b*k
+        rows = gathered[:, 1]
+        return self._scanner.merge(scores, rows, self._offsets, k_out, g_stride=2 * b * k)
+
+    def search(self, queries: torch.Tensor, k: int):
+        """Returns (scores [b,k] fp32, global rows [b,k] int64), identical on every rank."""
+        s, r = self.local_search(queries, k)
+        packed = pack_candidates(s, r)                        # [2, b, k] int32
+        if self.world == 1:
+            gathered = packed[None]
+        else:
+            shape = (self.world,) + tuple(packed.shape)
+            if self._gather_buf is None or tuple(self._gather_buf.shape) != shape or \
+                    self._gather_buf.device != packed.device:
+                self._gather_buf = torch.empty(shape, dtype=torch.int32, device=packed.device)
+            dist.all_gather_into_tensor(self._gather_buf, packed, group=self.group)
+            gathered = self._gather_buf
+        merge = self._merge or self._cuda_merge
+        return merge(gathered, k)
