@@ -122,8 +122,9 @@ int vq_rescore_topk(const float* store_f32, int64_t n, int dim, int ld,
  *   upper_adj  [slots, m] int32: slot(node, lv) = upper_off[node] + lv - 1
  *   entry / max_level: entry point and its level;  ef = max(ef_search, k) like :264
  *   out_dist   [b, k] fp32 (1 - dot, ascending), out_rows [b, k] int32
- *   out_stats  optional [b, 2] uint32: distance evaluations, expanded nodes (roofline) */
-size_t vq_hnsw_workspace_bytes(int b, int dim, int ef);
+ *   out_stats  optional [b, 4] uint32: distance evaluations, expanded nodes, visited-set
+ *              overflow flag, reserved (feeds the gather-bandwidth roofline) */
+size_t vq_hnsw_workspace_bytes(int b, int ld, int ef);
 int vq_hnsw_search(const void* store, int64_t n, int dim, int ld, int store_dtype,
                    const int32_t* levels, const int32_t* adj0, int m0,
                    const int32_t* upper_off, const int32_t* upper_adj, int m,

@@ -1,17 +1,517 @@
-// placeholder: HNSW kernels land in the next commit
+// (d) HNSW on the GPU: warp-per-query greedy/beam search, and a brute-force layer builder.
+//
+// Search replaces HNSWIndex.search / _search_layer (reference src/indexes/hnsw.py:76-121,
+// 238-280, 488-528).  One warp owns one query:
+//   * the query vector, the result list, the visited set and the neighbour staging buffer all
+//     live in that warp's slice of shared memory;
+//   * the reference's two heaps collapse into ONE list sorted by (distance, id) with an
+//     "expanded" flag per entry: a candidate that has been evicted from the bounded result
+//     heap can only ever terminate the search (its distance is >= the worst kept), so the
+//     next node to expand is simply the first unexpanded entry of the list (same stop rule as
+//     hnsw.py:103 and the same strict admit rule as :113, exact ties aside);
+//   * neighbour ids of the expanded node are read by the first `deg` lanes, filtered through
+//     an exact open-addressing visited set (atomicCAS in shared memory, per-layer reset through
+//     a slot log like the reference's per-layer `visited = set()`), compacted with a ballot, and
+//     their rows gathered 4 at a time: 8 lanes per row, 128-bit `ld.global.nc` loads, 16 loads
+//     in flight per lane, fp32 FMA against the query in shared memory;
+//   * distance evaluations and expansions are counted per query for the gather-bandwidth
+//     roofline (bytes = evals * ld * elem + hops * deg * 4).
+//
+// Build: the reference inserts one node at a time in Python (~10 ms/insert, hnsw.py:150-229).
+// Here a layer is built in three data-parallel steps: exact k-nearest members of every member
+// (the fused scan + top-k kernels), reverse edges appended with atomics, and every list pruned
+// back to the closest m (the batch analogue of :197-223, "closest M" selection of :123-148).
 #include "vq_common.cuh"
+
+int vq_scan_fma_grid(int n, int bt);
+int vq_scan_fma_launch(const void* store, int n, int ld, int store_dtype, const float* q, int bt, int k,
+                       float* part_scores, int* part_rows, int grid, cudaStream_t stream);
+int vq_topk_merge_launch(const float* scores, const int* rows, int g, long long g_stride, int b_out, int k_in,
+                         const long long* offsets, int k_out, float* out_scores, void* out_rows,
+                         int rows64, int negate_out, cudaStream_t stream);
+int vq_ingest_launch(const float* src, long long rows, int dim, int src_ld, void* dst, int dst_dtype,
+                     int dst_ld, int mode, cudaStream_t stream);
+
+namespace {
+
+constexpr unsigned kFull = 0xffffffffu;
+constexpr int kExpanded = 0x40000000;      // flag bit on list ids (node ids are < 2^30)
+constexpr int kLogCap = 1024;              // visited-slot log (per-layer reset without a full clear)
+
+struct WarpState {
+    float* q;        // [ld]
+    float* ld_;      // list distances [ef]
+    int* li;         // list ids (| kExpanded) [ef]
+    int* hash;       // [cap]
+    unsigned short* log;   // [kLogCap]
+    int* nbr;        // [32]
+    float* nd;       // [32]
+};
+
+// ascending (distance, id) insert into a list of `cnt` entries bounded by `cap`; returns new cnt
+__device__ __forceinline__ int list_insert_asc(float* d, int* id, int cnt, int cap, float cd, int cid, int lane) {
+    int pos = 0;
+    for (int base = 0; base < cnt; base += 32) {
+        const int i = base + lane;
+        bool b = false;
+        if (i < cnt) {
+            const float e = d[i];
+            const int eid = id[i] & ~kExpanded;
+            b = (e < cd) || (e == cd && eid < cid);
+        }
+        pos += __popc(__ballot_sync(kFull, b));
+    }
+    if (pos >= cap) return cnt;
+    const int ncnt = cnt < cap ? cnt + 1 : cap;
+    for (int base = ((ncnt - 1) / 32) * 32; base >= 0; base -= 32) {
+        const int i = base + lane;
+        float s = 0.f; int r = 0;
+        const bool mv = (i < ncnt) && (i > pos);
+        if (mv) { s = d[i - 1]; r = id[i - 1]; }
+        __syncwarp();
+        if (mv) { d[i] = s; id[i] = r; }
+        __syncwarp();
+        if (base <= pos) break;
+    }
+    if (lane == 0) { d[pos] = cd; id[pos] = cid; }
+    __syncwarp();
+    return ncnt;
+}
+
+template <bool BF16>
+__device__ __forceinline__ float row_dot_8lanes(const unsigned char* row, const float* q, int ld, int l8) {
+    // 8 lanes cooperate on one row; lane l8 takes the 16-byte pieces l8, l8+8, ...
+    constexpr int EPL = BF16 ? 8 : 4;            // elements per 16-byte load
+    const int steps = ld / (8 * EPL);
+    float acc = 0.f;
+    for (int j0 = 0; j0 < steps; j0 += 4) {
+        uint4 x[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (j0 + u < steps) x[u] = vq_ldg_stream(row + ((size_t)(j0 + u) * 8 + l8) * 16);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (j0 + u < steps) {
+                const float* qq = q + ((j0 + u) * 8 + l8) * EPL;
+                const float4 q0 = *reinterpret_cast<const float4*>(qq);
+                if (BF16) {
+                    const float4 q1 = *reinterpret_cast<const float4*>(qq + 4);
+                    acc = fmaf(vq_bf16lo(x[u].x), q0.x, acc); acc = fmaf(vq_bf16hi(x[u].x), q0.y, acc);
+                    acc = fmaf(vq_bf16lo(x[u].y), q0.z, acc); acc = fmaf(vq_bf16hi(x[u].y), q0.w, acc);
+                    acc = fmaf(vq_bf16lo(x[u].z), q1.x, acc); acc = fmaf(vq_bf16hi(x[u].z), q1.y, acc);
+                    acc = fmaf(vq_bf16lo(x[u].w), q1.z, acc); acc = fmaf(vq_bf16hi(x[u].w), q1.w, acc);
+                } else {
+                    acc = fmaf(__uint_as_float(x[u].x), q0.x, acc); acc = fmaf(__uint_as_float(x[u].y), q0.y, acc);
+                    acc = fmaf(__uint_as_float(x[u].z), q0.z, acc); acc = fmaf(__uint_as_float(x[u].w), q0.w, acc);
+                }
+            }
+        }
+    }
+    acc += __shfl_xor_sync(kFull, acc, 1);
+    acc += __shfl_xor_sync(kFull, acc, 2);
+    acc += __shfl_xor_sync(kFull, acc, 4);
+    return acc;
+}
+
+template <bool BF16>
+__global__ void __launch_bounds__(256)
+hnsw_search_kernel(const void* __restrict__ store_v, int ld,
+                   const int* __restrict__ adj0, int m0,
+                   const int* __restrict__ upper_off, const int* __restrict__ upper_adj, int m,
+                   int entry, int max_level, int ef, int cap,
+                   const float* __restrict__ qn,    // [b, ld]
+                   int b, int k,
+                   float* __restrict__ out_dist, int* __restrict__ out_rows, unsigned* __restrict__ out_stats,
+                   int warp_smem_bytes) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int qi = blockIdx.x * (blockDim.x >> 5) + warp;
+    if (qi >= b) return;                                   // whole warp exits together
+    unsigned char* base = smem_raw + (size_t)warp * warp_smem_bytes;
+    WarpState w;
+    w.q = reinterpret_cast<float*>(base);
+    w.ld_ = w.q + ld;
+    w.li = reinterpret_cast<int*>(w.ld_ + ef);
+    w.hash = w.li + ef;
+    w.nbr = w.hash + cap;
+    w.nd = reinterpret_cast<float*>(w.nbr + 32);
+    w.log = reinterpret_cast<unsigned short*>(w.nd + 32);
+
+    const unsigned char* store = reinterpret_cast<const unsigned char*>(store_v);
+    const size_t row_bytes = (size_t)ld * (BF16 ? 2 : 4);
+    const int l8 = lane & 7, grp = lane >> 3;
+    const unsigned mask_cap = (unsigned)cap - 1u;
+    const int shift = 32 - __ffs(cap) + 1;                 // cap = 2^p  ->  hash >> (32 - p)
+
+    for (int i = lane * 4; i < ld; i += 128)
+        *reinterpret_cast<float4*>(w.q + i) = *reinterpret_cast<const float4*>(qn + (size_t)qi * ld + i);
+    for (int i = lane; i < cap; i += 32) w.hash[i] = -1;
+    __syncwarp();
+
+    unsigned evals = 0, hops = 0, overflow = 0;
+    int visited_cnt = 0;            // entries currently in the hash (all lanes hold the same value)
+    int logged = 0;                 // slots recorded in the log (== visited_cnt while <= kLogCap)
+
+    // exact visited-set insert; returns true if `v` was not present.  Divergent-safe (smem atomics).
+    auto visit = [&](int v, int& slot_out) -> bool {
+        unsigned h = ((unsigned)v * 2654435761u) >> shift;
+        for (;;) {
+            const int prev = atomicCAS(&w.hash[h], -1, v);
+            if (prev == -1) { slot_out = (int)h; return true; }
+            if (prev == v) { slot_out = -1; return false; }
+            h = (h + 1) & mask_cap;
+        }
+    };
+
+    // distance of the entry point
+    float cur_d;
+    {
+        const float dot = row_dot_8lanes<BF16>(store + (size_t)entry * row_bytes, w.q, ld, l8);
+        cur_d = 1.0f - __shfl_sync(kFull, dot, 0);
+        evals += 1;
+    }
+    int cur = entry;
+
+    for (int lv = max_level; lv >= 0; --lv) {
+        const int ef_l = lv == 0 ? ef : 1;
+        const int deg = lv == 0 ? m0 : m;
+        // ---- per-layer reset of the visited set (hnsw.py:87 creates a fresh set per layer)
+        if (visited_cnt > 0) {
+            if (logged == visited_cnt && logged <= kLogCap) {
+                for (int i = lane; i < logged; i += 32) w.hash[w.log[i]] = -1;
+            } else {
+                for (int i = lane; i < cap; i += 32) w.hash[i] = -1;
+            }
+            __syncwarp();
+        }
+        visited_cnt = 0; logged = 0;
+        int cnt = 1;
+        if (lane == 0) {
+            w.ld_[0] = cur_d; w.li[0] = cur;
+            int s; visit(cur, s);
+            w.log[0] = (unsigned short)s;
+        }
+        visited_cnt = 1; logged = 1;
+        __syncwarp();
+
+        for (;;) {
+            // first unexpanded entry of the list = closest open candidate
+            int pos = -1;
+            for (int base0 = 0; base0 < cnt && pos < 0; base0 += 32) {
+                const int i = base0 + lane;
+                const unsigned mk = __ballot_sync(kFull, i < cnt && !(w.li[i] & kExpanded));
+                if (mk) pos = base0 + __ffs(mk) - 1;
+            }
+            if (pos < 0) break;
+            const int u = w.li[pos];
+            __syncwarp();
+            if (lane == 0) w.li[pos] = u | kExpanded;
+            hops += 1;
+            const int* arow = lv == 0 ? adj0 + (size_t)u * m0
+                                      : upper_adj + ((size_t)upper_off[u] + lv - 1) * m;
+            for (int c0 = 0; c0 < deg; c0 += 32) {
+                int v = (c0 + lane < deg) ? arow[c0 + lane] : -1;
+                int slot = -1;
+                bool fresh = false;
+                if (v >= 0 && !overflow) fresh = visit(v, slot);
+                const unsigned mk = __ballot_sync(kFull, fresh);
+                const int nnew = __popc(mk);
+                const int my = __popc(mk & ((1u << lane) - 1u));
+                if (fresh) {
+                    w.nbr[my] = v;
+                    if (logged + my < kLogCap) w.log[logged + my] = (unsigned short)slot;
+                }
+                visited_cnt += nnew;
+                logged = (logged + nnew <= kLogCap) ? logged + nnew : kLogCap + 1;   // > cap => full clear next time
+                if (visited_cnt > cap - cap / 8) overflow = 1;
+                __syncwarp();
+                // gather + distance, 4 rows per step (8 lanes each)
+                for (int i0 = 0; i0 < nnew; i0 += 4) {
+                    const int mine = i0 + grp;
+                    const int node = w.nbr[mine < nnew ? mine : nnew - 1];
+                    const float dot = row_dot_8lanes<BF16>(store + (size_t)node * row_bytes, w.q, ld, l8);
+                    if (l8 == 0 && mine < nnew) w.nd[mine] = 1.0f - dot;
+                }
+                evals += nnew;
+                __syncwarp();
+                // admit in neighbour order (hnsw.py:113): not full, or strictly better than the worst kept
+                for (int i = 0; i < nnew; ++i) {
+                    const float d = w.nd[i];
+                    const int node = w.nbr[i];
+                    const bool admit = (cnt < ef_l) || (d < w.ld_[ef_l - 1]);
+                    if (admit) cnt = list_insert_asc(w.ld_, w.li, cnt, ef_l, d, node, lane);
+                }
+                __syncwarp();
+            }
+        }
+        cur = w.li[0] & ~kExpanded;
+        cur_d = w.ld_[0];
+        if (lv == 0) {
+            for (int i = lane; i < k; i += 32) {
+                const bool ok = i < cnt;
+                out_dist[(size_t)qi * k + i] = ok ? w.ld_[i] : INFINITY;
+                out_rows[(size_t)qi * k + i] = ok ? (w.li[i] & ~kExpanded) : -1;
+            }
+        }
+        __syncwarp();
+    }
+    if (out_stats && lane == 0) {
+        out_stats[(size_t)qi * 4 + 0] = evals;
+        out_stats[(size_t)qi * 4 + 1] = hops;
+        out_stats[(size_t)qi * 4 + 2] = overflow;
+        out_stats[(size_t)qi * 4 + 3] = 0;
+    }
+}
+
+// ------------------------------------------------------------------------------------ build
+__global__ void gather_rows_kernel(const uint4* __restrict__ src, const int* __restrict__ members, long long n_members,
+                                   int row_vec, uint4* __restrict__ dst) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_members * row_vec) return;
+    const long long r = i / row_vec;
+    const int c = (int)(i - r * row_vec);
+    dst[i] = src[(size_t)members[r] * row_vec + c];
+}
+
+// forward pick: first m non-self, valid entries of u's exact k-nearest list; every pick also
+// lands in the target's reverse buffer (bounded, atomics).
+__global__ void link_reverse_kernel(const float* __restrict__ knn_s, const int* __restrict__ knn_r, long long n_members,
+                                    int kk, int m, int rcap, int* __restrict__ fwd, float* __restrict__ fwd_s,
+                                    int* __restrict__ rev_cnt, int* __restrict__ rev, float* __restrict__ rev_s) {
+    const long long u = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= n_members) return;
+    int taken = 0;
+    for (int j = 0; j < kk && taken < m; ++j) {
+        const int v = knn_r[u * kk + j];
+        if (v < 0 || v == (int)u) continue;
+        const float s = knn_s[u * kk + j];
+        fwd[u * m + taken] = v;
+        fwd_s[u * m + taken] = s;
+        ++taken;
+        const int slot = atomicAdd(&rev_cnt[v], 1);
+        if (slot < rcap) { rev[(size_t)v * rcap + slot] = (int)u; rev_s[(size_t)v * rcap + slot] = s; }
+    }
+    for (; taken < m; ++taken) { fwd[u * m + taken] = -1; fwd_s[u * m + taken] = VQ_NEG_INF; }
+}
+
+// one warp per node: union(forward, reverse) -> dedupe -> closest m by (score desc, id asc)
+__global__ void __launch_bounds__(256)
+prune_kernel(const int* __restrict__ fwd, const float* __restrict__ fwd_s, const int* __restrict__ rev_cnt,
+             const int* __restrict__ rev, const float* __restrict__ rev_s, long long n_members, int m, int rcap,
+             const int* __restrict__ members, int* __restrict__ adj_out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long u = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
+    if (u >= n_members) return;
+    const int tmax = m + rcap;
+    float* cs = reinterpret_cast<float*>(smem_raw) + (size_t)warp * tmax * 2;
+    int* ci = reinterpret_cast<int*>(cs + tmax);
+    int nrev = rev_cnt[u];
+    nrev = nrev < rcap ? nrev : rcap;
+    const int total = m + nrev;
+    for (int i = lane; i < total; i += 32) {
+        if (i < m) { ci[i] = fwd[u * m + i]; cs[i] = fwd_s[u * m + i]; }
+        else { ci[i] = rev[(size_t)u * rcap + (i - m)]; cs[i] = rev_s[(size_t)u * rcap + (i - m)]; }
+    }
+    for (int i = lane; i < m; i += 32) adj_out[u * m + i] = -1;
+    __syncwarp();
+    // pass 1: drop later copies of an id (an edge can be both a forward pick and a reverse add)
+    bool dupf[4] = {false, false, false, false};
+    for (int e = lane, t = 0; e < total && t < 4; e += 32, ++t) {
+        const int id = ci[e];
+        if (id < 0) continue;
+        for (int f = 0; f < e; ++f)
+            if (ci[f] == id) { dupf[t] = true; break; }
+    }
+    __syncwarp();
+    for (int e = lane, t = 0; e < total && t < 4; e += 32, ++t)
+        if (dupf[t]) ci[e] = -1;
+    __syncwarp();
+    // pass 2: rank by (score desc, id asc) and keep the closest m
+    for (int e = lane; e < total; e += 32) {
+        const int id = ci[e];
+        if (id < 0) continue;
+        const float s = cs[e];
+        int rank = 0;
+        for (int f = 0; f < total; ++f) {
+            const int fid = ci[f];
+            if (fid >= 0 && f != e && vq_better(cs[f], fid, s, id)) ++rank;
+        }
+        if (rank < m) adj_out[u * m + rank] = members ? members[id] : id;
+    }
+}
+
+inline size_t align256(size_t v) { return (v + 255) / 256 * 256; }
+inline int pow2_ge(int v) { int p = 1; while (p < v) p <<= 1; return p; }
+
+struct SearchPlan { int cap, warp_bytes, warps; size_t smem; };
+SearchPlan plan_search(int ld, int ef) {
+    SearchPlan p;
+    p.cap = pow2_ge(ef * 24 < 1024 ? 1024 : ef * 24);
+    if (p.cap > 32768) p.cap = 32768;
+    p.warp_bytes = (int)align256((size_t)ld * 4 + (size_t)ef * 8 + (size_t)p.cap * 4 + 32 * 8 + kLogCap * 2);
+    p.warps = 8;
+    while (p.warps > 1 && (size_t)p.warps * p.warp_bytes > 200 * 1024) p.warps >>= 1;
+    p.smem = (size_t)p.warps * p.warp_bytes;
+    return p;
+}
+
+}  // namespace
+
 extern "C" {
-size_t vq_hnsw_workspace_bytes(int, int, int) { return 256; }
-int vq_hnsw_search(const void*, int64_t, int, int, int, const int32_t*, const int32_t*, int, const int32_t*,
-                   const int32_t*, int, int32_t, int, int, const float*, int, int, int, float*, int32_t*, uint32_t*,
-                   void*, size_t, void*) {
-    vq_set_error("hnsw_search not built yet");
-    return VQ_EUNSUPPORTED;
+
+size_t vq_hnsw_workspace_bytes(int b, int ld, int ef) {
+    (void)ef;
+    return align256((size_t)(b > 0 ? b : 1) * ld * 4) + 256;
 }
-size_t vq_hnsw_layer_workspace_bytes(int64_t, int, int, int, int, int) { return 256; }
-int vq_hnsw_build_layer(const void*, int64_t, int, int, int, const int32_t*, int64_t, int, int, int, int32_t*, void*,
-                        size_t, void*) {
-    vq_set_error("hnsw_build_layer not built yet");
-    return VQ_EUNSUPPORTED;
+
+int vq_hnsw_search(const void* store, int64_t n, int dim, int ld, int store_dtype, const int32_t* levels,
+                   const int32_t* adj0, int m0, const int32_t* upper_off, const int32_t* upper_adj, int m,
+                   int32_t entry, int max_level, int ef, const float* queries, int b, int k, int query_norm,
+                   float* out_dist, int32_t* out_rows, uint32_t* out_stats, void* workspace, size_t workspace_bytes,
+                   void* stream_v) {
+    (void)levels;
+    cudaStream_t stream = (cudaStream_t)stream_v;
+    VQ_CHECK_ARG(store_dtype == VQ_F32 || store_dtype == VQ_BF16, "bad store_dtype %d", store_dtype);
+    VQ_CHECK_ARG(n > 0 && n < (1 << 30), "n=%lld out of range (node ids must be < 2^30)", (long long)n);
+    VQ_CHECK_ARG(dim > 0 && ld >= dim && ld % (store_dtype == VQ_BF16 ? 64 : 32) == 0, "bad dim/ld %d/%d", dim, ld);
+    VQ_CHECK_ARG(m0 > 0 && m > 0 && m0 <= 1024 && m <= 1024, "bad degrees m0=%d m=%d", m0, m);
+    VQ_CHECK_ARG(entry >= 0 && entry < n && max_level >= 0, "bad entry/max_level %d/%d", entry, max_level);
+    VQ_CHECK_ARG(b >= 0 && k > 0, "bad b/k %d/%d", b, k);
+    VQ_CHECK_ARG(query_norm >= VQ_NORM_NONE && query_norm <= VQ_NORM_PLAIN, "bad query_norm %d", query_norm);
+    if (b == 0) return VQ_OK;
+    VQ_CHECK_ARG(store && adj0 && queries && out_dist && out_rows && workspace, "NULL pointer argument");
+    VQ_CHECK_ARG(max_level == 0 || (upper_off && upper_adj), "upper layers missing");
+    if (ef < k) ef = k;                                       // hnsw.py:264  ef = max(ef_search, k)
+    VQ_CHECK_ARG(ef <= 4096, "ef=%d too large (max 4096)", ef);
+    if (workspace_bytes < vq_hnsw_workspace_bytes(b, ld, ef)) {
+        vq_set_error("hnsw workspace too small");
+        return VQ_EWORKSPACE;
+    }
+    float* qn = (float*)workspace;
+    int rc = vq_ingest_launch(queries, b, dim, dim, qn, VQ_F32, ld, query_norm, stream);
+    if (rc) return rc;
+    const SearchPlan p = plan_search(ld, ef);
+    if ((size_t)p.warp_bytes > 200 * 1024) {
+        vq_set_error("hnsw_search: per-query shared memory %d B too large (ld=%d ef=%d)", p.warp_bytes, ld, ef);
+        return VQ_EUNSUPPORTED;
+    }
+    const int grid = (b + p.warps - 1) / p.warps;
+    vq_prof_begin(stream);
+    if (store_dtype == VQ_BF16) {
+        VQ_CUDA(cudaFuncSetAttribute(hnsw_search_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        hnsw_search_kernel<true><<<grid, p.warps * 32, p.smem, stream>>>(store, ld, adj0, m0, upper_off, upper_adj, m, entry,
+                                                                       max_level, ef, p.cap, qn, b, k, out_dist, out_rows,
+                                                                       out_stats, p.warp_bytes);
+    } else {
+        VQ_CUDA(cudaFuncSetAttribute(hnsw_search_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        hnsw_search_kernel<false><<<grid, p.warps * 32, p.smem, stream>>>(store, ld, adj0, m0, upper_off, upper_adj, m, entry,
+                                                                        max_level, ef, p.cap, qn, b, k, out_dist, out_rows,
+                                                                        out_stats, p.warp_bytes);
+    }
+    vq_prof_end(stream);
+    VQ_LAUNCH_CHECK("hnsw_search_kernel");
+    vq_note_launch(store_dtype == VQ_BF16 ? "hnsw_search_bf16" : "hnsw_search_f32", 2);
+    return VQ_OK;
 }
+
+// workspace layout of one layer build
+struct BuildPlan {
+    int kk, rcap, grid;
+    size_t compact, knn_s, knn_r, part_s, part_r, fwd, fwd_s, rev_cnt, rev, rev_s, total;
+};
+static BuildPlan plan_build(int64_t n_members, int ld, int k_cand, int m_out, bool need_compact) {
+    BuildPlan p;
+    p.kk = (k_cand > m_out ? k_cand : m_out) + 1;           // +1: the node itself is its own nearest
+    p.rcap = 4 * m_out;
+    p.grid = vq_scan_fma_grid((int)n_members, 16);
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off += align256(bytes); return o; };
+    p.compact = take(need_compact ? (size_t)n_members * ld * 4 : 0);
+    p.knn_s = take((size_t)n_members * p.kk * 4);
+    p.knn_r = take((size_t)n_members * p.kk * 4);
+    p.part_s = take((size_t)p.grid * 16 * p.kk * 4);
+    p.part_r = take((size_t)p.grid * 16 * p.kk * 4);
+    p.fwd = take((size_t)n_members * m_out * 4);
+    p.fwd_s = take((size_t)n_members * m_out * 4);
+    p.rev_cnt = take((size_t)n_members * 4);
+    p.rev = take((size_t)n_members * p.rcap * 4);
+    p.rev_s = take((size_t)n_members * p.rcap * 4);
+    p.total = off + 256;
+    return p;
 }
+
+size_t vq_hnsw_layer_workspace_bytes(int64_t n_members, int dim, int ld, int store_dtype, int k_cand, int m_out) {
+    (void)dim; (void)store_dtype;
+    if (n_members <= 0) return 256;
+    return plan_build(n_members, ld, k_cand, m_out, true).total;
+}
+
+int vq_hnsw_build_layer(const void* store, int64_t n, int dim, int ld, int store_dtype, const int32_t* members,
+                        int64_t n_members, int k_cand, int m_out, int diversify, int32_t* adj_out, void* workspace,
+                        size_t workspace_bytes, void* stream_v) {
+    cudaStream_t stream = (cudaStream_t)stream_v;
+    VQ_CHECK_ARG(store_dtype == VQ_F32, "hnsw_build_layer needs the fp32 store (got dtype %d)", store_dtype);
+    VQ_CHECK_ARG(n > 0 && n < (1 << 30) && dim > 0 && ld >= dim && ld % 32 == 0, "bad shape n=%lld dim=%d ld=%d", (long long)n, dim, ld);
+    VQ_CHECK_ARG(n_members >= 0 && n_members <= n, "bad n_members %lld", (long long)n_members);
+    VQ_CHECK_ARG(m_out > 0 && m_out <= 25 && k_cand > 0 && k_cand <= 512, "bad m_out/k_cand %d/%d", m_out, k_cand);
+    if (diversify != 0) {
+        vq_set_error("diversify=1 is not implemented yet (only the reference's closest-M selection)");
+        return VQ_EUNSUPPORTED;
+    }
+    if (n_members == 0) return VQ_OK;
+    VQ_CHECK_ARG(store && adj_out && workspace, "NULL pointer argument");
+    VQ_CHECK_ARG(((uintptr_t)workspace & 255) == 0, "workspace must be 256-byte aligned");
+    const bool compact = members != nullptr;
+    const BuildPlan p = plan_build(n_members, ld, k_cand, m_out, true);
+    if (workspace_bytes < p.total) {
+        vq_set_error("hnsw build workspace too small: %zu < %zu", workspace_bytes, p.total);
+        return VQ_EWORKSPACE;
+    }
+    unsigned char* ws = (unsigned char*)workspace;
+    const float* mat = (const float*)store;
+    int launches = 0;
+    if (compact) {
+        const int row_vec = ld / 4;
+        const long long items = (long long)n_members * row_vec;
+        gather_rows_kernel<<<(unsigned)((items + 255) / 256), 256, 0, stream>>>((const uint4*)store, members, n_members,
+                                                                              row_vec, (uint4*)(ws + p.compact));
+        VQ_LAUNCH_CHECK("gather_rows_kernel");
+        mat = (const float*)(ws + p.compact);
+        ++launches;
+    }
+    float* knn_s = (float*)(ws + p.knn_s);
+    int* knn_r = (int*)(ws + p.knn_r);
+    // exact k-nearest members of every member: the rows themselves are the (already unit-norm,
+    // zero-padded) query tiles, 16 per pass of the fused scan + top-k kernel.
+    const int nm = (int)n_members;
+    for (int q0 = 0; q0 < nm;) {
+        int bt, start;
+        if (nm - q0 >= 16) { bt = 16; start = q0; }
+        else if (nm >= 16) { bt = 16; start = nm - 16; }      // last tile shifted back (recomputes a few rows)
+        else { bt = 1; start = q0; }                           // tiny top layers: one query per pass
+        const int grid = vq_scan_fma_grid(nm, bt);
+        int rc = vq_scan_fma_launch(mat, nm, ld, VQ_F32, mat + (size_t)start * ld, bt, p.kk, (float*)(ws + p.part_s),
+                                    (int*)(ws + p.part_r), grid, stream);
+        if (rc) return rc;
+        rc = vq_topk_merge_launch((float*)(ws + p.part_s), (int*)(ws + p.part_r), grid, (long long)bt * p.kk, bt, p.kk, nullptr,
+                                  p.kk, knn_s + (size_t)start * p.kk, knn_r + (size_t)start * p.kk, 0, 0, stream);
+        if (rc) return rc;
+        launches += 2;
+        q0 = start + bt;
+    }
+    VQ_CUDA(cudaMemsetAsync(ws + p.rev_cnt, 0, (size_t)n_members * 4, stream));
+    link_reverse_kernel<<<(unsigned)((n_members + 255) / 256), 256, 0, stream>>>(
+        knn_s, knn_r, n_members, p.kk, m_out, p.rcap, (int*)(ws + p.fwd), (float*)(ws + p.fwd_s), (int*)(ws + p.rev_cnt),
+        (int*)(ws + p.rev), (float*)(ws + p.rev_s));
+    VQ_LAUNCH_CHECK("link_reverse_kernel");
+    const size_t psmem = (size_t)8 * (m_out + p.rcap) * 8;
+    prune_kernel<<<(unsigned)((n_members + 7) / 8), 256, psmem, stream>>>(
+        (int*)(ws + p.fwd), (float*)(ws + p.fwd_s), (int*)(ws + p.rev_cnt), (int*)(ws + p.rev), (float*)(ws + p.rev_s),
+        n_members, m_out, p.rcap, members, adj_out);
+    VQ_LAUNCH_CHECK("prune_kernel");
+    vq_note_launch("hnsw_build_layer", launches + 2);
+    return VQ_OK;
+}
+
+}  // extern "C"

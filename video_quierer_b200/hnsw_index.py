@@ -1,0 +1,429 @@
+"""B200HNSWIndex — drop-in for the reference's ``OptimizedHNSWIndex``
+(reference src/indexes/hnsw.py:19-528): same constructor, ``add`` / ``add_batch`` /
+``search`` / ``search_batch`` / ``size`` / ``save`` / ``load`` / ``get_stats``, same result
+dicts (``{'id','distance','score'}`` ascending distance), same pickle + ``.sha256`` sidecar.
+
+What changes is the engine:
+  * vectors live in a contiguous device matrix, L2-normalised on ingest by `vq_ingest_rows`
+    (hnsw.py:157);
+  * the graph is a dense device structure (layer-0 ``[N, max_M]`` + upper-layer slot table);
+  * ``search`` / ``search_batch`` are ONE `vq_hnsw_search` launch, a warp per query, instead
+    of a Python heap loop per query serialised by a lock (hnsw.py:252, 282-300);
+  * construction is a batched GPU build (`vq_hnsw_build_layer`: exact k-nearest members per
+    layer + reverse edges + closest-M prune — the batch analogue of hnsw.py:183-223) that runs
+    lazily before the first search after inserts.  Rows added after a build are served by an
+    exact scan of that delta until it grows past `rebuild_fraction` of the graph, so inserts
+    never trigger an O(N^2) rebuild each.
+
+Levels are drawn exactly like the reference (``int(-ln(U) * mL)`` from the global ``random``
+stream, hnsw.py:68-74) so the same ``random.seed`` gives the same level sequence and the same
+entry point (first node that reaches the maximum level, hnsw.py:226-227).
+"""
+
+from __future__ import annotations
+
+import hashlib
+import math
+import os
+import pickle
+import random
+import threading
+import time
+from collections import defaultdict
+from concurrent.futures import ThreadPoolExecutor
+from typing import Dict, List
+
+import numpy as np
+import torch
+
+from . import _lib
+from .engine import DeviceStore, Scanner, Workspace, _ptr, _require_cuda, _stream, as_device_queries
+
+
+class DeviceGraph:
+    """Dense HNSW graph on the device (layout documented in DESIGN.md §3 / include/vq_search.h)."""
+
+    def __init__(self, levels, adj0, upper_off, upper_adj, entry: int, max_level: int):
+        self.levels, self.adj0, self.upper_off, self.upper_adj = levels, adj0, upper_off, upper_adj
+        self.entry, self.max_level = int(entry), int(max_level)
+        self.n = int(adj0.shape[0])
+
+    @classmethod
+    def from_numpy(cls, levels, adj0, upper_off, upper_adj, entry, max_level, device):
+        t = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.int32)).to(device)  # noqa: E731
+        return cls(t(levels), t(adj0), t(upper_off), t(upper_adj), entry, max_level)
+
+
+class B200HNSWIndex:
+    def __init__(self, dimension: int = 512, M: int = 16, ef_construction: int = 200, ef_search: int = 50,
+                 max_M: int = 16, level_generation_factor: float = 1.0 / math.log(2.0), num_threads: int = 4,
+                 use_numpy_optimization: bool = True, device=None, search_dtype: str = "fp32",
+                 rebuild_fraction: float = 0.10):
+        self.dimension = dimension
+        self.M = M
+        self.max_M = max_M
+        self.ef_construction = ef_construction
+        self.ef_search = ef_search
+        self.level_generation_factor = level_generation_factor
+        self.num_threads = num_threads
+        self.use_numpy_optimization = use_numpy_optimization
+        self.search_dtype = "bf16" if search_dtype in ("bf16", "bfloat16") else "fp32"
+        self.rebuild_fraction = float(rebuild_fraction)
+
+        self.levels: Dict = {}               # id -> level (public in the reference)
+        self.entry_point = None              # external id of the entry node
+        self.element_count = 0
+        self.lock = threading.RLock()
+        self.thread_pool = ThreadPoolExecutor(max_workers=max(1, num_threads))   # kept: callers shut it down
+        self.build_time = 0
+        self.search_times: List[float] = []
+        self.last_stats = None               # [b,4] uint32 of the last search: evals, hops, overflow, -
+
+        self.device = _require_cuda(device)
+        self.lib = _lib.load()
+        self._store = DeviceStore(dimension, self.device, keep_fp32=True, keep_bf16=self.search_dtype == "bf16")
+        self._scanner = Scanner(self.device)
+        self._ws = Workspace(self.device)
+        self._bws = Workspace(self.device)
+        self._ids: List = []                 # row -> external id
+        self._row_of: Dict = {}              # external id -> row (latest)
+        self._dead = set()                   # rows superseded by a re-added id
+        self._level_list: List[int] = []     # row -> level
+        self._pending: List[np.ndarray] = [] # rows not yet uploaded
+        self._graph: DeviceGraph | None = None
+        self._entry_row = -1
+
+    # ------------------------------------------------------------------ primitives kept for API parity
+    def _get_random_level(self) -> int:
+        """hnsw.py:68-74 (global `random` stream on purpose)."""
+        return int(-math.log(random.uniform(0, 1)) * self.level_generation_factor)
+
+    def _distance(self, vec1: np.ndarray, vec2: np.ndarray) -> float:
+        """hnsw.py:59-66 — host helper only; the search path computes distances on the device."""
+        return 1.0 - np.dot(vec1, vec2)
+
+    # ------------------------------------------------------------------ ingest
+    def add(self, vector: np.ndarray, node_id) -> None:
+        with self.lock:
+            v = np.asarray(vector, dtype=np.float32).reshape(-1)
+            if v.shape[0] != self.dimension:
+                raise ValueError(f"vector dimension {v.shape[0]} != index dimension {self.dimension}")
+            level = self._get_random_level()
+            row = len(self._ids)
+            if node_id in self._row_of:
+                self._dead.add(self._row_of[node_id])
+            self._ids.append(node_id)
+            self._row_of[node_id] = row
+            self._level_list.append(level)
+            self.levels[node_id] = level
+            self._pending.append(v)
+            if self.entry_point is None or level > self._level_list[self._entry_row]:
+                self.entry_point = node_id            # hnsw.py:168-169, 226-227
+                self._entry_row = row
+            self.element_count += 1
+
+    def add_batch(self, vectors, node_ids) -> None:
+        """hnsw.py:231-236 (same order → same level stream)."""
+        for vector, node_id in zip(vectors, node_ids):
+            self.add(vector, node_id)
+
+    def _upload(self):
+        if self._pending:
+            chunk = 1 << 16
+            for s in range(0, len(self._pending), chunk):
+                self._store.append(np.stack(self._pending[s:s + chunk]), _lib.NORM_PLAIN)   # hnsw.py:157
+            self._pending = []
+
+    # ------------------------------------------------------------------ build
+    def build(self) -> None:
+        """(Re)build the graph over every stored row on the GPU."""
+        with self.lock:
+            self._upload()
+            n = self._store.n
+            if n == 0:
+                self._graph = None
+                return
+            t0 = time.time()
+            dev = self.device
+            st = self._store
+            levels_np = np.asarray(self._level_list, dtype=np.int32)
+            max_level = int(levels_np.max())
+            entry = int(np.argmax(levels_np == max_level))        # first row that reaches the top level
+            with torch.cuda.device(dev):
+                levels = torch.from_numpy(levels_np).to(dev)
+                adj0 = torch.full((n, self.max_M), -1, dtype=torch.int32, device=dev)
+                self._build_layer(None, n, self.max_M, adj0)
+                up_cnt = np.where(levels_np > 0, levels_np, 0).astype(np.int64)
+                off_np = np.cumsum(up_cnt) - up_cnt
+                slots = int(up_cnt.sum())
+                upper_off_np = np.where(levels_np > 0, off_np, -1).astype(np.int32)
+                upper_off = torch.from_numpy(upper_off_np).to(dev)
+                upper_adj = torch.full((max(slots, 1), self.M), -1, dtype=torch.int32, device=dev)
+                for lv in range(1, max_level + 1):
+                    members_np = np.nonzero(levels_np >= lv)[0].astype(np.int32)
+                    if len(members_np) < 2:
+                        continue
+                    members = torch.from_numpy(members_np).to(dev)
+                    adj = torch.full((len(members_np), self.M), -1, dtype=torch.int32, device=dev)
+                    self._build_layer(members, len(members_np), self.M, adj)
+                    dst = (upper_off[members.long()] + (lv - 1)).long()
+                    upper_adj[dst] = adj
+                torch.cuda.synchronize(dev)
+            self._graph = DeviceGraph(levels, adj0, upper_off, upper_adj, entry, max_level)
+            self._entry_row = entry
+            self.entry_point = self._ids[entry]
+            self.build_time = time.time() - t0
+
+    def _build_layer(self, members, n_members: int, m_out: int, adj_out: torch.Tensor):
+        st = self._store
+        # "closest M" selection (hnsw.py:123-148) only ever looks at the M nearest candidates, so the
+        # exact candidate pool is m_out wide; ef_construction bounds it like the reference's beam.
+        k_cand = min(max(m_out, 1), max(self.ef_construction, m_out))
+        need = self.lib.vq_hnsw_layer_workspace_bytes(n_members, st.dim, st.ld, _lib.F32, k_cand, m_out)
+        ws = self._bws.get(need)
+        rc = self.lib.vq_hnsw_build_layer(_ptr(st.f32), st.n, st.dim, st.ld, _lib.F32, _ptr(members), n_members,
+                                          k_cand, m_out, 0, _ptr(adj_out), _ptr(ws), ws.numel(), _stream(self.device))
+        _lib.check(rc, "vq_hnsw_build_layer")
+
+    def _ensure_graph(self):
+        self._upload()
+        n = self._store.n
+        g = self._graph
+        if n == 0:
+            return
+        if g is None or (n - g.n) > max(1024, self.rebuild_fraction * g.n):
+            self.build()
+
+    # ------------------------------------------------------------------ search
+    def _search_rows(self, queries, k: int):
+        """→ (dist [b,k'] float32, rows [b,k'] int64) numpy, ascending distance, -1 padded."""
+        with self.lock:
+            self._ensure_graph()
+            st, g = self._store, self._graph
+            q = as_device_queries(queries, self.dimension, self.device)
+            b = q.shape[0]
+            ef = max(int(self.ef_search), int(k))                # hnsw.py:264
+            kk = min(int(k), g.n)
+            mat = st.bf16 if self.search_dtype == "bf16" else st.f32
+            dt = _lib.BF16 if self.search_dtype == "bf16" else _lib.F32
+            with torch.cuda.device(self.device):
+                out_d = torch.empty((b, kk), dtype=torch.float32, device=self.device)
+                out_r = torch.empty((b, kk), dtype=torch.int32, device=self.device)
+                stats = torch.zeros((b, 4), dtype=torch.int32, device=self.device)
+                ws = self._ws.get(self.lib.vq_hnsw_workspace_bytes(b, st.ld, ef))
+                rc = self.lib.vq_hnsw_search(_ptr(mat), g.n, st.dim, st.ld, dt, _ptr(g.levels), _ptr(g.adj0),
+                                             g.adj0.shape[1], _ptr(g.upper_off), _ptr(g.upper_adj),
+                                             g.upper_adj.shape[1], g.entry, g.max_level, ef, _ptr(q), b, kk,
+                                             _lib.NORM_PLAIN, _ptr(out_d), _ptr(out_r), _ptr(stats), _ptr(ws),
+                                             ws.numel(), _stream(self.device))
+                _lib.check(rc, "vq_hnsw_search")
+                dist = out_d.cpu().numpy()
+                rows = out_r.cpu().numpy().astype(np.int64)
+                self.last_stats = stats.cpu().numpy().astype(np.uint32)
+                if st.n > g.n:                                    # rows newer than the graph: exact scan of the delta
+                    kd = min(int(k), st.n - g.n)
+                    s2, r2 = self._scanner.scan(st.f32[g.n:], st.n - g.n, st.dim, q, kd, _lib.NORM_PLAIN, "fma")
+                    d2 = (1.0 - s2).cpu().numpy()
+                    r2 = r2.cpu().numpy().astype(np.int64)
+                    r2 = np.where(r2 >= 0, r2 + g.n, -1)
+                    dist = np.concatenate([dist, d2], axis=1)
+                    rows = np.concatenate([rows, r2], axis=1)
+                    dist = np.where(rows >= 0, dist, np.inf)
+                    order = np.lexsort((rows, dist), axis=1)[:, :min(int(k), st.n)]
+                    dist = np.take_along_axis(dist, order, axis=1)
+                    rows = np.take_along_axis(rows, order, axis=1)
+            return dist, rows
+
+    def _format(self, dist_row, rows_row, k):
+        out = []
+        for d, r in zip(dist_row, rows_row):
+            if r < 0 or int(r) in self._dead:
+                continue
+            d32 = np.float32(d)
+            out.append({'id': self._ids[int(r)], 'distance': d32, 'score': np.float32(1.0) - d32})
+            if len(out) >= k:
+                break
+        return out
+
+    def search(self, query: np.ndarray, k: int = 5) -> List[Dict]:
+        """hnsw.py:488-528."""
+        if self.entry_point is None or self.element_count == 0:
+            return []
+        t0 = time.time()
+        dist, rows = self._search_rows(np.asarray(query), k)
+        res = self._format(dist[0], rows[0], k)
+        self.search_times.append((time.time() - t0) * 1000)
+        return res
+
+    def search_batch(self, queries, k: int = 5) -> List[List[Dict]]:
+        """hnsw.py:282-300 — here one kernel launch for the whole batch, order preserved."""
+        if len(queries) == 0:
+            return []
+        if self.entry_point is None or self.element_count == 0:
+            return [[] for _ in queries]
+        t0 = time.time()
+        q = queries if isinstance(queries, (np.ndarray, torch.Tensor)) else np.stack([np.asarray(x) for x in queries])
+        dist, rows = self._search_rows(q, k)
+        out = [self._format(d, r, k) for d, r in zip(dist, rows)]
+        per = (time.time() - t0) * 1000 / len(out)
+        self.search_times.extend([per] * len(out))
+        return out
+
+    def search_arrays(self, queries, k: int = 5):
+        """Batched search returning (distance [b,k'], row [b,k']) numpy arrays (rows = insertion order)."""
+        return self._search_rows(queries, k)
+
+    def size(self) -> int:
+        return self.element_count
+
+    # ------------------------------------------------------------------ reference-format views
+    @property
+    def data(self) -> Dict:
+        """id -> normalised vector, like the reference's `data` dict (built on demand)."""
+        with self.lock:
+            self._upload()
+            host = self._store.rows_to_host()
+            return {self._ids[r]: host[r] for r in range(len(self._ids)) if r not in self._dead}
+
+    @property
+    def graph(self):
+        """level -> id -> set(ids), like the reference's `graph` (built on demand)."""
+        with self.lock:
+            self._ensure_graph()
+            out = defaultdict(lambda: defaultdict(set))
+            g = self._graph
+            if g is None:
+                return out
+            adj0 = g.adj0.cpu().numpy()
+            up_off = g.upper_off.cpu().numpy()
+            up_adj = g.upper_adj.cpu().numpy()
+            lv_np = g.levels.cpu().numpy()
+            for r in range(g.n):
+                out[0][self._ids[r]] = {self._ids[int(v)] for v in adj0[r] if v >= 0}
+                for lv in range(1, int(lv_np[r]) + 1):
+                    out[lv][self._ids[r]] = {self._ids[int(v)] for v in up_adj[up_off[r] + lv - 1] if v >= 0}
+            return out
+
+    # ------------------------------------------------------------------ persistence (hnsw.py:306-380)
+    def save(self, filepath: str) -> None:
+        with self.lock:
+            save_data = {
+                'dimension': self.dimension, 'M': self.M, 'max_M': self.max_M,
+                'ef_construction': self.ef_construction, 'ef_search': self.ef_search,
+                'level_generation_factor': self.level_generation_factor,
+                'data': self.data, 'levels': dict(self.levels),
+                'graph': {lv: dict(nodes) for lv, nodes in self.graph.items()},
+                'entry_point': self.entry_point, 'element_count': self.element_count,
+            }
+            os.makedirs(os.path.dirname(filepath), exist_ok=True)   # bare filename raises like the reference (:327)
+            with open(filepath, 'wb') as f:
+                pickle.dump(save_data, f, protocol=pickle.HIGHEST_PROTOCOL)
+            with open(filepath, 'rb') as f:
+                checksum = hashlib.sha256(f.read()).hexdigest()
+            with open(filepath + '.sha256', 'w') as f:
+                f.write(checksum)
+
+    def load(self, filepath: str) -> None:
+        try:
+            with open(filepath, 'rb') as f:
+                current_checksum = hashlib.sha256(f.read()).hexdigest()
+            with open(filepath + '.sha256', 'r') as f:
+                expected_checksum = f.read().strip()
+            if current_checksum != expected_checksum:
+                raise ValueError("Index file corrupted (checksum mismatch)")
+        except FileNotFoundError:
+            print("Warning: No checksum file found, skipping verification")
+        with open(filepath, 'rb') as f:
+            save_data = pickle.load(f)
+        with self.lock:
+            self.dimension = save_data['dimension']
+            self.M = save_data['M']
+            self.max_M = save_data['max_M']
+            self.ef_construction = save_data['ef_construction']
+            self.ef_search = save_data['ef_search']
+            self.level_generation_factor = save_data['level_generation_factor']
+            data, levels, graph = save_data['data'], save_data['levels'], save_data['graph']
+            self._ids = list(data.keys())
+            self._row_of = {nid: r for r, nid in enumerate(self._ids)}
+            self._dead = set()
+            self.levels = dict(levels)
+            self._level_list = [int(levels[nid]) for nid in self._ids]
+            self.entry_point = save_data['entry_point']
+            self.element_count = save_data['element_count']
+            self._pending = []
+            self._store = DeviceStore(self.dimension, self.device, keep_fp32=True,
+                                      keep_bf16=self.search_dtype == "bf16")
+            n = len(self._ids)
+            if n == 0:
+                self._graph = None
+                self._entry_row = -1
+                return
+            vecs = np.stack([np.asarray(data[nid], dtype=np.float32) for nid in self._ids])
+            self._store.append(vecs, _lib.NORM_NONE)           # stored vectors are already normalised
+            self._entry_row = self._row_of[self.entry_point]
+            self._graph = self._graph_from_dicts(graph)
+
+    def _graph_from_dicts(self, graph) -> DeviceGraph:
+        n = len(self._ids)
+        lv_np = np.asarray(self._level_list, dtype=np.int32)
+        m0 = max(self.max_M, max((len(nb) for nb in graph.get(0, {}).values()), default=0))
+        mu = max(self.M, max((len(nb) for lv, nodes in graph.items() if int(lv) > 0 for nb in nodes.values()),
+                             default=0))
+        adj0 = np.full((n, m0), -1, np.int32)
+        up_cnt = np.where(lv_np > 0, lv_np, 0).astype(np.int64)
+        off = np.cumsum(up_cnt) - up_cnt
+        upper_off = np.where(lv_np > 0, off, -1).astype(np.int32)
+        upper_adj = np.full((max(int(up_cnt.sum()), 1), mu), -1, np.int32)
+        for lv, nodes in graph.items():
+            lv = int(lv)
+            for nid, nbrs in nodes.items():
+                r = self._row_of[nid]
+                rows = sorted(self._row_of[x] for x in nbrs)
+                if lv == 0:
+                    adj0[r, :len(rows)] = rows
+                elif lv <= lv_np[r]:
+                    upper_adj[upper_off[r] + lv - 1, :len(rows)] = rows
+        return DeviceGraph.from_numpy(lv_np, adj0, upper_off, upper_adj, self._entry_row,
+                                      int(lv_np[self._entry_row]), self.device)
+
+    def load_arrays(self, vectors: np.ndarray, levels, adj0, upper_off, upper_adj, entry: int, ids=None):
+        """Adopt a prebuilt dense graph (e.g. one exported by the oracle or the reference)."""
+        with self.lock:
+            n = len(vectors)
+            self._ids = list(range(n)) if ids is None else list(ids)
+            self._row_of = {nid: r for r, nid in enumerate(self._ids)}
+            self._dead = set()
+            self._level_list = [int(x) for x in levels]
+            self.levels = {nid: lv for nid, lv in zip(self._ids, self._level_list)}
+            self._pending = []
+            self._store = DeviceStore(self.dimension, self.device, keep_fp32=True,
+                                      keep_bf16=self.search_dtype == "bf16")
+            self._store.append(np.asarray(vectors, dtype=np.float32), _lib.NORM_NONE)
+            self._entry_row = int(entry)
+            self.entry_point = self._ids[int(entry)]
+            self.element_count = n
+            self._graph = DeviceGraph.from_numpy(levels, adj0, upper_off, upper_adj, entry,
+                                                 int(self._level_list[int(entry)]), self.device)
+
+    # ------------------------------------------------------------------ stats (hnsw.py:382-402)
+    def get_stats(self) -> Dict:
+        if not self.search_times:
+            avg_search_time = 0
+            p95_search_time = 0
+        else:
+            avg_search_time = sum(self.search_times) / len(self.search_times)
+            p95_search_time = np.percentile(self.search_times, 95)
+        return {
+            'element_count': self.element_count,
+            'entry_point_level': self.levels.get(self.entry_point, 0) if self.entry_point else 0,
+            'avg_search_time_ms': avg_search_time,
+            'p95_search_time_ms': p95_search_time,
+            'total_searches': len(self.search_times),
+            'dimension': self.dimension,
+            'M': self.M,
+            'ef_search': self.ef_search,
+        }
+
+
+# the reference exports both names; both map to the same engine here
+B200OptimizedHNSWIndex = B200HNSWIndex
