@@ -29,6 +29,8 @@ def main():
     st.append(x)
     del x
     sc = engine.Scanner(dev)
+    lib = _lib.load()
+    lib.vq_profile_enable(1)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     for dt in a.dtypes.split(","):
         mat = st.view(dt)
@@ -44,6 +46,7 @@ def main():
                     continue
                 torch.cuda.synchronize()
                 ts = []
+                ks = []
                 for _ in range(a.iters):
                     flush.zero_()
                     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -52,10 +55,11 @@ def main():
                     e1.record()
                     torch.cuda.synchronize()
                     ts.append(e0.elapsed_time(e1))
+                    ks.append(lib.vq_profile_last_kernel_ms())
                 ts.sort()
                 med = ts[len(ts) // 2]
                 print(json.dumps({"dtype": dt, "path": sc.last_path, "b": b, "ms_med": round(med, 4),
-                                  "ms_min": round(ts[0], 4), "GBps": round(bytes_pass / med / 1e6, 1),
+                                  "ms_min": round(ts[0], 4), "kernel_ms": round(sorted(ks)[len(ks) // 2], 4), "GBps_kernel": round(bytes_pass / sorted(ks)[len(ks) // 2] / 1e6, 1),
                                   "qps": round(b / med * 1e3, 1), "launches": sc.last_launches,
                                   "tflops": round(2.0 * b * st.n * a.dim / med / 1e9, 2)}), flush=True)
 

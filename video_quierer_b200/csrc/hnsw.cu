@@ -341,6 +341,145 @@ prune_kernel(const int* __restrict__ fwd, const float* __restrict__ fwd_s, const
     }
 }
 
+
+// ---- diversity selection (the HNSW "select neighbours" heuristic, evaluated from k-nearest lists)
+// Candidates (member indices `cid`, scores `cs`, sorted best first, T of them) of node u are taken
+// greedily; candidate c is rejected when some already selected a is closer to c than u is:
+// s(c,a) > s(c,u).  s(c,a) is looked up in c's own exact k-nearest list — if a is not among c's
+// k nearest then s(c,a) <= s_k(c), which cannot exceed s(c,u) whenever u itself is in that list —
+// so no embedding row is gathered at all.  Rejected candidates refill the list while there is
+// room ("keep pruned connections"), so every node keeps its full degree.
+__device__ int diverse_select(const int* cid, const float* cs, int T, const int* __restrict__ knn_r,
+                              const float* __restrict__ knn_s, int kk, int m, int* sel, float* sel_s,
+                              unsigned char* rej, int lane) {
+    int ns = 0;
+    for (int j = 0; j < T && ns < m; ++j) {
+        const int c = cid[j];
+        const float sc = cs[j];
+        int li[3]; float lsc[3];
+#pragma unroll
+        for (int t = 0; t < 3; ++t) {
+            const int idx = lane + 32 * t;
+            li[t] = idx < kk ? knn_r[(size_t)c * kk + idx] : -2;
+            lsc[t] = idx < kk ? knn_s[(size_t)c * kk + idx] : 0.f;
+        }
+        bool reject = false;
+        for (int a = 0; a < ns && !reject; ++a) {
+            const int aid = sel[a];
+#pragma unroll
+            for (int t = 0; t < 3; ++t) {
+                const unsigned bm = __ballot_sync(kFull, li[t] == aid);
+                if (bm) {
+                    const float sca = __shfl_sync(kFull, lsc[t], __ffs(bm) - 1);
+                    if (sca > sc) reject = true;
+                }
+            }
+        }
+        if (lane == 0) rej[j] = reject ? 1 : 0;
+        if (!reject) {
+            if (lane == 0) { sel[ns] = c; sel_s[ns] = sc; }
+            ++ns;
+        }
+        __syncwarp();
+    }
+    for (int j = 0; j < T && ns < m; ++j) {      // refill with the closest rejected candidates
+        if (rej[j]) {
+            if (lane == 0) { sel[ns] = cid[j]; sel_s[ns] = cs[j]; }
+            ++ns;
+        }
+    }
+    __syncwarp();
+    return ns;
+}
+
+// forward picks with the diversity heuristic (one warp per node) + reverse-buffer append
+__global__ void __launch_bounds__(256)
+select_forward_diverse_kernel(const float* __restrict__ knn_s, const int* __restrict__ knn_r, long long n_members, int kk,
+                              int m, int rcap, int* __restrict__ fwd, float* __restrict__ fwd_s, int* __restrict__ rev_cnt,
+                              int* __restrict__ rev, float* __restrict__ rev_s) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long u = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
+    if (u >= n_members) return;
+    const int per = kk * 9 + m * 8 + 16;                       // cid, cs, rej | sel, sel_s
+    unsigned char* base = smem_raw + (size_t)warp * ((per + 15) / 16 * 16);
+    int* cid = reinterpret_cast<int*>(base);
+    float* cs = reinterpret_cast<float*>(cid + kk);
+    int* sel = reinterpret_cast<int*>(cs + kk);
+    float* sel_s = reinterpret_cast<float*>(sel + m);
+    unsigned char* rej = reinterpret_cast<unsigned char*>(sel_s + m);
+    // compact the valid, non-self candidates (order preserved)
+    int T = 0;
+    for (int b0 = 0; b0 < kk; b0 += 32) {
+        const int i = b0 + lane;
+        const int v = i < kk ? knn_r[u * kk + i] : -1;
+        const bool ok = v >= 0 && v != (int)u;
+        const unsigned bm = __ballot_sync(kFull, ok);
+        if (ok) { const int at = T + __popc(bm & ((1u << lane) - 1u)); cid[at] = v; cs[at] = knn_s[u * kk + i]; }
+        T += __popc(bm);
+    }
+    __syncwarp();
+    const int ns = diverse_select(cid, cs, T, knn_r, knn_s, kk, m, sel, sel_s, rej, lane);
+    for (int i = lane; i < m; i += 32) {
+        const bool ok = i < ns;
+        fwd[u * m + i] = ok ? sel[i] : -1;
+        fwd_s[u * m + i] = ok ? sel_s[i] : VQ_NEG_INF;
+        if (ok) {
+            const int v = sel[i];
+            const int slot = atomicAdd(&rev_cnt[v], 1);
+            if (slot < rcap) { rev[(size_t)v * rcap + slot] = (int)u; rev_s[(size_t)v * rcap + slot] = sel_s[i]; }
+        }
+    }
+}
+
+// Final adjacency of a node (one thread per node): the first half of its diversity-ordered forward
+// picks, then the closest reverse edges (nodes that picked it) for the other half — this keeps
+// in-degrees up so that few nodes become unreachable — then whatever is left, never exceeding m.
+__global__ void __launch_bounds__(128)
+merge_fwd_rev_kernel(const int* __restrict__ fwd, const int* __restrict__ rev_cnt, const int* __restrict__ rev,
+                     const float* __restrict__ rev_s, long long n_members, int m, int rcap,
+                     const int* __restrict__ members, int* __restrict__ adj_out) {
+    const long long u = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= n_members) return;
+    int out[32];
+    int no = 0;
+    const int half = (m + 1) / 2;
+    auto has = [&](int v) { for (int i = 0; i < no; ++i) if (out[i] == v) return true; return false; };
+    for (int i = 0; i < half; ++i) { const int v = fwd[u * m + i]; if (v >= 0 && !has(v)) out[no++] = v; }
+    int nrev = rev_cnt[u];
+    nrev = nrev < rcap ? nrev : rcap;
+    const int* rv = rev + (size_t)u * rcap;
+    const float* rs = rev_s + (size_t)u * rcap;
+    // closest reverse edges first (selection by repeated max; ties by id for determinism)
+    float last_s = INFINITY; int last_id = -1;
+    int taken = 0;
+    while (no < m && taken < m / 2) {
+        float bs = VQ_NEG_INF; int bid = -1;
+        for (int j = 0; j < nrev; ++j) {
+            const float s = rs[j]; const int id = rv[j];
+            const bool after_last = (s < last_s) || (s == last_s && id > last_id);
+            if (after_last && (s > bs || (s == bs && id < bid) || bid < 0)) { bs = s; bid = id; }
+        }
+        if (bid < 0) break;
+        last_s = bs; last_id = bid;
+        if (!has(bid)) { out[no++] = bid; ++taken; }
+    }
+    for (int i = half; i < m && no < m; ++i) { const int v = fwd[u * m + i]; if (v >= 0 && !has(v)) out[no++] = v; }
+    // still room: remaining reverse edges in closeness order
+    while (no < m) {
+        float bs = VQ_NEG_INF; int bid = -1;
+        for (int j = 0; j < nrev; ++j) {
+            const float s = rs[j]; const int id = rv[j];
+            const bool after_last = (s < last_s) || (s == last_s && id > last_id);
+            if (after_last && (s > bs || (s == bs && id < bid) || bid < 0)) { bs = s; bid = id; }
+        }
+        if (bid < 0) break;
+        last_s = bs; last_id = bid;
+        if (!has(bid)) out[no++] = bid;
+    }
+    for (int i = 0; i < m; ++i) adj_out[u * m + i] = i < no ? (members ? members[out[i]] : out[i]) : -1;
+}
+
 inline size_t align256(size_t v) { return (v + 255) / 256 * 256; }
 inline int pow2_ge(int v) { int p = 1; while (p < v) p <<= 1; return p; }
 
@@ -455,10 +594,7 @@ int vq_hnsw_build_layer(const void* store, int64_t n, int dim, int ld, int store
     VQ_CHECK_ARG(n > 0 && n < (1 << 30) && dim > 0 && ld >= dim && ld % 32 == 0, "bad shape n=%lld dim=%d ld=%d", (long long)n, dim, ld);
     VQ_CHECK_ARG(n_members >= 0 && n_members <= n, "bad n_members %lld", (long long)n_members);
     VQ_CHECK_ARG(m_out > 0 && m_out <= 25 && k_cand > 0 && k_cand <= 512, "bad m_out/k_cand %d/%d", m_out, k_cand);
-    if (diversify != 0) {
-        vq_set_error("diversify=1 is not implemented yet (only the reference's closest-M selection)");
-        return VQ_EUNSUPPORTED;
-    }
+    VQ_CHECK_ARG(diversify == 0 || k_cand + 1 <= 96, "diversify needs k_cand <= 95 (got %d)", k_cand);
     if (n_members == 0) return VQ_OK;
     VQ_CHECK_ARG(store && adj_out && workspace, "NULL pointer argument");
     VQ_CHECK_ARG(((uintptr_t)workspace & 255) == 0, "workspace must be 256-byte aligned");
@@ -501,15 +637,27 @@ int vq_hnsw_build_layer(const void* store, int64_t n, int dim, int ld, int store
         q0 = start + bt;
     }
     VQ_CUDA(cudaMemsetAsync(ws + p.rev_cnt, 0, (size_t)n_members * 4, stream));
-    link_reverse_kernel<<<(unsigned)((n_members + 255) / 256), 256, 0, stream>>>(
-        knn_s, knn_r, n_members, p.kk, m_out, p.rcap, (int*)(ws + p.fwd), (float*)(ws + p.fwd_s), (int*)(ws + p.rev_cnt),
-        (int*)(ws + p.rev), (float*)(ws + p.rev_s));
-    VQ_LAUNCH_CHECK("link_reverse_kernel");
-    const size_t psmem = (size_t)8 * (m_out + p.rcap) * 8;
-    prune_kernel<<<(unsigned)((n_members + 7) / 8), 256, psmem, stream>>>(
-        (int*)(ws + p.fwd), (float*)(ws + p.fwd_s), (int*)(ws + p.rev_cnt), (int*)(ws + p.rev), (float*)(ws + p.rev_s),
-        n_members, m_out, p.rcap, members, adj_out);
-    VQ_LAUNCH_CHECK("prune_kernel");
+    if (diversify) {
+        const size_t per_f = ((size_t)p.kk * 9 + m_out * 8 + 16 + 15) / 16 * 16;
+        select_forward_diverse_kernel<<<(unsigned)((n_members + 7) / 8), 256, 8 * per_f, stream>>>(
+            knn_s, knn_r, n_members, p.kk, m_out, p.rcap, (int*)(ws + p.fwd), (float*)(ws + p.fwd_s),
+            (int*)(ws + p.rev_cnt), (int*)(ws + p.rev), (float*)(ws + p.rev_s));
+        VQ_LAUNCH_CHECK("select_forward_diverse_kernel");
+        merge_fwd_rev_kernel<<<(unsigned)((n_members + 127) / 128), 128, 0, stream>>>(
+            (int*)(ws + p.fwd), (int*)(ws + p.rev_cnt), (int*)(ws + p.rev), (float*)(ws + p.rev_s), n_members, m_out,
+            p.rcap, members, adj_out);
+        VQ_LAUNCH_CHECK("merge_fwd_rev_kernel");
+    } else {
+        link_reverse_kernel<<<(unsigned)((n_members + 255) / 256), 256, 0, stream>>>(
+            knn_s, knn_r, n_members, p.kk, m_out, p.rcap, (int*)(ws + p.fwd), (float*)(ws + p.fwd_s), (int*)(ws + p.rev_cnt),
+            (int*)(ws + p.rev), (float*)(ws + p.rev_s));
+        VQ_LAUNCH_CHECK("link_reverse_kernel");
+        const size_t psmem = (size_t)8 * (m_out + p.rcap) * 8;
+        prune_kernel<<<(unsigned)((n_members + 7) / 8), 256, psmem, stream>>>(
+            (int*)(ws + p.fwd), (float*)(ws + p.fwd_s), (int*)(ws + p.rev_cnt), (int*)(ws + p.rev), (float*)(ws + p.rev_s),
+            n_members, m_out, p.rcap, members, adj_out);
+        VQ_LAUNCH_CHECK("prune_kernel");
+    }
     vq_note_launch("hnsw_build_layer", launches + 2);
     return VQ_OK;
 }

@@ -58,7 +58,7 @@ class B200HNSWIndex:
     def __init__(self, dimension: int = 512, M: int = 16, ef_construction: int = 200, ef_search: int = 50,
                  max_M: int = 16, level_generation_factor: float = 1.0 / math.log(2.0), num_threads: int = 4,
                  use_numpy_optimization: bool = True, device=None, search_dtype: str = "fp32",
-                 rebuild_fraction: float = 0.10):
+                 rebuild_fraction: float = 0.10, select: str = "diverse", max_candidates: int = 64):
         self.dimension = dimension
         self.M = M
         self.max_M = max_M
@@ -69,6 +69,11 @@ class B200HNSWIndex:
         self.use_numpy_optimization = use_numpy_optimization
         self.search_dtype = "bf16" if search_dtype in ("bf16", "bfloat16") else "fp32"
         self.rebuild_fraction = float(rebuild_fraction)
+        # neighbour selection of the GPU builder: "closest" = the reference's plain closest-M
+        # (hnsw.py:123-148); "diverse" = the HNSW diversity heuristic that function is named after,
+        # over a candidate pool of min(ef_construction, max_candidates) exact nearest neighbours.
+        self.select = select
+        self.max_candidates = int(max_candidates)
 
         self.levels: Dict = {}               # id -> level (public in the reference)
         self.entry_point = None              # external id of the entry node
@@ -176,13 +181,15 @@ class B200HNSWIndex:
 
     def _build_layer(self, members, n_members: int, m_out: int, adj_out: torch.Tensor):
         st = self._store
-        # "closest M" selection (hnsw.py:123-148) only ever looks at the M nearest candidates, so the
-        # exact candidate pool is m_out wide; ef_construction bounds it like the reference's beam.
-        k_cand = min(max(m_out, 1), max(self.ef_construction, m_out))
+        if self.select == "closest":
+            # closest-M only ever looks at the M nearest candidates, so the exact pool is m_out wide
+            k_cand, div = m_out, 0
+        else:
+            k_cand, div = max(m_out, min(int(self.ef_construction), self.max_candidates, 95)), 1
         need = self.lib.vq_hnsw_layer_workspace_bytes(n_members, st.dim, st.ld, _lib.F32, k_cand, m_out)
         ws = self._bws.get(need)
         rc = self.lib.vq_hnsw_build_layer(_ptr(st.f32), st.n, st.dim, st.ld, _lib.F32, _ptr(members), n_members,
-                                          k_cand, m_out, 0, _ptr(adj_out), _ptr(ws), ws.numel(), _stream(self.device))
+                                          k_cand, m_out, div, _ptr(adj_out), _ptr(ws), ws.numel(), _stream(self.device))
         _lib.check(rc, "vq_hnsw_build_layer")
 
     def _ensure_graph(self):

@@ -74,11 +74,12 @@ class ShardedSearcher:
         if self.world == 1:
             gathered = packed[None]
         else:
-            shape = (self.world,) + tuple(packed.shape)
+            # flat (world*2, b, k) buffer: the concatenated form every backend accepts
+            shape = (self.world * packed.shape[0],) + tuple(packed.shape[1:])
             if self._gather_buf is None or tuple(self._gather_buf.shape) != shape or \
                     self._gather_buf.device != packed.device:
                 self._gather_buf = torch.empty(shape, dtype=torch.int32, device=packed.device)
             dist.all_gather_into_tensor(self._gather_buf, packed, group=self.group)
-            gathered = self._gather_buf
+            gathered = self._gather_buf.view((self.world,) + tuple(packed.shape))
         merge = self._merge or self._cuda_merge
         return merge(gathered, k)
