@@ -138,12 +138,16 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
-def _config(batch, gpus, path):
-    return {"workload": f"exact cosine top-{K_TOP}: {N_ROWS}x{DIM} fp32 frame store, query batch {batch} "
+def _config(batch, gpus, path, two_stage=False):
+    elem = 2 if two_stage else 4
+    return {"workload": f"exact cosine top-{K_TOP}: {N_ROWS}x{DIM} frame store, query batch {batch} "
                         f"(BASELINE config 2), row-sharded over {gpus} GPU(s)",
-            "n_rows": N_ROWS, "dim": DIM, "k": K_TOP, "batch": batch, "store_dtype": "fp32", "scan_path": path,
-            "l2": "store shard >= 256 MB > 126 MB L2, no flush needed between steps" if N_ROWS // gpus * DIM * 4 > 200e6
-                  else "store shard fits L2: a 256 MB buffer is written between timed steps",
+            "n_rows": N_ROWS, "dim": DIM, "k": K_TOP, "batch": batch,
+            "store_dtype": "fp32 master + bf16 scan copy (tensor-core scan selects 32 candidates, exact fp32 "
+                           "re-score, certified)" if two_stage else "fp32",
+            "scan_path": path,
+            "l2": "scanned shard > 300 MB > 126 MB L2, no flush needed between steps" if N_ROWS // gpus * DIM * elem > 300e6
+                  else "scanned shard could sit in L2: a 256 MB buffer is written between timed steps",
             "parallelism": f"rows/{gpus}"}
 
 
@@ -152,7 +156,7 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
     from video_quierer_b200 import _lib, engine
-    from video_quierer_b200.flat_index import B200FlatIndex  # noqa: F401  (public facade, used for e2e)
+    from video_quierer_b200.flat_index import exact_fallback, two_stage_search
     from video_quierer_b200.sharded import ShardedSearcher, shard_range
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -163,33 +167,34 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.load()
+    two_stage = args.mode == "exact2"
 
     # ---- synthetic store shard, generated on the device (S-gauss, fixed seed per 64k-row block)
     lo, hi = shard_range(N_ROWS, world, rank)
-    store = engine.DeviceStore(DIM, dev, keep_fp32=True, keep_bf16=False, capacity=hi - lo)
+    store = engine.DeviceStore(DIM, dev, keep_fp32=True, keep_bf16=two_stage, capacity=hi - lo)
     blk = 1 << 16
-    for b0 in range(lo // blk * blk, hi, blk):           # block b0 is the same on every rank layout
+    for b0 in range(lo // blk * blk, hi, blk):           # block b0 is the same whatever the sharding
         g = torch.Generator(device=dev).manual_seed(1000 + b0 // blk)
         x = torch.randn((blk, DIM), device=dev, generator=g)
         s, e = max(lo, b0), min(hi, b0 + blk)
         store.append(x[s - b0: e - b0], _lib.NORM_PLAIN)  # kernel (a): L2-normalise on ingest
     scanner = engine.Scanner(dev)
-    mat = store.view("fp32")
+    uncertified = torch.zeros((), dtype=torch.int64, device=dev)
+    elem = 2 if two_stage else 4
 
     def local_search(q, k):
-        return scanner.scan(mat, store.n, DIM, q, k, _lib.NORM_EPS, args.path)
+        if two_stage:
+            s, r, bad = two_stage_search(scanner, store, q, k, args.path)
+            if bad is not None:
+                uncertified.add_(bad.sum())
+            return s, r
+        return scanner.scan(store.f32, store.n, DIM, q, k, _lib.NORM_EPS, args.path)
 
     searcher = ShardedSearcher(local_search, N_ROWS, device=dev)
-    B = args.batch
     gq = torch.Generator(device="cpu").manual_seed(7)
-    host_q = torch.randn((B, DIM), generator=gq).pin_memory()
-    dev_q = host_q.to(dev)
     flush = None
-    if (hi - lo) * DIM * 4 <= 200e6:
+    if (hi - lo) * DIM * elem <= 300e6:
         flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-
-    def step_device():
-        return searcher.search(dev_q, K_TOP)
 
     def barrier():
         torch.cuda.synchronize()
@@ -197,27 +202,44 @@ def run_ours(args):
             dist.barrier()
             torch.cuda.synchronize()
 
-    for _ in range(max(args.warmup, 3)):
-        step_device()
-    launches_per_step = scanner.last_launches + 1          # + merge of the shard/merge layer
-    barrier()
-
-    # ---- timed region 1: device-resident inputs, CUDA events on the launch stream
-    lib.vq_profile_enable(1)
-    kern_ms = []
-    with ClockSampler(local) as clocks:
+    def measure(B, steps, warmup, with_e2e):
+        host_q = torch.randn((B, DIM), generator=gq).pin_memory()
+        dev_q = host_q.to(dev)
+        for _ in range(max(warmup, 3)):
+            searcher.search(dev_q, K_TOP)
+        launches = scanner.last_launches + (1 if world > 1 else 0)   # + merge of the shard/merge layer
+        path = scanner.last_path
         barrier()
+        # the serving path for a fixed batch shape: the whole step captured once as a CUDA graph
+        graphed = None
+        if not args.no_graph:
+            try:
+                from video_quierer_b200.graphs import GraphedSearch
+                graphed = GraphedSearch(lambda qq: searcher.search(qq, K_TOP), B, DIM, dev)
+                graphed.q.copy_(dev_q)
+            except Exception as e:  # noqa: BLE001 — e.g. a collective that refuses capture: run eagerly
+                print(f"[bench] CUDA graph capture unavailable ({type(e).__name__}: {e}); eager launches", file=sys.stderr)
+                graphed = None
+            barrier()
+
+        def step_device():
+            if graphed is not None:
+                graphed.graph.replay()
+                return graphed.out
+            return searcher.search(dev_q, K_TOP)
+
+        # -- timed region 1: device-resident queries, CUDA events on the launch stream
         if flush is None:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            for _ in range(args.steps):
+            for _ in range(steps):
                 step_device()
             e1.record()
             barrier()
             dev_ms = e0.elapsed_time(e1)
         else:
             dev_ms = 0.0
-            for _ in range(args.steps):
+            for _ in range(steps):
                 flush.zero_()
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
@@ -226,64 +248,107 @@ def run_ours(args):
                 torch.cuda.synchronize()
                 dev_ms += e0.elapsed_time(e1)
             barrier()
-        # dominant-kernel time: a second short loop reading the library's own events each step
-        for _ in range(min(args.steps, 20)):
+        # -- dominant kernel alone: the library's own events around the scan kernel
+        lib.vq_profile_enable(1)
+        kern = []
+        for _ in range(min(steps, 20)):
             if flush is not None:
                 flush.zero_()
-            step_device()
-            kern_ms.append(lib.vq_profile_last_kernel_ms())
-        kern = sorted(v for v in kern_ms if v is not None and v > 0)
+            scanner.scan(store.bf16 if two_stage else store.f32, store.n, DIM, dev_q,
+                         (32 if two_stage else K_TOP), _lib.NORM_EPS, args.path)
+            kern.append(lib.vq_profile_last_kernel_ms())
         lib.vq_profile_enable(0)
+        kern = sorted(v for v in kern if v > 0)
+        kmed = kern[len(kern) // 2] if kern else None
+        e2e_ms = None
+        if with_e2e:
+            # -- timed region 2: end to end with HOST (pinned) buffers: H2D + search + D2H (+ fallback)
+            out_rows = torch.empty((B, K_TOP), dtype=torch.int64).pin_memory()
+            out_scores = torch.empty((B, K_TOP), dtype=torch.float32).pin_memory()
+            flag = torch.zeros((), dtype=torch.int64).pin_memory()
 
-        # ---- timed region 2: end to end through the public facade with host buffers
-        out_rows = torch.empty((B, K_TOP), dtype=torch.int64).pin_memory()
-        out_scores = torch.empty((B, K_TOP), dtype=torch.float32).pin_memory()
+            def step_e2e():
+                uncertified.zero_()
+                if graphed is not None:
+                    s, r = graphed(host_q)                     # H2D of this step's inputs + one graph launch
+                    q = graphed.q
+                else:
+                    q = host_q.to(dev, non_blocking=True)      # H2D of this step's inputs
+                    s, r = searcher.search(q, K_TOP)
+                out_scores.copy_(s, non_blocking=True)         # D2H of the step's result
+                out_rows.copy_(r, non_blocking=True)
+                flag.copy_(uncertified, non_blocking=True)
+                torch.cuda.synchronize()
+                if int(flag) and world == 1:                   # never on this data; kept for correctness
+                    s2, r2, bad = two_stage_search(scanner, store, q, K_TOP, args.path)
+                    idx = torch.nonzero(bad).flatten()
+                    sf, rf = exact_fallback(scanner, store, q, K_TOP, idx)
+                    out_scores[idx.cpu()] = sf.cpu()
+                    out_rows[idx.cpu()] = rf.cpu().long()
 
-        def step_e2e():
-            q = host_q.to(dev, non_blocking=True)          # H2D of this step's inputs (pinned)
-            s, r = searcher.search(q, K_TOP)
-            out_scores.copy_(s, non_blocking=True)         # D2H of the step's result
-            out_rows.copy_(r, non_blocking=True)
-            torch.cuda.synchronize()
+            for _ in range(3):
+                step_e2e()
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(steps):
+                step_e2e()
+            barrier()
+            e2e_ms = (time.perf_counter() - t0) * 1e3
+        t = torch.tensor([dev_ms, e2e_ms or 0.0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dev_ms, e2e_ms = (float(v) for v in t.cpu())
+        return {"B": B, "dev_ms": dev_ms, "e2e_ms": e2e_ms, "kernel_ms": kmed, "launches": launches, "path": path,
+                "graph": graphed is not None}
 
-        for _ in range(3):
-            step_e2e()
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            step_e2e()
-        barrier()
-        e2e_s = time.perf_counter() - t0
-
-    t = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_ms, e2e_ms = (float(v) for v in t.cpu())
+    with ClockSampler(local) as clocks:
+        main = measure(args.batch, args.steps, args.warmup, True)
+        sweep = []
+        if not args.no_sweep:
+            for B in (1, 32, 1024):
+                if B != args.batch:
+                    sweep.append(measure(B, min(args.steps, 30), 3, False))
+    n_unc = int(uncertified.item())
 
     if rank == 0:
-        hbm_peak, _, peak_src = _peaks()
-        kmed = kern[len(kern) // 2] if kern else None
+        hbm_peak, tf_peak, peak_src = _peaks()
         n_local = hi - lo
-        scan_bytes = n_local * store.ld * 4 + min(B, 16) * DIM * 4 + min(B, 16) * K_TOP * 8
-        achieved = scan_bytes / (kmed * 1e-3) / 1e9 if kmed else None
-        cpu_qps, cores, sample, _ = cpu_reference(B, budget_s=12.0) if world == 1 and not args.no_cpu else (None, None, None, None)
+
+        def roof(m):
+            if m["kernel_ms"] is None:
+                return None
+            bytes_ = n_local * store.ld * elem + min(m["B"], 128) * DIM * elem
+            flops = 2.0 * m["B"] * n_local * DIM
+            gbs = bytes_ / (m["kernel_ms"] * 1e-3) / 1e9
+            tfs = flops / (m["kernel_ms"] * 1e-3) / 1e12
+            if two_stage and flops / bytes_ > tf_peak * 1e12 / (hbm_peak * 1e9):
+                return {"bound": "tensor", "achieved": tfs, "peak": tf_peak, "unit": "TFLOP/s", "frac": tfs / tf_peak,
+                        "traffic": None, "kernel": "scan_mma_bf16_kernel", "kernel_ms": m["kernel_ms"],
+                        "peak_source": peak_src + " (bf16 burst)", "algorithmic_flops": flops}
+            return {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
+                    "traffic": None, "kernel": "scan_mma_bf16_kernel" if two_stage else "scan_fma_kernel",
+                    "kernel_ms": m["kernel_ms"], "peak_source": peak_src + " (copy bandwidth)",
+                    "algorithmic_bytes": bytes_}
+
+        B = main["B"]
+        cpu = cpu_reference(B, budget_s=12.0) if world == 1 and not args.no_cpu else None
         line = {
-            "metric": METRIC, "value": B * args.steps / (dev_ms * 1e-3), "unit": "queries/s", "n_gpus": world,
-            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": dev_ms / args.steps,
-            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": _config(B, world, scanner.last_path),
+            "metric": METRIC, "value": B * args.steps / (main["dev_ms"] * 1e-3), "unit": "queries/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": main["dev_ms"] / args.steps,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "bf16 scan + f32 rescore" if two_stage else "f32", "data": "synthetic",
+            "config": dict(_config(B, world, main["path"], two_stage), launch="cuda-graph" if main["graph"] else "eager"),
             "clocks": clocks.summary(),
-            "e2e": {"value": B * args.steps / (e2e_ms * 1e-3), "unit": "queries/s",
-                    "h2d_bytes_per_step": B * DIM * 4, "d2h_bytes_per_step": B * K_TOP * 12},
-            "gpu_launches": launches_per_step * args.steps,
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": (achieved / hbm_peak) if achieved else None, "traffic": None,
-                         "kernel": scanner.last_path, "kernel_ms": kmed, "peak_source": peak_src,
-                         "algorithmic_bytes": scan_bytes,
-                         "note": "scan kernel of the first <=16-query pass; B>16 on the FMA path makes ceil(B/16) passes"},
+            "e2e": {"value": B * args.steps / (main["e2e_ms"] * 1e-3), "unit": "queries/s",
+                    "h2d_bytes_per_step": B * DIM * 4, "d2h_bytes_per_step": B * K_TOP * 12 + 8},
+            "gpu_launches": main["launches"] * args.steps,
+            "roofline": roof(main),
+            "uncertified_queries": n_unc,
+            "sweep": [{"batch": m["B"], "value": m["B"] * min(args.steps, 30) / (m["dev_ms"] * 1e-3),
+                       "ms_per_step": m["dev_ms"] / min(args.steps, 30), "roofline": roof(m)} for m in sweep],
         }
-        if cpu_qps is not None:
-            line["cpu_baseline"] = {"value": cpu_qps, "unit": "queries/s", "cores": cores, "kind": "port", "sample": sample}
+        if cpu is not None:
+            line["cpu_baseline"] = {"value": cpu[0], "unit": "queries/s", "cores": cpu[1], "kind": "port", "sample": cpu[2]}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
@@ -299,6 +364,10 @@ def main():
     ap.add_argument("--path", default="auto")
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-sweep", action="store_true", help="skip the batch 1/32/1024 sweep")
+    ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying a CUDA graph")
+    ap.add_argument("--mode", default="exact2", choices=["exact2", "fp32"],
+                    help="exact2: bf16 tensor scan + exact fp32 re-score (default); fp32: FMA scan of the fp32 store")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -107,10 +107,11 @@ int vq_topk_merge(const float* scores, const int32_t* rows, int g, int64_t g_str
  * re-scores them from the fp32 shadow store and keeps the best k).     [kernel: rescore_rows]
  *   cand_rows [b, k_cand] int32 (row < 0 ignored); queries [b, ld] fp32 *already normalised*
  *   and zero padded to the store's ld (i.e. the output of vq_ingest_rows on the queries)
- *   out_scores [b, k] fp32, out_rows [b, k] int32 */
+ *   out_scores [b, k] fp32, out_rows [b, k] int32; workspace >= b*k_cand*4 bytes */
 int vq_rescore_topk(const float* store_f32, int64_t n, int dim, int ld,
                     const float* queries, int b, const int32_t* cand_rows, int k_cand, int k,
-                    float* out_scores, int32_t* out_rows, void* stream);
+                    float* out_scores, int32_t* out_rows,
+                    void* workspace, size_t workspace_bytes, void* stream);
 
 /* (d) HNSW greedy/beam search, one warp per query.                     [kernel: hnsw_search]
  * Replaces: HNSWIndex.search / OptimizedHNSWIndex.search, src/indexes/hnsw.py:238-280,
@@ -123,14 +124,16 @@ int vq_rescore_topk(const float* store_f32, int64_t n, int dim, int ld,
  *   entry / max_level: entry point and its level;  ef = max(ef_search, k) like :264
  *   out_dist   [b, k] fp32 (1 - dot, ascending), out_rows [b, k] int32
  *   out_stats  optional [b, 4] uint32: distance evaluations, expanded nodes, visited-set
- *              overflow flag, reserved (feeds the gather-bandwidth roofline) */
+ *              overflow flag, reserved (feeds the gather-bandwidth roofline)
+ *   visited_capacity  slots of the per-query visited set (0 = 16*ef); a query whose set fills up
+ *              sets its overflow flag and should be re-run with a larger capacity */
 size_t vq_hnsw_workspace_bytes(int b, int ld, int ef);
 int vq_hnsw_search(const void* store, int64_t n, int dim, int ld, int store_dtype,
                    const int32_t* levels, const int32_t* adj0, int m0,
                    const int32_t* upper_off, const int32_t* upper_adj, int m,
                    int32_t entry, int max_level, int ef,
                    const float* queries, int b, int k, int query_norm,
-                   float* out_dist, int32_t* out_rows, uint32_t* out_stats,
+                   float* out_dist, int32_t* out_rows, uint32_t* out_stats, int visited_capacity,
                    void* workspace, size_t workspace_bytes, void* stream);
 
 /* HNSW construction on the GPU (the reference's per-insert Python build,

@@ -89,3 +89,12 @@ def topk_f64(store: np.ndarray, queries: np.ndarray, k: int):
     # deterministic tie rule of the new engine: score desc, row asc
     order = np.lexsort((np.arange(s.shape[1])[None, :].repeat(s.shape[0], 0), -s), axis=1)[:, :k]
     return order.astype(np.int64), np.take_along_axis(s, order, axis=1)
+
+
+def scan_prenormalised_f64(store: np.ndarray, queries: np.ndarray, k: int):
+    """float64 scores of queries used AS GIVEN (no normalisation) and their top-k under the
+    engine's (score desc, row asc) rule — ground truth for kernels fed pre-rounded operands."""
+    s = queries.astype(np.float64) @ store.astype(np.float64).T
+    k = min(k, s.shape[1])
+    order = np.lexsort((np.broadcast_to(np.arange(s.shape[1]), s.shape), -s), axis=1)[:, :k]
+    return order.astype(np.int64), np.take_along_axis(s, order, axis=1)

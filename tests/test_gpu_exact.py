@@ -177,3 +177,80 @@ def test_bf16_two_stage_rescore_is_exact(eng):
     s, r = idx.search_arrays(queries, 10)
     ro, so = exact.exact_search_batch(store, queries, 10)
     assert compare.check_topk_batch(r, s, ro, so) == []
+
+
+# ----------------------------------------------------------------------------- tcgen05 path
+def _bf16_round(a, torch):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(torch.bfloat16).to(torch.float32).numpy()
+
+
+@pytest.mark.parametrize("n,dim,b,k", [(128, 64, 1, 1), (1000, 128, 17, 10), (5000, 512, 32, 10), (20000, 512, 130, 10),
+                                       (4097, 256, 5, 32), (60000, 768, 300, 16), (777, 100, 3, 7)])
+def test_mma_path_vs_oracle_on_bf16_operands(eng, n, dim, b, k):
+    """tcgen05 scan: bf16 x bf16 products are exact and accumulate in fp32, so against the oracle
+    fed the same bf16-rounded operands the ids are identical and scores agree to ~1e-6."""
+    engine, _lib, torch = eng
+    store = _bf16_round(synth.gauss(n, dim, seed=21), torch)
+    q = synth.gauss(b, dim, seed=22)
+    q = _bf16_round(q, torch)
+    st = engine.DeviceStore(dim, keep_fp32=False, keep_bf16=True)
+    st.append(store)
+    sc = engine.Scanner()
+    s, r = sc.scan(st.view("bf16"), st.n, st.dim, engine.as_device_queries(q, dim, st.device), k, _lib.NORM_NONE, "mma")
+    torch.cuda.synchronize()
+    assert sc.last_path == "scan_mma_bf16"
+    ro, so = exact.scan_prenormalised_f64(store, q, k)
+    assert compare.check_topk_batch(r.cpu().numpy(), s.cpu().numpy(), ro, so) == []
+
+
+def test_mma_auto_dispatch_and_fp32_never_uses_tensor_path(eng):
+    engine, _lib, torch = eng
+    store = synth.gauss(3000, 128, seed=23)
+    st = engine.DeviceStore(128, keep_fp32=True, keep_bf16=True)
+    st.append(store)
+    sc = engine.Scanner()
+    q = engine.as_device_queries(store[:4], 128, st.device)
+    sc.scan(st.view("bf16"), st.n, 128, q, 10, _lib.NORM_EPS, "auto")
+    assert sc.last_path == "scan_mma_bf16"
+    sc.scan(st.view("fp32"), st.n, 128, q, 10, _lib.NORM_EPS, "auto")
+    assert sc.last_path == "scan_fma_f32"                 # parity: no silent tf32
+    sc.scan(st.view("bf16"), st.n, 128, q, 100, _lib.NORM_EPS, "auto")
+    assert sc.last_path == "scan_fma_bf16"                # k beyond the register lists falls back to FMA
+    with pytest.raises(_lib.VQError):
+        sc.scan(st.view("fp32"), st.n, 128, q, 10, _lib.NORM_EPS, "mma")
+
+
+@pytest.mark.parametrize("gen,n,b", [("gauss", 50000, 40), ("clip", 30000, 200)])
+def test_two_stage_certified_exact(eng, gen, n, b):
+    from video_quierer_b200.flat_index import B200FlatIndex
+    store = synth.gauss(n, 512, seed=31) if gen == "gauss" else synth.clip_like(n, 512, seed=31)
+    queries = np.random.default_rng(32).standard_normal((b, 512), dtype=np.float32) if gen == "gauss" \
+        else synth.clip_like(b, 512, seed=32, n_store=n)
+    idx = B200FlatIndex(store_dtype="bf16", rescore=True)
+    idx.add_frames(store, ["a.mp4"] * n, np.arange(n, dtype=float))
+    s, r = idx.search_arrays(queries, 10)
+    ro, so = exact.exact_search_batch(store, queries, 10)
+    assert compare.check_topk_batch(r, s, ro, so) == []
+    assert compare.id_match_fraction(r, ro) == 1.0
+    assert idx.stats["two_stage_queries"] == b
+    # clustered data packs near-duplicates tighter than the bf16 resolution now and then: those
+    # queries are answered by the exact fp32 path (the certificate is what makes the result exact)
+    assert idx.stats["uncertified_queries"] <= (0 if gen == "gauss" else b // 2)
+
+
+def test_two_stage_falls_back_when_it_cannot_certify(eng):
+    """Near-duplicate rows closer together than the bf16 resolution: the certificate fails and the
+    exact fp32 path answers, so the result is still exact."""
+    from video_quierer_b200.flat_index import B200FlatIndex
+    rng = np.random.default_rng(41)
+    base = synth.gauss(1, 256, seed=40)[0]
+    near = base[None, :] + 1e-4 * rng.standard_normal((500, 256)).astype(np.float32)
+    near /= np.linalg.norm(near, axis=1, keepdims=True)
+    store = np.concatenate([synth.gauss(4000, 256, seed=42), near.astype(np.float32)])
+    idx = B200FlatIndex(store_dtype="bf16", rescore=True)
+    idx.add_frames(store, ["a.mp4"] * len(store), np.arange(len(store), dtype=float))
+    q = np.stack([base, synth.gauss(1, 256, seed=43)[0]])
+    s, r = idx.search_arrays(q, 10)
+    ro, so = exact.exact_search_batch(store, q, 10)
+    assert compare.check_topk_batch(r, s, ro, so) == []
+    assert idx.stats["uncertified_queries"] >= 1

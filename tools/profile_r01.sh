@@ -1,0 +1,10 @@
+# ncu evidence for round 1 (one GPU).  Every profiled command first runs plainly and must exit 0.
+set -x
+B="python bench.py --steps 5 --warmup 3 --no-cpu --no-sweep"
+Q32="python tools/quick_bench.py --dtypes bf16 --paths mma --batches 32 --iters 2"
+Q1024="python tools/quick_bench.py --dtypes bf16 --paths mma --batches 1024 --iters 2"
+$B > gpurun_out/plain_bench.log 2>&1 && $Q32 > gpurun_out/plain_q32.log 2>&1 && $Q1024 > gpurun_out/plain_q1024.log 2>&1 && \
+ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r01_launches_bench.csv $B > gpurun_out/ncu_bench.log 2>&1 ; \
+ncu --set full --clock-control none --import-source on -k regex:scan_mma -s 3 -c 1 -o gpurun_out/r01_scan_mma_b32 $Q32 > gpurun_out/ncu_q32.log 2>&1 ; \
+ncu --set full --clock-control none --import-source on -k regex:scan_mma -s 3 -c 1 -o gpurun_out/r01_scan_mma_b1024 $Q1024 > gpurun_out/ncu_q1024.log 2>&1
+ls -la gpurun_out/

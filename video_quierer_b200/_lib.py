@@ -31,10 +31,10 @@ SIGNATURES = {
     "vq_topk_merge": (_i32, [_vp, _vp, _i32, _i64, _i32, _i32, _vp, _i32, _vp, _vp, _vp]),
     "vq_profile_enable": (_i32, [_i32]),
     "vq_profile_last_kernel_ms": (C.c_float, []),
-    "vq_rescore_topk": (_i32, [_vp, _i64, _i32, _i32, _vp, _i32, _vp, _i32, _i32, _vp, _vp, _vp]),
+    "vq_rescore_topk": (_i32, [_vp, _i64, _i32, _i32, _vp, _i32, _vp, _i32, _i32, _vp, _vp, _vp, _sz, _vp]),
     "vq_hnsw_workspace_bytes": (_sz, [_i32, _i32, _i32]),
     "vq_hnsw_search": (_i32, [_vp, _i64, _i32, _i32, _i32, _vp, _vp, _i32, _vp, _vp, _i32, _i32, _i32, _i32,
-                              _vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _sz, _vp]),
+                              _vp, _i32, _i32, _i32, _vp, _vp, _vp, _i32, _vp, _sz, _vp]),
     "vq_hnsw_layer_workspace_bytes": (_sz, [_i64, _i32, _i32, _i32, _i32, _i32]),
     "vq_hnsw_build_layer": (_i32, [_vp, _i64, _i32, _i32, _i32, _vp, _i64, _i32, _i32, _i32, _vp, _vp, _sz, _vp]),
 }

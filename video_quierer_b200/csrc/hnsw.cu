@@ -31,12 +31,16 @@ int vq_topk_merge_launch(const float* scores, const int* rows, int g, long long 
                          int rows64, int negate_out, cudaStream_t stream);
 int vq_ingest_launch(const float* src, long long rows, int dim, int src_ld, void* dst, int dst_dtype,
                      int dst_ld, int mode, cudaStream_t stream);
+bool vq_scan_mma_supported(int64_t n, int dim, int ld, int store_dtype, int b, int k);
+size_t vq_scan_mma_prepared_workspace(int64_t n, int ld, int b, int k);
+int vq_scan_mma_prepared(const void* store, int64_t n, int ld, const void* qbf, int b, int k, float* out_scores,
+                         int32_t* out_rows, void* ws, size_t ws_bytes, cudaStream_t stream);
 
 namespace {
 
 constexpr unsigned kFull = 0xffffffffu;
 constexpr int kExpanded = 0x40000000;      // flag bit on list ids (node ids are < 2^30)
-constexpr int kLogCap = 1024;              // visited-slot log (per-layer reset without a full clear)
+constexpr int kLogCap = 512;               // visited-slot log (per-layer reset without a full clear)
 
 struct WarpState {
     float* q;        // [ld]
@@ -114,7 +118,7 @@ __device__ __forceinline__ float row_dot_8lanes(const unsigned char* row, const 
 }
 
 template <bool BF16>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(128)
 hnsw_search_kernel(const void* __restrict__ store_v, int ld,
                    const int* __restrict__ adj0, int m0,
                    const int* __restrict__ upper_off, const int* __restrict__ upper_adj, int m,
@@ -316,15 +320,15 @@ prune_kernel(const int* __restrict__ fwd, const float* __restrict__ fwd_s, const
     for (int i = lane; i < m; i += 32) adj_out[u * m + i] = -1;
     __syncwarp();
     // pass 1: drop later copies of an id (an edge can be both a forward pick and a reverse add)
-    bool dupf[4] = {false, false, false, false};
-    for (int e = lane, t = 0; e < total && t < 4; e += 32, ++t) {
+    bool dupf[8] = {false, false, false, false, false, false, false, false};
+    for (int e = lane, t = 0; e < total && t < 8; e += 32, ++t) {
         const int id = ci[e];
         if (id < 0) continue;
         for (int f = 0; f < e; ++f)
             if (ci[f] == id) { dupf[t] = true; break; }
     }
     __syncwarp();
-    for (int e = lane, t = 0; e < total && t < 4; e += 32, ++t)
+    for (int e = lane, t = 0; e < total && t < 8; e += 32, ++t)
         if (dupf[t]) ci[e] = -1;
     __syncwarp();
     // pass 2: rank by (score desc, id asc) and keep the closest m
@@ -433,8 +437,11 @@ select_forward_diverse_kernel(const float* __restrict__ knn_s, const int* __rest
 }
 
 // Final adjacency of a node (one thread per node): the first half of its diversity-ordered forward
-// picks, then the closest reverse edges (nodes that picked it) for the other half — this keeps
-// in-degrees up so that few nodes become unreachable — then whatever is left, never exceeding m.
+// picks, then reverse edges (nodes that picked it) for the other half, then whatever is left, never
+// exceeding m.  Reverse candidates that hardly anybody links to (forward in-degree < kLowIn: the
+// "anti-hubs" of high-dimensional data, which a plain closest-M rule leaves unreachable) are
+// served first, closest first; the rest follow in closeness order.
+constexpr int kLowIn = 4;
 __global__ void __launch_bounds__(128)
 merge_fwd_rev_kernel(const int* __restrict__ fwd, const int* __restrict__ rev_cnt, const int* __restrict__ rev,
                      const float* __restrict__ rev_s, long long n_members, int m, int rcap,
@@ -450,32 +457,37 @@ merge_fwd_rev_kernel(const int* __restrict__ fwd, const int* __restrict__ rev_cn
     nrev = nrev < rcap ? nrev : rcap;
     const int* rv = rev + (size_t)u * rcap;
     const float* rs = rev_s + (size_t)u * rcap;
-    // closest reverse edges first (selection by repeated max; ties by id for determinism)
-    float last_s = INFINITY; int last_id = -1;
-    int taken = 0;
-    while (no < m && taken < m / 2) {
-        float bs = VQ_NEG_INF; int bid = -1;
+    // next reverse candidate after (last_s, last_id) in (score desc, id asc) order, restricted to a class
+    auto next_rev = [&](float last_s, int last_id, int want_low, float& bs, int& bid) {
+        bs = VQ_NEG_INF; bid = -1;
         for (int j = 0; j < nrev; ++j) {
             const float s = rs[j]; const int id = rv[j];
+            if (want_low >= 0 && (int)(rev_cnt[id] < kLowIn) != want_low) continue;
             const bool after_last = (s < last_s) || (s == last_s && id > last_id);
-            if (after_last && (s > bs || (s == bs && id < bid) || bid < 0)) { bs = s; bid = id; }
+            if (after_last && (bid < 0 || s > bs || (s == bs && id < bid))) { bs = s; bid = id; }
         }
-        if (bid < 0) break;
-        last_s = bs; last_id = bid;
-        if (!has(bid)) { out[no++] = bid; ++taken; }
+    };
+    int taken = 0;
+    for (int cls = 1; cls >= 0; --cls) {                 // rarely-linked nodes first, then the others
+        float last_s = INFINITY; int last_id = -1;
+        while (no < m && taken < m / 2) {
+            float bs; int bid;
+            next_rev(last_s, last_id, cls, bs, bid);
+            if (bid < 0) break;
+            last_s = bs; last_id = bid;
+            if (!has(bid)) { out[no++] = bid; ++taken; }
+        }
     }
     for (int i = half; i < m && no < m; ++i) { const int v = fwd[u * m + i]; if (v >= 0 && !has(v)) out[no++] = v; }
-    // still room: remaining reverse edges in closeness order
-    while (no < m) {
-        float bs = VQ_NEG_INF; int bid = -1;
-        for (int j = 0; j < nrev; ++j) {
-            const float s = rs[j]; const int id = rv[j];
-            const bool after_last = (s < last_s) || (s == last_s && id > last_id);
-            if (after_last && (s > bs || (s == bs && id < bid) || bid < 0)) { bs = s; bid = id; }
+    {   // still room: remaining reverse edges in closeness order
+        float last_s = INFINITY; int last_id = -1;
+        while (no < m) {
+            float bs; int bid;
+            next_rev(last_s, last_id, -1, bs, bid);
+            if (bid < 0) break;
+            last_s = bs; last_id = bid;
+            if (!has(bid)) out[no++] = bid;
         }
-        if (bid < 0) break;
-        last_s = bs; last_id = bid;
-        if (!has(bid)) out[no++] = bid;
     }
     for (int i = 0; i < m; ++i) adj_out[u * m + i] = i < no ? (members ? members[out[i]] : out[i]) : -1;
 }
@@ -484,12 +496,16 @@ inline size_t align256(size_t v) { return (v + 255) / 256 * 256; }
 inline int pow2_ge(int v) { int p = 1; while (p < v) p <<= 1; return p; }
 
 struct SearchPlan { int cap, warp_bytes, warps; size_t smem; };
-SearchPlan plan_search(int ld, int ef) {
+SearchPlan plan_search(int ld, int ef, int visited_capacity) {
     SearchPlan p;
-    p.cap = pow2_ge(ef * 24 < 1024 ? 1024 : ef * 24);
+    // visited set: 16 slots per beam entry covers the evaluations of a typical query with room to
+    // spare (measured 4-9 evaluations per beam entry); a query that does fill it reports overflow
+    // and is re-run by the caller with a larger table, so the common case keeps its occupancy.
+    int want = visited_capacity > 0 ? visited_capacity : (ef * 16 < 1024 ? 1024 : ef * 16);
+    p.cap = pow2_ge(want);
     if (p.cap > 32768) p.cap = 32768;
     p.warp_bytes = (int)align256((size_t)ld * 4 + (size_t)ef * 8 + (size_t)p.cap * 4 + 32 * 8 + kLogCap * 2);
-    p.warps = 8;
+    p.warps = 4;
     while (p.warps > 1 && (size_t)p.warps * p.warp_bytes > 200 * 1024) p.warps >>= 1;
     p.smem = (size_t)p.warps * p.warp_bytes;
     return p;
@@ -507,8 +523,8 @@ size_t vq_hnsw_workspace_bytes(int b, int ld, int ef) {
 int vq_hnsw_search(const void* store, int64_t n, int dim, int ld, int store_dtype, const int32_t* levels,
                    const int32_t* adj0, int m0, const int32_t* upper_off, const int32_t* upper_adj, int m,
                    int32_t entry, int max_level, int ef, const float* queries, int b, int k, int query_norm,
-                   float* out_dist, int32_t* out_rows, uint32_t* out_stats, void* workspace, size_t workspace_bytes,
-                   void* stream_v) {
+                   float* out_dist, int32_t* out_rows, uint32_t* out_stats, int visited_capacity, void* workspace,
+                   size_t workspace_bytes, void* stream_v) {
     (void)levels;
     cudaStream_t stream = (cudaStream_t)stream_v;
     VQ_CHECK_ARG(store_dtype == VQ_F32 || store_dtype == VQ_BF16, "bad store_dtype %d", store_dtype);
@@ -530,7 +546,7 @@ int vq_hnsw_search(const void* store, int64_t n, int dim, int ld, int store_dtyp
     float* qn = (float*)workspace;
     int rc = vq_ingest_launch(queries, b, dim, dim, qn, VQ_F32, ld, query_norm, stream);
     if (rc) return rc;
-    const SearchPlan p = plan_search(ld, ef);
+    const SearchPlan p = plan_search(ld, ef, visited_capacity);
     if ((size_t)p.warp_bytes > 200 * 1024) {
         vq_set_error("hnsw_search: per-query shared memory %d B too large (ld=%d ef=%d)", p.warp_bytes, ld, ef);
         return VQ_EUNSUPPORTED;
@@ -555,18 +571,19 @@ int vq_hnsw_search(const void* store, int64_t n, int dim, int ld, int store_dtyp
 }
 
 // workspace layout of one layer build
+constexpr int kBuildQB = 2048;      // queries per tensor-core k-nearest pass (16 query tiles)
 struct BuildPlan {
     int kk, rcap, grid;
-    size_t compact, knn_s, knn_r, part_s, part_r, fwd, fwd_s, rev_cnt, rev, rev_s, total;
+    size_t compact, knn_s, knn_r, part_s, part_r, fwd, fwd_s, rev_cnt, rev, rev_s, qpad, mma_ws, mma_ws_bytes, total;
 };
-static BuildPlan plan_build(int64_t n_members, int ld, int k_cand, int m_out, bool need_compact) {
+static BuildPlan plan_build(int64_t n_members, int ld, int k_cand, int m_out, bool need_compact, int elem = 4) {
     BuildPlan p;
     p.kk = (k_cand > m_out ? k_cand : m_out) + 1;           // +1: the node itself is its own nearest
-    p.rcap = 4 * m_out;
+    p.rcap = 8 * m_out;
     p.grid = vq_scan_fma_grid((int)n_members, 16);
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off += align256(bytes); return o; };
-    p.compact = take(need_compact ? (size_t)n_members * ld * 4 : 0);
+    p.compact = take(need_compact ? (size_t)n_members * ld * elem : 0);
     p.knn_s = take((size_t)n_members * p.kk * 4);
     p.knn_r = take((size_t)n_members * p.kk * 4);
     p.part_s = take((size_t)p.grid * 16 * p.kk * 4);
@@ -576,22 +593,26 @@ static BuildPlan plan_build(int64_t n_members, int ld, int k_cand, int m_out, bo
     p.rev_cnt = take((size_t)n_members * 4);
     p.rev = take((size_t)n_members * p.rcap * 4);
     p.rev_s = take((size_t)n_members * p.rcap * 4);
+    p.qpad = take(elem == 2 ? (size_t)kBuildQB * ld * 2 : 0);
+    p.mma_ws_bytes = elem == 2 ? vq_scan_mma_prepared_workspace(n_members, ld, kBuildQB, p.kk) : 0;
+    p.mma_ws = take(p.mma_ws_bytes);
     p.total = off + 256;
     return p;
 }
 
 size_t vq_hnsw_layer_workspace_bytes(int64_t n_members, int dim, int ld, int store_dtype, int k_cand, int m_out) {
-    (void)dim; (void)store_dtype;
+    (void)dim;
     if (n_members <= 0) return 256;
-    return plan_build(n_members, ld, k_cand, m_out, true).total;
+    return plan_build(n_members, ld, k_cand, m_out, true, store_dtype == VQ_BF16 ? 2 : 4).total;
 }
 
 int vq_hnsw_build_layer(const void* store, int64_t n, int dim, int ld, int store_dtype, const int32_t* members,
                         int64_t n_members, int k_cand, int m_out, int diversify, int32_t* adj_out, void* workspace,
                         size_t workspace_bytes, void* stream_v) {
     cudaStream_t stream = (cudaStream_t)stream_v;
-    VQ_CHECK_ARG(store_dtype == VQ_F32, "hnsw_build_layer needs the fp32 store (got dtype %d)", store_dtype);
-    VQ_CHECK_ARG(n > 0 && n < (1 << 30) && dim > 0 && ld >= dim && ld % 32 == 0, "bad shape n=%lld dim=%d ld=%d", (long long)n, dim, ld);
+    VQ_CHECK_ARG(store_dtype == VQ_F32 || store_dtype == VQ_BF16, "bad store dtype %d", store_dtype);
+    const bool bf = store_dtype == VQ_BF16;
+    VQ_CHECK_ARG(n > 0 && n < (1 << 30) && dim > 0 && ld >= dim && ld % (bf ? 64 : 32) == 0, "bad shape n=%lld dim=%d ld=%d", (long long)n, dim, ld);
     VQ_CHECK_ARG(n_members >= 0 && n_members <= n, "bad n_members %lld", (long long)n_members);
     VQ_CHECK_ARG(m_out > 0 && m_out <= 25 && k_cand > 0 && k_cand <= 512, "bad m_out/k_cand %d/%d", m_out, k_cand);
     VQ_CHECK_ARG(diversify == 0 || k_cand + 1 <= 96, "diversify needs k_cand <= 95 (got %d)", k_cand);
@@ -599,7 +620,13 @@ int vq_hnsw_build_layer(const void* store, int64_t n, int dim, int ld, int store
     VQ_CHECK_ARG(store && adj_out && workspace, "NULL pointer argument");
     VQ_CHECK_ARG(((uintptr_t)workspace & 255) == 0, "workspace must be 256-byte aligned");
     const bool compact = members != nullptr;
-    const BuildPlan p = plan_build(n_members, ld, k_cand, m_out, true);
+    const BuildPlan p = plan_build(n_members, ld, k_cand, m_out, true, bf ? 2 : 4);
+    // tensor-core k-nearest pass needs the bf16 store and lists that fit the register top-k
+    const bool use_mma = bf && vq_scan_mma_supported(n_members, dim, ld, VQ_BF16, kBuildQB, p.kk);
+    if (bf && !use_mma) {
+        vq_set_error("hnsw_build_layer: bf16 store needs ld <= 768 and k_cand <= 63 (ld=%d k_cand=%d)", ld, k_cand);
+        return VQ_EUNSUPPORTED;
+    }
     if (workspace_bytes < p.total) {
         vq_set_error("hnsw build workspace too small: %zu < %zu", workspace_bytes, p.total);
         return VQ_EWORKSPACE;
@@ -608,7 +635,7 @@ int vq_hnsw_build_layer(const void* store, int64_t n, int dim, int ld, int store
     const float* mat = (const float*)store;
     int launches = 0;
     if (compact) {
-        const int row_vec = ld / 4;
+        const int row_vec = ld * (bf ? 2 : 4) / 16;
         const long long items = (long long)n_members * row_vec;
         gather_rows_kernel<<<(unsigned)((items + 255) / 256), 256, 0, stream>>>((const uint4*)store, members, n_members,
                                                                               row_vec, (uint4*)(ws + p.compact));
@@ -621,6 +648,23 @@ int vq_hnsw_build_layer(const void* store, int64_t n, int dim, int ld, int store
     // exact k-nearest members of every member: the rows themselves are the (already unit-norm,
     // zero-padded) query tiles, 16 per pass of the fused scan + top-k kernel.
     const int nm = (int)n_members;
+    if (use_mma) {
+        // bf16 rows are their own unit-norm, zero-padded query tiles: 2048 queries per tensor-core pass
+        const unsigned char* matb = (const unsigned char*)mat;
+        for (int q0 = 0; q0 < nm; q0 += kBuildQB) {
+            const int bq = nm - q0 < kBuildQB ? nm - q0 : kBuildQB;
+            const void* qptr = matb + (size_t)q0 * ld * 2;
+            if (bq % 128 != 0) {                               // ragged tail: copy into a zero-padded tile
+                VQ_CUDA(cudaMemsetAsync(ws + p.qpad, 0, (size_t)kBuildQB * ld * 2, stream));
+                VQ_CUDA(cudaMemcpyAsync(ws + p.qpad, qptr, (size_t)bq * ld * 2, cudaMemcpyDeviceToDevice, stream));
+                qptr = ws + p.qpad;
+            }
+            int rc = vq_scan_mma_prepared(mat, nm, ld, qptr, bq, p.kk, knn_s + (size_t)q0 * p.kk, knn_r + (size_t)q0 * p.kk,
+                                          ws + p.mma_ws, p.mma_ws_bytes, stream);
+            if (rc) return rc;
+            launches += 3;
+        }
+    } else
     for (int q0 = 0; q0 < nm;) {
         int bt, start;
         if (nm - q0 >= 16) { bt = 16; start = q0; }

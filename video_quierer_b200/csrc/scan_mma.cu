@@ -4,23 +4,32 @@
 // Replaces the reference's per-query np.dot + argsort (video_search_overhaul.py:53,56 looped by
 // src/api/routes.py:627-634) when the query batch makes the scan a dense contraction.
 //
-// Orientation: D[query, row] = Q[query, :] . S[row, :]  with  A = 128 queries (UMMA M = 128),
-// B = 128 store rows (UMMA N = 128), both K-major, 128-byte swizzle.  After tcgen05.ld every
+// Orientation: D[query, row] = Q[query, :] . S[row, :]  with  A = 128 queries (UMMA M = 128) and
+// B = NT store rows (UMMA N = NT, K-major, 128-byte swizzle).  The query tile never changes while
+// a CTA lives, so it is written ONCE into tensor memory (tcgen05.st, packed bf16 pairs, lane =
+// query) and every MMA takes its A operand from TMEM: shared memory carries only the streamed
+// store tiles (deep TMA ring, half the smem operand traffic per MMA).  After tcgen05.ld every
 // epilogue thread owns ONE query (its TMEM lane) and sees the scores of 32 store rows at a time in
-// registers: the running k-th best is a per-thread register, the top-k list is a private column
-// of shared memory, no cross-thread traffic, and the scores never leave the SM.
+// registers: the running k-th best and the top-k list are registers of that thread, so there is
+// no cross-thread traffic and the scores never leave the SM.  The k-th best of every query is also
+// shared between CTAs through a global array (atomic max), so a row is dropped as soon as ANY CTA
+// has k better ones — insertions fall from ~k*ln(rows per CTA) per CTA to ~k*ln(N) in total.
 //
+// TMEM (512 columns): [0, 2*NT) two fp32 accumulators (MMA of tile i+1 overlaps the epilogue of
+// tile i), [2*NT, 2*NT + ld/2) the resident query tile.
 // Warp roles (256 threads, 1 CTA / SM):
-//   warp 0   TMA producer  : query tile once (resident for the whole kernel), then the store
-//                            tiles k-block by k-block through a `stages`-deep mbarrier ring
+//   warp 0   TMA producer  : store tiles k-block by k-block through a `stages`-deep mbarrier ring
 //   warp 1   MMA issuer    : one thread, 4 x tcgen05.mma (K = 16) per k-block, tcgen05.commit
 //                            frees the smem slot / publishes the accumulator
-//   warp 2   TMEM allocator: 256 columns = two 128-column accumulators (MMA of tile i+1 overlaps
-//                            the top-k epilogue of tile i)
-//   warps 4-7 epilogue     : tcgen05.ld 32x32b.x32, threshold filter, insertion into the list
+//   warp 2   TMEM allocator
+//   warps 4-7 epilogue     : load the query tile into TMEM, then per tile tcgen05.ld 32x32b.x32,
+//                            branch-free threshold filter, register insertion
 // Grid: persistent, gridDim = groups * n_qt; CTA c serves query tile c % n_qt and the store tiles
 // c / n_qt, + groups, ... ; it writes one k-entry list per query, `topk_merge` reduces them.
 #include <cuda.h>
+#include <stdlib.h>
+
+#include <mutex>
 
 #include "vq_common.cuh"
 
@@ -33,13 +42,10 @@ int vq_ingest_launch(const float* src, long long rows, int dim, int src_ld, void
 namespace {
 
 constexpr int QT = 128;                 // queries per tile   (UMMA M)
-constexpr int NT = 128;                 // store rows per tile (UMMA N)
 constexpr int KB_ELEMS = 64;            // bf16 per k-block = one 128-byte swizzle span
-constexpr int A_KB_BYTES = QT * 128;    // 16 KB
-constexpr int B_KB_BYTES = NT * 128;    // 16 KB
-constexpr int TMEM_COLS = 2 * NT;       // double-buffered fp32 accumulator
+constexpr int TMEM_COLS = 512;          // whole tensor memory: 2 accumulators + resident query tile
 constexpr int kThreads = 256;
-constexpr int kMaxK = 32;
+constexpr int kMaxK = 64;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -84,17 +90,33 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
     d |= (uint64_t)2 << 61;                               // SWIZZLE_128B
     return d;
 }
-// kind::f16 instruction descriptor: bf16 x bf16 -> fp32, both operands K-major, M = 128, N = NT
-__device__ __forceinline__ uint32_t umma_idesc_bf16() {
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NT >> 3) << 17) | ((uint32_t)(QT >> 4) << 24);
+// kind::f16 instruction descriptor: bf16 x bf16 -> fp32, both operands K-major, M = 128, N = nt
+__device__ __forceinline__ uint32_t umma_idesc_bf16(int nt) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(nt >> 3) << 17) | ((uint32_t)(QT >> 4) << 24);
 }
-__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+// D[tmem] (+)= A[tmem] * B[smem]   (A operand resident in tensor memory)
+__device__ __forceinline__ void umma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
     asm volatile(
         "{\n\t"
         ".reg .pred p;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
-        "}" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+        "}" ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+        ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]),
+          "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]),
+          "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]),
+          "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
+        : "memory");
+}
+__device__ __forceinline__ void atomic_max_float(float* addr, float v) {
+    if (v >= 0.f) atomicMax(reinterpret_cast<int*>(addr), __float_as_int(v));
+    else atomicMin(reinterpret_cast<unsigned*>(addr), __float_as_uint(v));
 }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -112,17 +134,19 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+template <int KL, int NT>
 __global__ void __launch_bounds__(kThreads, 1)
-scan_mma_bf16_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmS,
-                     int n, int nkb, int n_qt, int k, int stages, int b_pad,
-                     float* __restrict__ part_s, int* __restrict__ part_r) {
+scan_mma_bf16_kernel(const __grid_constant__ CUtensorMap tmS,
+                     const __nv_bfloat16* __restrict__ qbf,   // [b_pad, ld] normalised, zero padded
+                     float* __restrict__ gtau,                // [b_pad] shared k-th best per query (-inf initialised)
+                     int n, int ld, int nkb, int n_qt, int k, int stages, int b_pad,
+                     float* __restrict__ part_s, int* __restrict__ part_r, int dbg) {
+    constexpr int B_KB_BYTES = NT * 128;
+    constexpr uint32_t A_COL0 = 2 * NT;                         // first TMEM column of the query tile
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    unsigned char* sA = smem;                                   // nkb k-blocks of the query tile
-    unsigned char* sB = sA + (size_t)nkb * A_KB_BYTES;          // ring of store-tile k-blocks
-    float* ls = reinterpret_cast<float*>(sB + (size_t)stages * B_KB_BYTES);   // [k][128]
-    int* lr = reinterpret_cast<int*>(ls + k * QT);                           // [k][128]
-    uint64_t* full = reinterpret_cast<uint64_t*>(lr + k * QT);
+    unsigned char* sB = smem;                                   // ring of store-tile k-blocks
+    uint64_t* full = reinterpret_cast<uint64_t*>(sB + (size_t)stages * B_KB_BYTES);
     uint64_t* empty = full + stages;
     uint64_t* a_full = empty + stages;
     uint64_t* tmem_full = a_full + 1;      // [2]
@@ -133,13 +157,10 @@ scan_mma_bf16_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     const int q_tile = blockIdx.x % n_qt, group = blockIdx.x / n_qt, n_groups = gridDim.x / n_qt;
     const int n_tiles = (n + NT - 1) / NT;
 
-    if (warp == 0 && lane == 0) {
-        tma_prefetch_desc(&tmQ);
-        tma_prefetch_desc(&tmS);
-    }
+    if (warp == 0 && lane == 0) tma_prefetch_desc(&tmS);
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-        mbar_init(a_full, 1);
+        mbar_init(a_full, 4);
         for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -148,10 +169,6 @@ scan_mma_bf16_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "r"((uint32_t)TMEM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    if (warp >= 4) {
-        const int t = threadIdx.x - 128;
-        for (int i = 0; i < k; ++i) { ls[i * QT + t] = VQ_NEG_INF; lr[i * QT + t] = VQ_EMPTY_ROW; }
-    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -159,22 +176,24 @@ scan_mma_bf16_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
 
     if (warp == 0) {
         if (lane == 0) {
-            mbar_expect_tx(a_full, (uint32_t)nkb * A_KB_BYTES);
-            for (int kb = 0; kb < nkb; ++kb) tma_load_2d(sA + (size_t)kb * A_KB_BYTES, &tmQ, a_full, kb * KB_ELEMS, q_tile * QT);
             int stage = 0; uint32_t phase = 0;
             for (int tile = group; tile < n_tiles; tile += n_groups) {
                 for (int kb = 0; kb < nkb; ++kb) {
                     mbar_wait(&empty[stage], phase ^ 1);
-                    mbar_expect_tx(&full[stage], B_KB_BYTES);
-                    tma_load_2d(sB + (size_t)stage * B_KB_BYTES, &tmS, &full[stage], kb * KB_ELEMS, tile * NT);
+                    if (dbg & 2) { mbar_arrive(&full[stage]); }
+                    else {
+                        mbar_expect_tx(&full[stage], B_KB_BYTES);
+                        tma_load_2d(sB + (size_t)stage * B_KB_BYTES, &tmS, &full[stage], kb * KB_ELEMS, tile * NT);
+                    }
                     if (++stage == stages) { stage = 0; phase ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
-            const uint32_t idesc = umma_idesc_bf16();
-            mbar_wait(a_full, 0);
+            const uint32_t idesc = umma_idesc_bf16(NT);
+            mbar_wait(a_full, 0);                          // query tile is in tensor memory
+            tc_fence_after();
             int stage = 0; uint32_t phase = 0; int it = 0;
             for (int tile = group; tile < n_tiles; tile += n_groups, ++it) {
                 const int acc = it & 1;
@@ -185,13 +204,12 @@ scan_mma_bf16_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
                 for (int kb = 0; kb < nkb; ++kb) {
                     mbar_wait(&full[stage], phase);
                     tc_fence_after();
-                    const uint32_t a_addr = smem_u32(sA + (size_t)kb * A_KB_BYTES);
                     const uint32_t b_addr = smem_u32(sB + (size_t)stage * B_KB_BYTES);
+                    const uint32_t a_tmem = tmem_base + A_COL0 + (uint32_t)kb * (KB_ELEMS / 2);
 #pragma unroll
                     for (int k4 = 0; k4 < KB_ELEMS / 16; ++k4) {
-                        const uint64_t ad = umma_desc_sw128(a_addr + k4 * 32);
                         const uint64_t bd = umma_desc_sw128(b_addr + k4 * 32);
-                        umma_bf16(d_tmem, ad, bd, idesc, (kb | k4) != 0 ? 1u : 0u);
+                        if (!(dbg & 1)) umma_bf16_ts(d_tmem, a_tmem + k4 * 8, bd, idesc, (kb | k4) != 0 ? 1u : 0u);
                     }
                     umma_commit(&empty[stage]);           // smem slot reusable once these MMAs retire
                     if (++stage == stages) { stage = 0; phase ^= 1; }
@@ -202,47 +220,105 @@ scan_mma_bf16_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     } else if (warp >= 4) {
         const int ew = warp - 4;                          // == warp % 4: TMEM lanes [32*ew, 32*ew+32)
         const int t = ew * 32 + lane;                     // query within the tile
-        float tau = VQ_NEG_INF;
+        const int q = q_tile * QT + t;
+        const uint32_t lane_base = tmem_base + ((uint32_t)(ew * 32) << 16);
+        // ---- query tile -> tensor memory: lane t holds query q, column c holds elements 2c, 2c+1
+        {
+            const uint4* qrow = reinterpret_cast<const uint4*>(qbf + (size_t)q * ld);
+            // 4 k-blocks (32 x 16 B loads) in flight per thread before the first tcgen05.st
+            for (int kb0 = 0; kb0 < nkb; kb0 += 4) {
+                uint32_t w[4][32];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    if (kb0 + u < nkb) {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const uint4 x = qrow[(kb0 + u) * 8 + i];
+                            w[u][4 * i] = x.x; w[u][4 * i + 1] = x.y; w[u][4 * i + 2] = x.z; w[u][4 * i + 3] = x.w;
+                        }
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (kb0 + u < nkb) tmem_st32(lane_base + A_COL0 + (uint32_t)(kb0 + u) * (KB_ELEMS / 2), w[u]);
+            }
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(a_full);
+        }
+        // top-k list of this thread's query, in registers, WORST first: slots [0,k) are live and
+        // ascending, slots [k,KL) hold +inf so a bubble pass stops in front of them.  The running
+        // k-th best is therefore always ls[0] (a static register, no dynamic indexing).
+        float ls[KL];
+        int lr[KL];
+#pragma unroll
+        for (int i = 0; i < KL; ++i) { ls[i] = i < k ? VQ_NEG_INF : INFINITY; lr[i] = VQ_EMPTY_ROW; }
+        float published = VQ_NEG_INF;
         int it = 0;
         for (int tile = group; tile < n_tiles; tile += n_groups, ++it) {
             const int acc = it & 1;
             const uint32_t acc_phase = (it >> 1) & 1;
+            // k-th best any CTA has published for this query; ties with it are kept (>=) so the
+            // (score desc, row asc) rule still sees every candidate it needs
+            const float g = *reinterpret_cast<volatile float*>(gtau + q);
+            const float g_keep = (g == VQ_NEG_INF) ? g : nextafterf(g, VQ_NEG_INF);
+            float thr = fmaxf(ls[0], g_keep);
             mbar_wait(&tmem_full[acc], acc_phase);
             tc_fence_after();
             const int row0 = tile * NT;
             const int valid = (n - row0) < NT ? (n - row0) : NT;
 #pragma unroll 1
-            for (int c0 = 0; c0 < NT; c0 += 32) {
+            for (int c0 = 0; c0 < ((dbg & 4) ? 0 : NT); c0 += 32) {
                 uint32_t v[32];
-                tmem_ld32(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * NT + c0), v);
+                tmem_ld32(lane_base + (uint32_t)(acc * NT + c0), v);
+                // branch-free filter (a stale threshold only lets more through; re-checked below)
+                unsigned mask = 0;
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const float s = __uint_as_float(v[j]);
-                    if (s > tau && (c0 + j) < valid) {
-                        // private insertion (rows arrive in ascending order, so equal scores keep row order)
-                        int i = k - 1;
-                        while (i > 0) {
-                            const float p = ls[(i - 1) * QT + t];
-                            if (!(p < s)) break;
-                            ls[i * QT + t] = p;
-                            lr[i * QT + t] = lr[(i - 1) * QT + t];
-                            --i;
+                for (int j = 0; j < 32; ++j) mask |= (__uint_as_float(v[j]) > thr) ? (1u << j) : 0u;
+                const int left = valid - c0;
+                if (left < 32) mask &= left > 0 ? ((1u << left) - 1u) : 0u;
+                while (mask) {
+                    const int j = __ffs(mask) - 1;
+                    mask &= mask - 1;
+                    float s = __uint_as_float(v[0]);
+#pragma unroll
+                    for (int jj = 1; jj < 32; ++jj) s = (j == jj) ? __uint_as_float(v[jj]) : s;
+                    if (s > thr) {
+                        // replace the current k-th best, then one bubble pass restores the order.  Rows
+                        // arrive in ascending order inside a CTA, so with the strict comparison equal
+                        // scores end up in ascending-row order (the engine's tie rule).
+                        ls[0] = s;
+                        lr[0] = row0 + c0 + j;
+#pragma unroll
+                        for (int i = 0; i + 1 < KL; ++i) {
+                            const bool sw = ls[i] > ls[i + 1];
+                            const float a0 = ls[i], a1 = ls[i + 1];
+                            const int r0 = lr[i], r1 = lr[i + 1];
+                            ls[i] = sw ? a1 : a0;
+                            ls[i + 1] = sw ? a0 : a1;
+                            lr[i] = sw ? r1 : r0;
+                            lr[i + 1] = sw ? r0 : r1;
                         }
-                        ls[i * QT + t] = s;
-                        lr[i * QT + t] = row0 + c0 + j;
-                        tau = ls[(k - 1) * QT + t];
+                        thr = fmaxf(ls[0], g_keep);
                     }
                 }
             }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+            if (ls[0] > published) {                      // list full and improved: share the new k-th best
+                published = ls[0];
+                atomic_max_float(gtau + q, published);
+            }
         }
-        const size_t dst = ((size_t)group * b_pad + (size_t)q_tile * QT + t) * k;
-        for (int i = 0; i < k; ++i) {
-            const int r = lr[i * QT + t];
-            part_s[dst + i] = ls[i * QT + t];
-            part_r[dst + i] = (r == VQ_EMPTY_ROW) ? -1 : r;
+        const size_t dst = ((size_t)group * b_pad + q) * k;
+#pragma unroll
+        for (int i = 0; i < KL; ++i) {
+            if (i < k) {                                  // slot i is the (k-1-i)-th best
+                part_s[dst + (k - 1 - i)] = ls[i];
+                part_r[dst + (k - 1 - i)] = (lr[i] == VQ_EMPTY_ROW) ? -1 : lr[i];
+            }
         }
     }
     tc_fence_before();
@@ -251,6 +327,33 @@ scan_mma_bf16_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS) : "memory");
     }
+}
+
+// fp32 queries -> L2-normalised bf16 [b_pad, ld] (rows >= b and columns >= dim are zero) and the
+// shared threshold array reset; one warp per row.
+__global__ void __launch_bounds__(256)
+prep_queries_bf16_kernel(const float* __restrict__ src, int b, int dim, int src_ld, __nv_bfloat16* __restrict__ dst, int ld,
+                         int b_pad, int mode, float* __restrict__ gtau) {
+    const int lane = threadIdx.x & 31;
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= b_pad) return;
+    __nv_bfloat16* o = dst + (size_t)row * ld;
+    if (lane == 0) gtau[row] = VQ_NEG_INF;
+    if (row >= b) {
+        for (int c = lane; c < ld; c += 32) o[c] = __float2bfloat16_rn(0.f);
+        return;
+    }
+    const float* s = src + (size_t)row * src_ld;
+    float d = 1.f;
+    if (mode != VQ_NORM_NONE) {
+        float sum = 0.f;
+        for (int c = lane; c < dim; c += 32) { const float v = s[c]; sum = fmaf(v, v, sum); }
+        sum = vq_warp_sum(sum);
+        d = sqrtf(sum);
+        if (mode == VQ_NORM_EPS) d += 1e-10f;
+    }
+    for (int c = lane; c < ld; c += 32)
+        o[c] = __float2bfloat16_rn(c < dim ? (mode == VQ_NORM_NONE ? s[c] : s[c] / d) : 0.f);
 }
 
 // ------------------------------------------------------------------------------------ host
@@ -269,96 +372,190 @@ EncodeTiledFn get_encode() {
     return fn;
 }
 
-bool make_map_bf16(CUtensorMap* map, const void* base, uint64_t rows, uint64_t ld, uint32_t box_rows) {
+// Tensor maps are pure functions of (base, rows, ld, box): keep the last few (encoding costs ~10 us of
+// host time per call, which is visible at batch 1).
+struct MapKey { const void* base; uint64_t rows, ld; uint32_t box_rows; };
+struct MapSlot { MapKey key; CUtensorMap map; bool used; };
+std::mutex g_map_mu;
+MapSlot g_maps[8];
+int g_map_next = 0;
+
+bool get_map_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint64_t ld, uint32_t box_rows) {
+    std::lock_guard<std::mutex> lock(g_map_mu);
+    for (auto& sl : g_maps)
+        if (sl.used && sl.key.base == base && sl.key.rows == rows && sl.key.ld == ld && sl.key.box_rows == box_rows) {
+            *out = sl.map;
+            return true;
+        }
     EncodeTiledFn enc = get_encode();
     if (!enc) return false;
     cuuint64_t dims[2] = {ld, rows};
     cuuint64_t strides[1] = {ld * 2};
     cuuint32_t box[2] = {KB_ELEMS, box_rows};
     cuuint32_t estr[2] = {1, 1};
-    return enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
-               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+    MapSlot& sl = g_maps[g_map_next];
+    g_map_next = (g_map_next + 1) % 8;
+    if (enc(&sl.map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) {
+        sl.used = false;
+        return false;
+    }
+    sl.key = {base, rows, ld, box_rows};
+    sl.used = true;
+    *out = sl.map;
+    return true;
 }
 
 inline size_t align256(size_t v) { return (v + 255) / 256 * 256; }
 
 struct MmaPlan {
-    int nkb, n_qt, b_pad, groups, grid, stages;
-    size_t smem, qbf_bytes, part_bytes;
+    int nkb, nt, n_qt, b_pad, groups, grid, stages;
+    size_t smem, qbf_bytes, tau_bytes, part_bytes;
 };
 MmaPlan plan(int64_t n, int ld, int b, int k) {
+    (void)k;
     MmaPlan p;
     p.nkb = ld / KB_ELEMS;
+    // TMEM budget: 2 accumulators of nt columns + ld/2 columns of resident queries <= 512
+    p.nt = (ld <= 512) ? 128 : (ld <= 768 ? 64 : 0);
     p.n_qt = (b + QT - 1) / QT;
     p.b_pad = p.n_qt * QT;
     const int sms = vq_num_sms();
-    const long long n_tiles = (n + NT - 1) / NT;
+    const long long n_tiles = p.nt ? (n + p.nt - 1) / p.nt : 1;
     long long groups = sms / p.n_qt;
     if (groups < 1) groups = 1;
     if (groups > n_tiles) groups = n_tiles;
     p.groups = (int)groups;
     p.grid = p.groups * p.n_qt;
-    const size_t fixed = 1024 + (size_t)p.nkb * A_KB_BYTES + (size_t)k * QT * 8 + 256;
-    int st = (int)((227 * 1024 - fixed) / B_KB_BYTES);
-    p.stages = st > 8 ? 8 : st;
-    p.smem = fixed + (size_t)(p.stages > 0 ? p.stages : 0) * B_KB_BYTES;
+    const size_t stage_bytes = (size_t)(p.nt ? p.nt : 128) * 128;
+    int st = (int)((200 * 1024) / stage_bytes);
+    p.stages = st > 12 ? 12 : st;
+    p.smem = 1024 + (size_t)p.stages * stage_bytes + 256;
     p.qbf_bytes = align256((size_t)p.b_pad * ld * 2);
+    p.tau_bytes = align256((size_t)p.b_pad * 4);
     p.part_bytes = align256((size_t)p.groups * p.b_pad * k * 4);
     return p;
 }
 
+template <int KL, int NT>
+cudaError_t launch_mma(const MmaPlan& p, const CUtensorMap& tmS, const __nv_bfloat16* qbf, float* gtau, int n, int ld, int k,
+                       float* part_s, int* part_r, int dbg, cudaStream_t stream) {
+    auto kern = scan_mma_bf16_kernel<KL, NT>;
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) return e;
+        attr_done = true;
+    }
+    kern<<<p.grid, kThreads, p.smem, stream>>>(tmS, qbf, gtau, n, ld, p.nkb, p.n_qt, k, p.stages, p.b_pad, part_s, part_r, dbg);
+    return cudaGetLastError();
+}
+
+int run_prepared(const MmaPlan& p, const CUtensorMap& tmS, const __nv_bfloat16* qbf, float* gtau, int n, int ld, int k,
+                 float* part_s, int* part_r, cudaStream_t stream) {
+    const int dbg = getenv("VQ_MMA_DEBUG") ? atoi(getenv("VQ_MMA_DEBUG")) : 0;
+    cudaError_t e;
+    vq_prof_begin(stream);
+    if (p.nt == 128)
+        e = k <= 16 ? launch_mma<16, 128>(p, tmS, qbf, gtau, n, ld, k, part_s, part_r, dbg, stream)
+          : k <= 32 ? launch_mma<32, 128>(p, tmS, qbf, gtau, n, ld, k, part_s, part_r, dbg, stream)
+                    : launch_mma<64, 128>(p, tmS, qbf, gtau, n, ld, k, part_s, part_r, dbg, stream);
+    else
+        e = k <= 16 ? launch_mma<16, 64>(p, tmS, qbf, gtau, n, ld, k, part_s, part_r, dbg, stream)
+          : k <= 32 ? launch_mma<32, 64>(p, tmS, qbf, gtau, n, ld, k, part_s, part_r, dbg, stream)
+                    : launch_mma<64, 64>(p, tmS, qbf, gtau, n, ld, k, part_s, part_r, dbg, stream);
+    vq_prof_end(stream);
+    if (e != cudaSuccess) {
+        vq_set_error("launch of scan_mma_bf16_kernel failed: %s", cudaGetErrorString(e));
+        return VQ_ECUDA;
+    }
+    return VQ_OK;
+}
+
+__global__ void fill_neg_inf_kernel(float* p, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = VQ_NEG_INF;
+}
+
 }  // namespace
+
+bool vq_scan_mma_supported(int64_t n, int dim, int ld, int store_dtype, int b, int k);
+
+// Scan with queries that are ALREADY unit-norm bf16 rows [b_pad, ld] (b_pad % 128 == 0, rows >= b zero):
+// used by the HNSW builder, whose queries are the stored rows themselves.
+size_t vq_scan_mma_prepared_workspace(int64_t n, int ld, int b, int k) {
+    // valid for every batch <= b: groups * b_pad <= max(SMs, n_qt) * 128 whatever the batch
+    const MmaPlan p = plan(n, ld, b, k);
+    const size_t lists = (size_t)(vq_num_sms() > p.n_qt ? vq_num_sms() : p.n_qt) * QT;
+    return p.tau_bytes + 2 * align256(lists * k * 4) + 256;
+}
+int vq_scan_mma_prepared(const void* store, int64_t n, int ld, const void* qbf, int b, int k, float* out_scores,
+                         int32_t* out_rows, void* ws_v, size_t ws_bytes, cudaStream_t stream) {
+    if (!vq_scan_mma_supported(n, ld, ld, VQ_BF16, b, k)) {
+        vq_set_error("scan_mma_prepared: unsupported shape n=%lld ld=%d b=%d k=%d", (long long)n, ld, b, k);
+        return VQ_EUNSUPPORTED;
+    }
+    const MmaPlan p = plan(n, ld, b, k);
+    if (ws_bytes < p.tau_bytes + 2 * p.part_bytes) {
+        vq_set_error("scan_mma_prepared: workspace too small (%zu < %zu)", ws_bytes, p.tau_bytes + 2 * p.part_bytes);
+        return VQ_EWORKSPACE;
+    }
+    unsigned char* ws = (unsigned char*)ws_v;
+    float* gtau = (float*)ws;
+    float* part_s = (float*)(ws + p.tau_bytes);
+    int* part_r = (int*)(ws + p.tau_bytes + p.part_bytes);
+    fill_neg_inf_kernel<<<(p.b_pad + 255) / 256, 256, 0, stream>>>(gtau, p.b_pad);
+    CUtensorMap tmS;
+    if (!get_map_bf16(&tmS, store, (uint64_t)n, (uint64_t)ld, (uint32_t)p.nt)) {
+        vq_set_error("scan_mma: cuTensorMapEncodeTiled failed");
+        return VQ_ECUDA;
+    }
+    int rc = run_prepared(p, tmS, (const __nv_bfloat16*)qbf, gtau, (int)n, ld, k, part_s, part_r, stream);
+    if (rc) return rc;
+    return vq_topk_merge_launch(part_s, part_r, p.groups, (long long)p.b_pad * k, b, k, nullptr, k, out_scores, out_rows, 0, 0, stream);
+}
 
 bool vq_scan_mma_supported(int64_t n, int dim, int ld, int store_dtype, int b, int k) {
     (void)dim;
     if (store_dtype != VQ_BF16) return false;                 // kind::tf32 path for fp32 stores: not built yet
-    if (ld % KB_ELEMS != 0 || n < 1 || b < 1 || k < 1 || k > kMaxK) return false;
-    const MmaPlan p = plan(n, ld, b, k);
-    if (p.n_qt > vq_num_sms()) return false;
-    return p.stages >= 3;                                     // resident query tile + a useful ring must fit
+    if (ld % KB_ELEMS != 0 || ld > 768 || n < 1 || b < 1 || k < 1 || k > kMaxK) return false;
+    return (b + QT - 1) / QT <= vq_num_sms();
 }
 
 size_t vq_scan_mma_workspace(int64_t n, int ld, int store_dtype, int b, int k) {
-    if (store_dtype != VQ_BF16 || b < 1 || k < 1 || k > kMaxK || n < 1) return 0;
+    if (store_dtype != VQ_BF16 || b < 1 || k < 1 || k > kMaxK || n < 1 || ld > 768) return 0;
     const MmaPlan p = plan(n, ld, b, k);
-    return p.qbf_bytes + 2 * p.part_bytes + 256;
+    return p.qbf_bytes + p.tau_bytes + 2 * p.part_bytes + 256;
 }
 
-int vq_scan_mma_run(const void* store, int64_t n, int dim, int ld, int store_dtype, const float* qnorm, int b, int k,
-                    float* out_scores, int32_t* out_rows, void* ws_v, size_t ws_bytes, cudaStream_t stream, int* launches) {
-    (void)dim;
+// queries: raw fp32 [b, dim]; normalisation (query_norm) is fused into the bf16 conversion.
+int vq_scan_mma_run(const void* store, int64_t n, int dim, int ld, int store_dtype, const float* queries, int query_norm,
+                    int b, int k, float* out_scores, int32_t* out_rows, void* ws_v, size_t ws_bytes, cudaStream_t stream,
+                    int* launches) {
     if (!vq_scan_mma_supported(n, dim, ld, store_dtype, b, k)) {
         vq_set_error("scan_mma: unsupported shape");
         return VQ_EUNSUPPORTED;
     }
     const MmaPlan p = plan(n, ld, b, k);
-    if (ws_bytes < p.qbf_bytes + 2 * p.part_bytes) {
+    if (ws_bytes < p.qbf_bytes + p.tau_bytes + 2 * p.part_bytes) {
         vq_set_error("scan_mma: workspace too small");
         return VQ_EWORKSPACE;
     }
     unsigned char* ws = (unsigned char*)ws_v;
     __nv_bfloat16* qbf = (__nv_bfloat16*)ws;
-    float* part_s = (float*)(ws + p.qbf_bytes);
-    int* part_r = (int*)(ws + p.qbf_bytes + p.part_bytes);
-    // queries: fp32 normalised [b, ld] -> bf16 [b_pad, ld], pad rows zero
-    VQ_CUDA(cudaMemsetAsync(qbf, 0, (size_t)p.b_pad * ld * 2, stream));
-    int rc = vq_ingest_launch(qnorm, b, ld, ld, qbf, VQ_BF16, ld, VQ_NORM_NONE, stream);
-    if (rc) return rc;
-    CUtensorMap tmQ, tmS;
-    if (!make_map_bf16(&tmQ, qbf, (uint64_t)p.b_pad, (uint64_t)ld, QT) || !make_map_bf16(&tmS, store, (uint64_t)n, (uint64_t)ld, NT)) {
+    float* gtau = (float*)(ws + p.qbf_bytes);
+    float* part_s = (float*)(ws + p.qbf_bytes + p.tau_bytes);
+    int* part_r = (int*)(ws + p.qbf_bytes + p.tau_bytes + p.part_bytes);
+    prep_queries_bf16_kernel<<<(p.b_pad + 7) / 8, 256, 0, stream>>>(queries, b, dim, dim, qbf, ld, p.b_pad, query_norm, gtau);
+    VQ_LAUNCH_CHECK("prep_queries_bf16_kernel");
+    CUtensorMap tmS;
+    if (!get_map_bf16(&tmS, store, (uint64_t)n, (uint64_t)ld, (uint32_t)p.nt)) {
         vq_set_error("scan_mma: cuTensorMapEncodeTiled failed");
         return VQ_ECUDA;
     }
-    static bool attr_done = false;
-    if (!attr_done) {
-        VQ_CUDA(cudaFuncSetAttribute(scan_mma_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        attr_done = true;
-    }
-    vq_prof_begin(stream);
-    scan_mma_bf16_kernel<<<p.grid, kThreads, p.smem, stream>>>(tmQ, tmS, (int)n, p.nkb, p.n_qt, k, p.stages, p.b_pad, part_s, part_r);
-    vq_prof_end(stream);
-    VQ_LAUNCH_CHECK("scan_mma_bf16_kernel");
+    int rc = run_prepared(p, tmS, qbf, gtau, (int)n, ld, k, part_s, part_r, stream);
+    if (rc) return rc;
     rc = vq_topk_merge_launch(part_s, part_r, p.groups, (long long)p.b_pad * k, b, k, nullptr, k, out_scores, out_rows, 0, 0, stream);
     if (rc) return rc;
     *launches = 3;

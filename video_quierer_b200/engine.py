@@ -175,10 +175,11 @@ class Scanner:
         with torch.cuda.device(self.device):
             out_s = torch.empty((b, k), dtype=torch.float32, device=self.device)
             out_r = torch.empty((b, k), dtype=torch.int32, device=self.device)
+            tmp = torch.empty((b, kc), dtype=torch.float32, device=self.device)
             rc = self.lib.vq_rescore_topk(_ptr(f32), n, dim, f32.stride(0), _ptr(queries_norm_padded), b,
-                                          _ptr(cand_rows), kc, k, _ptr(out_s), _ptr(out_r), _stream(self.device))
+                                          _ptr(cand_rows), kc, k, _ptr(out_s), _ptr(out_r), _ptr(tmp), tmp.numel() * 4,
+                                          _stream(self.device))
             _lib.check(rc, "vq_rescore_topk")
-            self.last_launches += 2
         return out_s, out_r
 
     def normalise_padded(self, queries: torch.Tensor, ld: int, norm: int) -> torch.Tensor:
@@ -188,7 +189,6 @@ class Scanner:
             out = torch.empty((b, ld), dtype=torch.float32, device=self.device)
             _lib.check(self.lib.vq_ingest_rows(_ptr(queries), b, dim, dim, _ptr(out), _lib.F32, ld, norm,
                                                _stream(self.device)), "vq_ingest_rows")
-            self.last_launches += 1
         return out
 
     def merge(self, scores: torch.Tensor, rows: torch.Tensor, offsets, k_out: int, g_stride: int = 0):

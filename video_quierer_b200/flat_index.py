@@ -82,6 +82,40 @@ class EmbeddingList(list):
     # append / extend only add rows past valid_prefix → nothing to record
 
 
+# Worst-case |bf16-operand score - fp32 score| for unit-norm rows and queries: each operand is
+# rounded to 8 significant bits (relative 2^-9), products are exact, so
+# |delta| <= (2*2^-9 + 2^-18) * sum|q_i x_i| <= 2^-8 * |q| |x|  (Cauchy-Schwarz) plus fp32 accumulation noise.
+BF16_SCORE_EPS = 2.0 ** -8 + 1e-5
+
+
+def two_stage_search(scanner: Scanner, st: DeviceStore, q_dev: torch.Tensor, k: int, path: str = "auto",
+                     max_row_norm: float = 1.0):
+    """Exact top-k from a bf16 scan: (1) the tensor-core scan of the bf16 copy selects k' candidates,
+    (2) they are re-scored exactly from the fp32 copy, (3) the result is *certified*: every row
+    outside the candidate set has exact score <= (k'-th bf16 score) + eps, so if the exact k-th
+    score is above that bound nothing was missed.  Returns ([b,k] f32, [b,k] i32, uncertified [b]
+    bool device tensor or None); the caller re-runs uncertified queries (near-duplicate heavy
+    data) with `exact_fallback` after its device->host read, so no extra sync is added here."""
+    kc = min(st.n, 32 if k <= 16 else max(2 * k, k + 22))
+    kc = max(kc, k)
+    s_lo, cand = scanner.scan(st.bf16, st.n, st.dim, q_dev, kc, _lib.NORM_EPS, path)
+    launches = scanner.last_launches
+    scan_path = scanner.last_path
+    qn = scanner.normalise_padded(q_dev, st.ld, _lib.NORM_EPS)
+    s_hi, rows = scanner.rescore(st.f32, st.n, st.dim, qn, cand, k)
+    bad = None
+    if kc < st.n:
+        bad = s_hi[:, k - 1] < (s_lo[:, kc - 1] + BF16_SCORE_EPS * max_row_norm)
+    scanner.last_launches = launches + 3
+    scanner.last_path = scan_path + "+rescore"
+    return s_hi, rows, bad
+
+
+def exact_fallback(scanner: Scanner, st: DeviceStore, q_dev: torch.Tensor, k: int, idx: torch.Tensor):
+    """fp32 FMA scan for the queries `idx` whose two-stage result could not be certified."""
+    return scanner.scan(st.f32, st.n, st.dim, q_dev[idx].contiguous(), k, _lib.NORM_EPS, "fma")
+
+
 class B200FlatIndex:
     """Exact cosine search over a device-resident frame-embedding matrix."""
 
@@ -100,6 +134,7 @@ class B200FlatIndex:
         self._scanner = Scanner(self.device)
         self._lock = threading.RLock()
         self.search_times: List[float] = []
+        self.stats = {"two_stage_queries": 0, "uncertified_queries": 0}
 
     # ------------------------------------------------------------------ attribute surface
     @property
@@ -156,20 +191,6 @@ class B200FlatIndex:
         emb.valid_prefix = n
 
     # ------------------------------------------------------------------ search
-    def _search_device(self, q_dev: torch.Tensor, k: int):
-        st = self._store
-        if self.store_dtype == "bf16":
-            if self.rescore:
-                kc = min(st.n, max(2 * k, k + 22))
-                _, cand = self._scanner.scan(st.bf16, st.n, st.dim, q_dev, kc, _lib.NORM_EPS, self.path)
-                launches = self._scanner.last_launches
-                qn = self._scanner.normalise_padded(q_dev, st.ld, _lib.NORM_EPS)
-                out = self._scanner.rescore(st.f32, st.n, st.dim, qn, cand, k)
-                self._scanner.last_launches += launches - 0
-                return out
-            return self._scanner.scan(st.bf16, st.n, st.dim, q_dev, k, _lib.NORM_EPS, self.path)
-        return self._scanner.scan(st.f32, st.n, st.dim, q_dev, k, _lib.NORM_EPS, self.path)
-
     def search_arrays(self, queries, k: int = 5):
         """Batched search returning ([b,k'] scores float32, [b,k'] rows int32) numpy arrays,
         k' = min(k, N).  `queries` may be numpy or a torch tensor (host or device)."""
@@ -179,10 +200,26 @@ class B200FlatIndex:
             if n == 0:
                 b = 1 if np.ndim(queries) == 1 else len(queries)
                 return np.zeros((b, 0), np.float32), np.zeros((b, 0), np.int32)
-            q = as_device_queries(queries, self._store.dim, self.device)
+            st = self._store
+            q = as_device_queries(queries, st.dim, self.device)
             kk = min(int(k), n)
-            s, r = self._search_device(q, kk)
-            return s.cpu().numpy(), r.cpu().numpy()
+            if self.store_dtype != "bf16":
+                s, r = self._scanner.scan(st.f32, st.n, st.dim, q, kk, _lib.NORM_EPS, self.path)
+                return s.cpu().numpy(), r.cpu().numpy()
+            if not self.rescore:
+                s, r = self._scanner.scan(st.bf16, st.n, st.dim, q, kk, _lib.NORM_EPS, self.path)
+                return s.cpu().numpy(), r.cpu().numpy()
+            s, r, bad = two_stage_search(self._scanner, st, q, kk, self.path)
+            s_h, r_h = s.cpu().numpy(), r.cpu().numpy()
+            self.stats["two_stage_queries"] += int(q.shape[0])
+            if bad is not None:
+                bad_h = np.nonzero(bad.cpu().numpy())[0]
+                if len(bad_h):
+                    self.stats["uncertified_queries"] += len(bad_h)
+                    idx = torch.from_numpy(bad_h).to(self.device)
+                    s2, r2 = exact_fallback(self._scanner, st, q, kk, idx)
+                    s_h[bad_h], r_h[bad_h] = s2.cpu().numpy(), r2.cpu().numpy()
+            return s_h, r_h
 
     def search(self, query_embedding: np.ndarray, k: int = 5) -> List[Dict]:
         """video_search_overhaul.py:40-64: list of metadata copies + 'score', best first."""

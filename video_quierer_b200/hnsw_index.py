@@ -58,7 +58,7 @@ class B200HNSWIndex:
     def __init__(self, dimension: int = 512, M: int = 16, ef_construction: int = 200, ef_search: int = 50,
                  max_M: int = 16, level_generation_factor: float = 1.0 / math.log(2.0), num_threads: int = 4,
                  use_numpy_optimization: bool = True, device=None, search_dtype: str = "fp32",
-                 rebuild_fraction: float = 0.10, select: str = "diverse", max_candidates: int = 64):
+                 rebuild_fraction: float = 0.10, select: str = "diverse", max_candidates: int = 63):
         self.dimension = dimension
         self.M = M
         self.max_M = max_M
@@ -86,7 +86,7 @@ class B200HNSWIndex:
 
         self.device = _require_cuda(device)
         self.lib = _lib.load()
-        self._store = DeviceStore(dimension, self.device, keep_fp32=True, keep_bf16=self.search_dtype == "bf16")
+        self._store = DeviceStore(dimension, self.device, keep_fp32=True, keep_bf16=True)
         self._scanner = Scanner(self.device)
         self._ws = Workspace(self.device)
         self._bws = Workspace(self.device)
@@ -186,9 +186,13 @@ class B200HNSWIndex:
             k_cand, div = m_out, 0
         else:
             k_cand, div = max(m_out, min(int(self.ef_construction), self.max_candidates, 95)), 1
-        need = self.lib.vq_hnsw_layer_workspace_bytes(n_members, st.dim, st.ld, _lib.F32, k_cand, m_out)
+        # the exact k-nearest pass runs on the tensor cores from the bf16 copy when the lists fit
+        # the register top-k (k_cand <= 63) — ~30x faster than the fp32 FMA pass at 1M rows
+        use_bf = st.bf16 is not None and k_cand <= 63 and st.ld <= 768
+        mat, dt = (st.bf16, _lib.BF16) if use_bf else (st.f32, _lib.F32)
+        need = self.lib.vq_hnsw_layer_workspace_bytes(n_members, st.dim, st.ld, dt, k_cand, m_out)
         ws = self._bws.get(need)
-        rc = self.lib.vq_hnsw_build_layer(_ptr(st.f32), st.n, st.dim, st.ld, _lib.F32, _ptr(members), n_members,
+        rc = self.lib.vq_hnsw_build_layer(_ptr(mat), st.n, st.dim, st.ld, dt, _ptr(members), n_members,
                                           k_cand, m_out, div, _ptr(adj_out), _ptr(ws), ws.numel(), _stream(self.device))
         _lib.check(rc, "vq_hnsw_build_layer")
 
@@ -218,15 +222,33 @@ class B200HNSWIndex:
                 out_r = torch.empty((b, kk), dtype=torch.int32, device=self.device)
                 stats = torch.zeros((b, 4), dtype=torch.int32, device=self.device)
                 ws = self._ws.get(self.lib.vq_hnsw_workspace_bytes(b, st.ld, ef))
-                rc = self.lib.vq_hnsw_search(_ptr(mat), g.n, st.dim, st.ld, dt, _ptr(g.levels), _ptr(g.adj0),
-                                             g.adj0.shape[1], _ptr(g.upper_off), _ptr(g.upper_adj),
-                                             g.upper_adj.shape[1], g.entry, g.max_level, ef, _ptr(q), b, kk,
-                                             _lib.NORM_PLAIN, _ptr(out_d), _ptr(out_r), _ptr(stats), _ptr(ws),
-                                             ws.numel(), _stream(self.device))
-                _lib.check(rc, "vq_hnsw_search")
+
+                def launch(qq, od, orr, stt, cap):
+                    rc = self.lib.vq_hnsw_search(_ptr(mat), g.n, st.dim, st.ld, dt, _ptr(g.levels), _ptr(g.adj0),
+                                                 g.adj0.shape[1], _ptr(g.upper_off), _ptr(g.upper_adj),
+                                                 g.upper_adj.shape[1], g.entry, g.max_level, ef, _ptr(qq), qq.shape[0], kk,
+                                                 _lib.NORM_PLAIN, _ptr(od), _ptr(orr), _ptr(stt), cap, _ptr(ws),
+                                                 ws.numel(), _stream(self.device))
+                    _lib.check(rc, "vq_hnsw_search")
+
+                launch(q, out_d, out_r, stats, 0)
                 dist = out_d.cpu().numpy()
                 rows = out_r.cpu().numpy().astype(np.int64)
                 self.last_stats = stats.cpu().numpy().astype(np.uint32)
+                over = np.nonzero(self.last_stats[:, 2])[0]
+                cap = 64 * ef
+                while len(over) and cap <= 32768 * 2:             # visited set filled up: re-run those queries
+                    idx = torch.from_numpy(over).to(self.device)
+                    q2 = q[idx].contiguous()
+                    d2 = torch.empty((len(over), kk), dtype=torch.float32, device=self.device)
+                    r2 = torch.empty((len(over), kk), dtype=torch.int32, device=self.device)
+                    s2 = torch.zeros((len(over), 4), dtype=torch.int32, device=self.device)
+                    launch(q2, d2, r2, s2, min(cap, 32768))
+                    dist[over] = d2.cpu().numpy()
+                    rows[over] = r2.cpu().numpy().astype(np.int64)
+                    self.last_stats[over] = s2.cpu().numpy().astype(np.uint32)
+                    over = over[np.nonzero(self.last_stats[over, 2])[0]]
+                    cap *= 4
                 if st.n > g.n:                                    # rows newer than the graph: exact scan of the delta
                     kd = min(int(k), st.n - g.n)
                     s2, r2 = self._scanner.scan(st.f32[g.n:], st.n - g.n, st.dim, q, kd, _lib.NORM_PLAIN, "fma")
@@ -358,8 +380,7 @@ class B200HNSWIndex:
             self.entry_point = save_data['entry_point']
             self.element_count = save_data['element_count']
             self._pending = []
-            self._store = DeviceStore(self.dimension, self.device, keep_fp32=True,
-                                      keep_bf16=self.search_dtype == "bf16")
+            self._store = DeviceStore(self.dimension, self.device, keep_fp32=True, keep_bf16=True)
             n = len(self._ids)
             if n == 0:
                 self._graph = None
@@ -403,8 +424,7 @@ class B200HNSWIndex:
             self._level_list = [int(x) for x in levels]
             self.levels = {nid: lv for nid, lv in zip(self._ids, self._level_list)}
             self._pending = []
-            self._store = DeviceStore(self.dimension, self.device, keep_fp32=True,
-                                      keep_bf16=self.search_dtype == "bf16")
+            self._store = DeviceStore(self.dimension, self.device, keep_fp32=True, keep_bf16=True)
             self._store.append(np.asarray(vectors, dtype=np.float32), _lib.NORM_NONE)
             self._entry_row = int(entry)
             self.entry_point = self._ids[int(entry)]

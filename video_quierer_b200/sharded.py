@@ -70,6 +70,8 @@ class ShardedSearcher:
     def search(self, queries: torch.Tensor, k: int):
         """Returns (scores [b,k] fp32, global rows [b,k] int64), identical on every rank."""
         s, r = self.local_search(queries, k)
+        if self.world == 1 and self._merge is None:
+            return s, r.to(torch.int64)                       # one shard: nothing to exchange or merge
         packed = pack_candidates(s, r)                        # [2, b, k] int32
         if self.world == 1:
             gathered = packed[None]
