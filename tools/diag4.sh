@@ -1,0 +1,8 @@
+timeout 120 python tools/mma_check.py 2>&1 | grep -v "torch fp32" | tail -3
+timeout 600 python -m pytest tests/test_gpu_exact.py -x -q -m gpu 2>&1 | tail -3
+echo "== k=10"; timeout 120 python tools/quick_bench.py --dtypes bf16 --paths mma --batches 1,32,128,256,1024,4096 --k 10 --iters 10 2>&1 | tail -6 | cut -c1-200
+echo "== k=32"; timeout 120 python tools/quick_bench.py --dtypes bf16 --paths mma --batches 1,32,128,256,1024 --k 32 --iters 10 2>&1 | tail -5 | cut -c1-200
+for dbg in 132 134 130 129; do
+echo "== VQ_MMA_DEBUG=$dbg"
+VQ_MMA_DEBUG=$dbg timeout 120 python tools/quick_bench.py --dtypes bf16 --paths mma --batches 1,1024 --k 10 --iters 2 2>&1 | grep -E "dbg\]|dtype" | awk '!seen[$0]++' | cut -c1-150 | tail -4
+done

@@ -26,6 +26,19 @@
 //                            branch-free threshold filter, register insertion
 // Grid: persistent, gridDim = groups * n_qt; CTA c serves query tile c % n_qt and the store tiles
 // c / n_qt, + groups, ... ; it writes one k-entry list per query, `topk_merge` reduces them.
+//
+// Measured design rules (tools/mmabench.cu, B200): a lone tcgen05.mma M128 N128 K16 retires every
+// 64 cycles, but every tcgen05.commit drains the tensor pipe (~160 cycles): one commit per 4 MMAs
+// gives 105-120 cycles/MMA.  Ring slots are therefore released in GROUPS of kGroup k-blocks (one
+// commit per 16 MMAs) while TMA completion stays per k-block.
+//
+// Threshold bootstrap: the per-query insertion cost is ~k*(1+ln(rows per CTA / k)) serial list
+// insertions per CTA.  For large stores a BOOT pass of the same kernel first scores a sample of
+// `boot_tiles` store tiles and writes only each tile's per-query MAXIMUM; the k-th largest of those
+// maxima (boot_select_kernel) is a valid lower bound of the global k-th best score (k distinct rows
+// reach it), so the main pass starts with that bound in `gtau` and inserts ~10x fewer rows.
+// Queries are dealt round-robin over the four epilogue warps (query i of a tile -> TMEM lane
+// (i%4)*32 + i/4) so that a batch of 32 keeps all four warps' schedulers busy instead of one.
 #include <cuda.h>
 #include <stdlib.h>
 
@@ -46,6 +59,8 @@ constexpr int KB_ELEMS = 64;            // bf16 per k-block = one 128-byte swizz
 constexpr int TMEM_COLS = 512;          // whole tensor memory: 2 accumulators + resident query tile
 constexpr int kThreads = 256;
 constexpr int kMaxK = 64;
+constexpr int kGroup = 4;              // ring slots released per tcgen05.commit
+constexpr int kMaxBootTiles = 256;     // sample tiles of the threshold bootstrap (8 per lane in boot_select)
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -73,6 +88,22 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, u
     asm volatile(
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
         ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_addr(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+// one lane of the (converged) warp; always the same lane, so tcgen05.commit sees the MMAs it tracks
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}" : "=r"(pred));
+    return pred != 0;
 }
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
@@ -134,7 +165,66 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-template <int KL, int NT>
+// tcgen05.ld split into issue + wait so that the next chunk's load overlaps the filter of this one.
+// The wait names the destination registers as in/out operands: their uses cannot be scheduled above it.
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait(uint32_t (&v)[32]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+        : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]),
+          "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]),
+          "+r"(v[16]), "+r"(v[17]), "+r"(v[18]), "+r"(v[19]), "+r"(v[20]), "+r"(v[21]), "+r"(v[22]), "+r"(v[23]),
+          "+r"(v[24]), "+r"(v[25]), "+r"(v[26]), "+r"(v[27]), "+r"(v[28]), "+r"(v[29]), "+r"(v[30]), "+r"(v[31])
+        :: "memory");
+}
+
+// Filter 32 fresh scores (store rows row_base .. row_base+31, the first `left` of them real) against
+// the running threshold and insert the survivors into the thread's register top-k list.
+template <int KL>
+__device__ __forceinline__ void filter_insert(const uint32_t (&v)[32], int row_base, int left, float g_keep, float& thr,
+                                              float (&ls)[KL], int (&lr)[KL]) {
+    // branch-free filter (a stale threshold only lets more through; re-checked below)
+    unsigned mask = 0;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) mask |= (__uint_as_float(v[j]) > thr) ? (1u << j) : 0u;
+    if (left < 32) mask &= left > 0 ? ((1u << left) - 1u) : 0u;
+    while (mask) {
+        const int j = __ffs(mask) - 1;
+        mask &= mask - 1;
+        float s = __uint_as_float(v[0]);
+#pragma unroll
+        for (int jj = 1; jj < 32; ++jj) s = (j == jj) ? __uint_as_float(v[jj]) : s;
+        if (s > thr) {
+            // replace the current k-th best, then one bubble pass restores the order.  Rows arrive in
+            // ascending order inside a CTA, so with the strict comparison equal scores end up in
+            // ascending-row order (the engine's tie rule).
+            ls[0] = s;
+            lr[0] = row_base + j;
+#pragma unroll
+            for (int i = 0; i + 1 < KL; ++i) {
+                const bool sw = ls[i] > ls[i + 1];
+                const float a0 = ls[i], a1 = ls[i + 1];
+                const int r0 = lr[i], r1 = lr[i + 1];
+                ls[i] = sw ? a1 : a0;
+                ls[i + 1] = sw ? a0 : a1;
+                lr[i] = sw ? r1 : r0;
+                lr[i + 1] = sw ? r0 : r1;
+            }
+            thr = fmaxf(ls[0], g_keep);
+        }
+    }
+}
+
+template <int KL, int NT, bool BOOT>
 __global__ void __launch_bounds__(kThreads, 1)
 scan_mma_bf16_kernel(const __grid_constant__ CUtensorMap tmS,
                      const __nv_bfloat16* __restrict__ qbf,   // [b_pad, ld] normalised, zero padded
@@ -174,53 +264,71 @@ scan_mma_bf16_kernel(const __grid_constant__ CUtensorMap tmS,
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
 
+    // Producer and MMA warps run their loops with ALL lanes (addresses, counters and descriptors stay
+    // in uniform registers) and elect one lane only for the asynchronous instruction itself: a loop
+    // executed by a single lane makes ptxas wrap every UTCHMMA in an ELECT / R2UR waterfall
+    // (~25 dependent instructions, measured 131 cycles per MMA instead of 64).
     if (warp == 0) {
-        if (lane == 0) {
-            int stage = 0; uint32_t phase = 0;
-            for (int tile = group; tile < n_tiles; tile += n_groups) {
-                for (int kb = 0; kb < nkb; ++kb) {
-                    mbar_wait(&empty[stage], phase ^ 1);
+        int stage = 0; uint32_t phase = 0;
+        const uint32_t sB_addr = smem_u32(sB), full_addr = smem_u32(full);
+        for (int tile = group; tile < n_tiles; tile += n_groups) {
+            for (int kb = 0; kb < nkb; ++kb) {
+                if (stage % kGroup == 0) mbar_wait(&empty[stage / kGroup], phase ^ 1);   // whole group free
+                if (elect_one()) {
                     if (dbg & 2) { mbar_arrive(&full[stage]); }
                     else {
                         mbar_expect_tx(&full[stage], B_KB_BYTES);
-                        tma_load_2d(sB + (size_t)stage * B_KB_BYTES, &tmS, &full[stage], kb * KB_ELEMS, tile * NT);
+                        tma_load_2d_addr(sB_addr + (uint32_t)stage * B_KB_BYTES, &tmS, full_addr + (uint32_t)stage * 8, kb * KB_ELEMS, tile * NT);
                     }
-                    if (++stage == stages) { stage = 0; phase ^= 1; }
                 }
+                __syncwarp();
+                if (++stage == stages) { stage = 0; phase ^= 1; }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            const uint32_t idesc = umma_idesc_bf16(NT);
-            mbar_wait(a_full, 0);                          // query tile is in tensor memory
+        const uint32_t idesc = umma_idesc_bf16(NT);
+        const uint32_t sB_addr = smem_u32(sB);
+        mbar_wait(a_full, 0);                          // query tile is in tensor memory
+        tc_fence_after();
+        int stage = 0; uint32_t phase = 0; int it = 0;
+        long long dbg_c0 = 0, dbg_t0 = 0;
+        if (dbg & 128) { dbg_c0 = clock64(); asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(dbg_t0)); }
+        for (int tile = group; tile < n_tiles; tile += n_groups, ++it) {
+            const int acc = it & 1;
+            const uint32_t acc_phase = (it >> 1) & 1;
+            if (!(dbg & 64)) mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
             tc_fence_after();
-            int stage = 0; uint32_t phase = 0; int it = 0;
-            for (int tile = group; tile < n_tiles; tile += n_groups, ++it) {
-                const int acc = it & 1;
-                const uint32_t acc_phase = (it >> 1) & 1;
-                mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+            const uint32_t d_tmem = tmem_base + (uint32_t)acc * NT;
+            for (int kb = 0; kb < nkb; ++kb) {
+                if (!(dbg & 32)) mbar_wait(&full[stage], phase);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + (uint32_t)acc * NT;
-                for (int kb = 0; kb < nkb; ++kb) {
-                    mbar_wait(&full[stage], phase);
-                    tc_fence_after();
-                    const uint32_t b_addr = smem_u32(sB + (size_t)stage * B_KB_BYTES);
-                    const uint32_t a_tmem = tmem_base + A_COL0 + (uint32_t)kb * (KB_ELEMS / 2);
+                if (elect_one()) {
+                    const uint64_t bd0 = umma_desc_sw128(sB_addr + (uint32_t)((dbg & 8) ? 0 : stage) * B_KB_BYTES);
+                    const uint32_t a_tmem = tmem_base + A_COL0 + (uint32_t)((dbg & 16) ? 0 : kb) * (KB_ELEMS / 2);
+                    if (!(dbg & 1)) {
 #pragma unroll
-                    for (int k4 = 0; k4 < KB_ELEMS / 16; ++k4) {
-                        const uint64_t bd = umma_desc_sw128(b_addr + k4 * 32);
-                        if (!(dbg & 1)) umma_bf16_ts(d_tmem, a_tmem + k4 * 8, bd, idesc, (kb | k4) != 0 ? 1u : 0u);
+                        for (int k4 = 0; k4 < KB_ELEMS / 16; ++k4)   // +32 bytes per K=16 step = +2 in the (addr >> 4) field
+                            umma_bf16_ts(d_tmem, a_tmem + k4 * 8, bd0 + (uint64_t)(k4 * 2), idesc, (kb | k4) != 0 ? 1u : 0u);
                     }
-                    umma_commit(&empty[stage]);           // smem slot reusable once these MMAs retire
-                    if (++stage == stages) { stage = 0; phase ^= 1; }
+                    // ring slots are handed back kGroup at a time: every commit drains the tensor pipe
+                    if (stage % kGroup == kGroup - 1) umma_commit(&empty[stage / kGroup]);
+                    if (kb == nkb - 1) umma_commit(&tmem_full[acc]);      // accumulator complete
                 }
-                umma_commit(&tmem_full[acc]);             // accumulator complete
+                __syncwarp();
+                if (++stage == stages) { stage = 0; phase ^= 1; }
             }
+        }
+        if ((dbg & 128) && blockIdx.x == 0 && lane == 0) {
+            long long c1 = clock64(), t1;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+            printf("[scan_mma dbg] issue loop: %d tiles, %lld cycles, %lld ns -> %.1f cycles/MMA, %.0f MHz\n", it, c1 - dbg_c0,
+                   t1 - dbg_t0, (double)(c1 - dbg_c0) / ((double)it * nkb * 4), (double)(c1 - dbg_c0) / (double)(t1 - dbg_t0) * 1e3);
         }
     } else if (warp >= 4) {
         const int ew = warp - 4;                          // == warp % 4: TMEM lanes [32*ew, 32*ew+32)
-        const int t = ew * 32 + lane;                     // query within the tile
-        const int q = q_tile * QT + t;
+        // TMEM lane ew*32+lane serves query (lane*4 + ew) of the tile: a small batch is spread over all
+        // four epilogue warps
+        const int q = q_tile * QT + lane * 4 + ew;
         const uint32_t lane_base = tmem_base + ((uint32_t)(ew * 32) << 16);
         // ---- query tile -> tensor memory: lane t holds query q, column c holds elements 2c, 2c+1
         {
@@ -247,6 +355,29 @@ scan_mma_bf16_kernel(const __grid_constant__ CUtensorMap tmS,
             __syncwarp();
             if (lane == 0) mbar_arrive(a_full);
         }
+        if (BOOT) {
+            // threshold bootstrap: only the per-query maximum of every sample tile is kept
+            int it = 0;
+            for (int tile = group; tile < n_tiles; tile += n_groups, ++it) {
+                const int acc = it & 1;
+                const uint32_t acc_phase = (it >> 1) & 1;
+                mbar_wait(&tmem_full[acc], acc_phase);
+                tc_fence_after();
+                const int valid = (n - tile * NT) < NT ? (n - tile * NT) : NT;
+                float m = VQ_NEG_INF;
+#pragma unroll 1
+                for (int c0 = 0; c0 < NT; c0 += 32) {
+                    uint32_t v[32];
+                    tmem_ld32(lane_base + (uint32_t)(acc * NT + c0), v);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) m = (c0 + j < valid) ? fmaxf(m, __uint_as_float(v[j])) : m;
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+                part_s[(size_t)tile * b_pad + q] = m;
+            }
+        } else {
         // top-k list of this thread's query, in registers, WORST first: slots [0,k) are live and
         // ascending, slots [k,KL) hold +inf so a bubble pass stops in front of them.  The running
         // k-th best is therefore always ls[0] (a static register, no dynamic indexing).
@@ -259,8 +390,8 @@ scan_mma_bf16_kernel(const __grid_constant__ CUtensorMap tmS,
         for (int tile = group; tile < n_tiles; tile += n_groups, ++it) {
             const int acc = it & 1;
             const uint32_t acc_phase = (it >> 1) & 1;
-            // k-th best any CTA has published for this query; ties with it are kept (>=) so the
-            // (score desc, row asc) rule still sees every candidate it needs
+            // k-th best any CTA has published for this query (or the bootstrap bound); ties with it are
+            // kept (>=) so the (score desc, row asc) rule still sees every candidate it needs
             const float g = *reinterpret_cast<volatile float*>(gtau + q);
             const float g_keep = (g == VQ_NEG_INF) ? g : nextafterf(g, VQ_NEG_INF);
             float thr = fmaxf(ls[0], g_keep);
@@ -268,40 +399,19 @@ scan_mma_bf16_kernel(const __grid_constant__ CUtensorMap tmS,
             tc_fence_after();
             const int row0 = tile * NT;
             const int valid = (n - row0) < NT ? (n - row0) : NT;
+            const int n_chunks = (dbg & 4) ? 0 : NT / 32;
+            // two register buffers: the tcgen05.ld of chunk c+1 is in flight while chunk c is filtered
+            uint32_t va[32], vb[32];
+            if (n_chunks > 0) tmem_ld32_issue(lane_base + (uint32_t)(acc * NT), va);
 #pragma unroll 1
-            for (int c0 = 0; c0 < ((dbg & 4) ? 0 : NT); c0 += 32) {
-                uint32_t v[32];
-                tmem_ld32(lane_base + (uint32_t)(acc * NT + c0), v);
-                // branch-free filter (a stale threshold only lets more through; re-checked below)
-                unsigned mask = 0;
-#pragma unroll
-                for (int j = 0; j < 32; ++j) mask |= (__uint_as_float(v[j]) > thr) ? (1u << j) : 0u;
-                const int left = valid - c0;
-                if (left < 32) mask &= left > 0 ? ((1u << left) - 1u) : 0u;
-                while (mask) {
-                    const int j = __ffs(mask) - 1;
-                    mask &= mask - 1;
-                    float s = __uint_as_float(v[0]);
-#pragma unroll
-                    for (int jj = 1; jj < 32; ++jj) s = (j == jj) ? __uint_as_float(v[jj]) : s;
-                    if (s > thr) {
-                        // replace the current k-th best, then one bubble pass restores the order.  Rows
-                        // arrive in ascending order inside a CTA, so with the strict comparison equal
-                        // scores end up in ascending-row order (the engine's tie rule).
-                        ls[0] = s;
-                        lr[0] = row0 + c0 + j;
-#pragma unroll
-                        for (int i = 0; i + 1 < KL; ++i) {
-                            const bool sw = ls[i] > ls[i + 1];
-                            const float a0 = ls[i], a1 = ls[i + 1];
-                            const int r0 = lr[i], r1 = lr[i + 1];
-                            ls[i] = sw ? a1 : a0;
-                            ls[i + 1] = sw ? a0 : a1;
-                            lr[i] = sw ? r1 : r0;
-                            lr[i + 1] = sw ? r0 : r1;
-                        }
-                        thr = fmaxf(ls[0], g_keep);
-                    }
+            for (int c = 0; c < n_chunks; c += 2) {
+                tmem_ld_wait(va);
+                if (c + 1 < n_chunks) tmem_ld32_issue(lane_base + (uint32_t)(acc * NT + (c + 1) * 32), vb);
+                filter_insert<KL>(va, row0 + c * 32, valid - c * 32, g_keep, thr, ls, lr);
+                if (c + 1 < n_chunks) {
+                    tmem_ld_wait(vb);
+                    if (c + 2 < n_chunks) tmem_ld32_issue(lane_base + (uint32_t)(acc * NT + (c + 2) * 32), va);
+                    filter_insert<KL>(vb, row0 + (c + 1) * 32, valid - (c + 1) * 32, g_keep, thr, ls, lr);
                 }
             }
             tc_fence_before();
@@ -319,6 +429,7 @@ scan_mma_bf16_kernel(const __grid_constant__ CUtensorMap tmS,
                 part_s[dst + (k - 1 - i)] = ls[i];
                 part_r[dst + (k - 1 - i)] = (lr[i] == VQ_EMPTY_ROW) ? -1 : lr[i];
             }
+        }
         }
     }
     tc_fence_before();
@@ -354,6 +465,45 @@ prep_queries_bf16_kernel(const float* __restrict__ src, int b, int dim, int src_
     }
     for (int c = lane; c < ld; c += 32)
         o[c] = __float2bfloat16_rn(c < dim ? (mode == VQ_NORM_NONE ? s[c] : s[c] / d) : 0.f);
+}
+
+// Threshold bootstrap, step 2: the k-th largest of the n_t per-tile maxima of a query is reached by k
+// distinct store rows, i.e. it is a valid lower bound of the global k-th best score.  One warp per
+// query, n_t <= kMaxBootTiles values held 8 per lane, k rounds of "extract the maximum".
+__global__ void __launch_bounds__(256)
+boot_select_kernel(const float* __restrict__ boot_max, int n_t, int b_pad, int k, float* __restrict__ gtau) {
+    const int lane = threadIdx.x & 31;
+    const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (q >= b_pad) return;
+    constexpr int PER = kMaxBootTiles / 32;
+    float v[PER];
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+        const int t = i * 32 + lane;
+        v[i] = t < n_t ? boot_max[(size_t)t * b_pad + q] : VQ_NEG_INF;
+    }
+    float kth = VQ_NEG_INF;
+    for (int r = 0; r < k; ++r) {
+        float m = v[0];
+#pragma unroll
+        for (int i = 1; i < PER; ++i) m = fmaxf(m, v[i]);
+        float wm = m;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) wm = fmaxf(wm, __shfl_xor_sync(0xffffffffu, wm, o));
+        kth = wm;
+        if (wm == VQ_NEG_INF) break;                       // fewer than k finite maxima (warp-uniform)
+        const unsigned owners = __ballot_sync(0xffffffffu, m == wm);
+        if (lane == __ffs(owners) - 1) {                   // remove ONE instance
+            bool done = false;
+#pragma unroll
+            for (int i = 0; i < PER; ++i) {
+                const bool hit = !done && v[i] == wm;
+                v[i] = hit ? VQ_NEG_INF : v[i];
+                done = done || hit;
+            }
+        }
+    }
+    if (lane == 0) gtau[q] = (n_t >= k) ? kth : VQ_NEG_INF;
 }
 
 // ------------------------------------------------------------------------------------ host
@@ -411,10 +561,10 @@ inline size_t align256(size_t v) { return (v + 255) / 256 * 256; }
 
 struct MmaPlan {
     int nkb, nt, n_qt, b_pad, groups, grid, stages;
-    size_t smem, qbf_bytes, tau_bytes, part_bytes;
+    int boot_tiles, boot_groups;                 // threshold bootstrap (0 = off)
+    size_t smem, qbf_bytes, tau_bytes, part_bytes, boot_bytes;
 };
 MmaPlan plan(int64_t n, int ld, int b, int k) {
-    (void)k;
     MmaPlan p;
     p.nkb = ld / KB_ELEMS;
     // TMEM budget: 2 accumulators of nt columns + ld/2 columns of resident queries <= 512
@@ -430,7 +580,15 @@ MmaPlan plan(int64_t n, int ld, int b, int k) {
     p.grid = p.groups * p.n_qt;
     const size_t stage_bytes = (size_t)(p.nt ? p.nt : 128) * 128;
     int st = (int)((200 * 1024) / stage_bytes);
-    p.stages = st > 12 ? 12 : st;
+    p.stages = (st > 12 ? 12 : st) / kGroup * kGroup;
+    // bootstrap the per-query threshold from a sample of tiles when the scan is long enough to pay for
+    // two extra (tiny) launches: sample >= 4k tiles so that the k-th largest tile maximum is a strong bound
+    int bt = sms > 4 * k ? sms : 4 * k;
+    if (bt > kMaxBootTiles) bt = kMaxBootTiles;
+    static const bool boot_on = getenv("VQ_MMA_BOOT") ? atoi(getenv("VQ_MMA_BOOT")) != 0 : true;
+    p.boot_tiles = (boot_on && p.nt && n_tiles >= 16LL * bt && bt >= k) ? bt : 0;
+    p.boot_groups = p.boot_tiles ? (p.boot_tiles < (int)groups ? p.boot_tiles : (int)groups) : 0;
+    p.boot_bytes = align256((size_t)kMaxBootTiles * p.b_pad * 4);
     p.smem = 1024 + (size_t)p.stages * stage_bytes + 256;
     p.qbf_bytes = align256((size_t)p.b_pad * ld * 2);
     p.tau_bytes = align256((size_t)p.b_pad * 4);
@@ -438,33 +596,48 @@ MmaPlan plan(int64_t n, int ld, int b, int k) {
     return p;
 }
 
-template <int KL, int NT>
+template <int KL, int NT, bool BOOT>
 cudaError_t launch_mma(const MmaPlan& p, const CUtensorMap& tmS, const __nv_bfloat16* qbf, float* gtau, int n, int ld, int k,
                        float* part_s, int* part_r, int dbg, cudaStream_t stream) {
-    auto kern = scan_mma_bf16_kernel<KL, NT>;
+    auto kern = scan_mma_bf16_kernel<KL, NT, BOOT>;
     static bool attr_done = false;
     if (!attr_done) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return e;
         attr_done = true;
     }
-    kern<<<p.grid, kThreads, p.smem, stream>>>(tmS, qbf, gtau, n, ld, p.nkb, p.n_qt, k, p.stages, p.b_pad, part_s, part_r, dbg);
+    const int grid = BOOT ? p.boot_groups * p.n_qt : p.grid;
+    kern<<<grid, kThreads, p.smem, stream>>>(tmS, qbf, gtau, n, ld, p.nkb, p.n_qt, k, p.stages, p.b_pad, part_s, part_r, dbg);
     return cudaGetLastError();
 }
 
 int run_prepared(const MmaPlan& p, const CUtensorMap& tmS, const __nv_bfloat16* qbf, float* gtau, int n, int ld, int k,
-                 float* part_s, int* part_r, cudaStream_t stream) {
+                 float* part_s, int* part_r, float* boot_max, cudaStream_t stream, int* launches) {
     const int dbg = getenv("VQ_MMA_DEBUG") ? atoi(getenv("VQ_MMA_DEBUG")) : 0;
     cudaError_t e;
+    *launches = 1;
+    if (p.boot_tiles) {
+        // sample pass over the first boot_tiles full tiles: per-tile maxima -> boot_max, then gtau
+        const int n_boot = p.boot_tiles * p.nt;
+        e = p.nt == 128 ? launch_mma<1, 128, true>(p, tmS, qbf, gtau, n_boot, ld, k, boot_max, nullptr, dbg, stream)
+                        : launch_mma<1, 64, true>(p, tmS, qbf, gtau, n_boot, ld, k, boot_max, nullptr, dbg, stream);
+        if (e != cudaSuccess) {
+            vq_set_error("launch of scan_mma_bf16_kernel<boot> failed: %s", cudaGetErrorString(e));
+            return VQ_ECUDA;
+        }
+        boot_select_kernel<<<(p.b_pad + 7) / 8, 256, 0, stream>>>(boot_max, p.boot_tiles, p.b_pad, k, gtau);
+        VQ_LAUNCH_CHECK("boot_select_kernel");
+        *launches = 3;
+    }
     vq_prof_begin(stream);
     if (p.nt == 128)
-        e = k <= 16 ? launch_mma<16, 128>(p, tmS, qbf, gtau, n, ld, k, part_s, part_r, dbg, stream)
-          : k <= 32 ? launch_mma<32, 128>(p, tmS, qbf, gtau, n, ld, k, part_s, part_r, dbg, stream)
-                    : launch_mma<64, 128>(p, tmS, qbf, gtau, n, ld, k, part_s, part_r, dbg, stream);
+        e = k <= 16 ? launch_mma<16, 128, false>(p, tmS, qbf, gtau, n, ld, k, part_s, part_r, dbg, stream)
+          : k <= 32 ? launch_mma<32, 128, false>(p, tmS, qbf, gtau, n, ld, k, part_s, part_r, dbg, stream)
+                    : launch_mma<64, 128, false>(p, tmS, qbf, gtau, n, ld, k, part_s, part_r, dbg, stream);
     else
-        e = k <= 16 ? launch_mma<16, 64>(p, tmS, qbf, gtau, n, ld, k, part_s, part_r, dbg, stream)
-          : k <= 32 ? launch_mma<32, 64>(p, tmS, qbf, gtau, n, ld, k, part_s, part_r, dbg, stream)
-                    : launch_mma<64, 64>(p, tmS, qbf, gtau, n, ld, k, part_s, part_r, dbg, stream);
+        e = k <= 16 ? launch_mma<16, 64, false>(p, tmS, qbf, gtau, n, ld, k, part_s, part_r, dbg, stream)
+          : k <= 32 ? launch_mma<32, 64, false>(p, tmS, qbf, gtau, n, ld, k, part_s, part_r, dbg, stream)
+                    : launch_mma<64, 64, false>(p, tmS, qbf, gtau, n, ld, k, part_s, part_r, dbg, stream);
     vq_prof_end(stream);
     if (e != cudaSuccess) {
         vq_set_error("launch of scan_mma_bf16_kernel failed: %s", cudaGetErrorString(e));
@@ -488,7 +661,7 @@ size_t vq_scan_mma_prepared_workspace(int64_t n, int ld, int b, int k) {
     // valid for every batch <= b: groups * b_pad <= max(SMs, n_qt) * 128 whatever the batch
     const MmaPlan p = plan(n, ld, b, k);
     const size_t lists = (size_t)(vq_num_sms() > p.n_qt ? vq_num_sms() : p.n_qt) * QT;
-    return p.tau_bytes + 2 * align256(lists * k * 4) + 256;
+    return p.tau_bytes + 2 * align256(lists * k * 4) + p.boot_bytes + 256;
 }
 int vq_scan_mma_prepared(const void* store, int64_t n, int ld, const void* qbf, int b, int k, float* out_scores,
                          int32_t* out_rows, void* ws_v, size_t ws_bytes, cudaStream_t stream) {
@@ -497,21 +670,23 @@ int vq_scan_mma_prepared(const void* store, int64_t n, int ld, const void* qbf, 
         return VQ_EUNSUPPORTED;
     }
     const MmaPlan p = plan(n, ld, b, k);
-    if (ws_bytes < p.tau_bytes + 2 * p.part_bytes) {
-        vq_set_error("scan_mma_prepared: workspace too small (%zu < %zu)", ws_bytes, p.tau_bytes + 2 * p.part_bytes);
+    if (ws_bytes < p.tau_bytes + 2 * p.part_bytes + p.boot_bytes) {
+        vq_set_error("scan_mma_prepared: workspace too small (%zu < %zu)", ws_bytes, p.tau_bytes + 2 * p.part_bytes + p.boot_bytes);
         return VQ_EWORKSPACE;
     }
     unsigned char* ws = (unsigned char*)ws_v;
     float* gtau = (float*)ws;
     float* part_s = (float*)(ws + p.tau_bytes);
     int* part_r = (int*)(ws + p.tau_bytes + p.part_bytes);
+    float* boot_max = (float*)(ws + p.tau_bytes + 2 * p.part_bytes);
     fill_neg_inf_kernel<<<(p.b_pad + 255) / 256, 256, 0, stream>>>(gtau, p.b_pad);
     CUtensorMap tmS;
     if (!get_map_bf16(&tmS, store, (uint64_t)n, (uint64_t)ld, (uint32_t)p.nt)) {
         vq_set_error("scan_mma: cuTensorMapEncodeTiled failed");
         return VQ_ECUDA;
     }
-    int rc = run_prepared(p, tmS, (const __nv_bfloat16*)qbf, gtau, (int)n, ld, k, part_s, part_r, stream);
+    int nl = 0;
+    int rc = run_prepared(p, tmS, (const __nv_bfloat16*)qbf, gtau, (int)n, ld, k, part_s, part_r, boot_max, stream, &nl);
     if (rc) return rc;
     return vq_topk_merge_launch(part_s, part_r, p.groups, (long long)p.b_pad * k, b, k, nullptr, k, out_scores, out_rows, 0, 0, stream);
 }
@@ -526,7 +701,7 @@ bool vq_scan_mma_supported(int64_t n, int dim, int ld, int store_dtype, int b, i
 size_t vq_scan_mma_workspace(int64_t n, int ld, int store_dtype, int b, int k) {
     if (store_dtype != VQ_BF16 || b < 1 || k < 1 || k > kMaxK || n < 1 || ld > 768) return 0;
     const MmaPlan p = plan(n, ld, b, k);
-    return p.qbf_bytes + p.tau_bytes + 2 * p.part_bytes + 256;
+    return p.qbf_bytes + p.tau_bytes + 2 * p.part_bytes + p.boot_bytes + 256;
 }
 
 // queries: raw fp32 [b, dim]; normalisation (query_norm) is fused into the bf16 conversion.
@@ -538,7 +713,7 @@ int vq_scan_mma_run(const void* store, int64_t n, int dim, int ld, int store_dty
         return VQ_EUNSUPPORTED;
     }
     const MmaPlan p = plan(n, ld, b, k);
-    if (ws_bytes < p.qbf_bytes + p.tau_bytes + 2 * p.part_bytes) {
+    if (ws_bytes < p.qbf_bytes + p.tau_bytes + 2 * p.part_bytes + p.boot_bytes) {
         vq_set_error("scan_mma: workspace too small");
         return VQ_EWORKSPACE;
     }
@@ -547,6 +722,7 @@ int vq_scan_mma_run(const void* store, int64_t n, int dim, int ld, int store_dty
     float* gtau = (float*)(ws + p.qbf_bytes);
     float* part_s = (float*)(ws + p.qbf_bytes + p.tau_bytes);
     int* part_r = (int*)(ws + p.qbf_bytes + p.tau_bytes + p.part_bytes);
+    float* boot_max = (float*)(ws + p.qbf_bytes + p.tau_bytes + 2 * p.part_bytes);
     prep_queries_bf16_kernel<<<(p.b_pad + 7) / 8, 256, 0, stream>>>(queries, b, dim, dim, qbf, ld, p.b_pad, query_norm, gtau);
     VQ_LAUNCH_CHECK("prep_queries_bf16_kernel");
     CUtensorMap tmS;
@@ -554,10 +730,11 @@ int vq_scan_mma_run(const void* store, int64_t n, int dim, int ld, int store_dty
         vq_set_error("scan_mma: cuTensorMapEncodeTiled failed");
         return VQ_ECUDA;
     }
-    int rc = run_prepared(p, tmS, qbf, gtau, (int)n, ld, k, part_s, part_r, stream);
+    int nl = 0;
+    int rc = run_prepared(p, tmS, qbf, gtau, (int)n, ld, k, part_s, part_r, boot_max, stream, &nl);
     if (rc) return rc;
     rc = vq_topk_merge_launch(part_s, part_r, p.groups, (long long)p.b_pad * k, b, k, nullptr, k, out_scores, out_rows, 0, 0, stream);
     if (rc) return rc;
-    *launches = 3;
+    *launches = 2 + nl;
     return VQ_OK;
 }
