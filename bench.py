@@ -179,14 +179,13 @@ def run_ours(args):
         s, e = max(lo, b0), min(hi, b0 + blk)
         store.append(x[s - b0: e - b0], _lib.NORM_PLAIN)  # kernel (a): L2-normalise on ingest
     scanner = engine.Scanner(dev)
-    uncertified = torch.zeros((), dtype=torch.int64, device=dev)
     elem = 2 if two_stage else 4
+    last = {"bad": None}            # certificate of the most recent local search ([b] int32 on the device)
 
     def local_search(q, k):
         if two_stage:
             s, r, bad = two_stage_search(scanner, store, q, k, args.path)
-            if bad is not None:
-                uncertified.add_(bad.sum())
+            last["bad"] = bad
             return s, r
         return scanner.scan(store.f32, store.n, DIM, q, k, _lib.NORM_EPS, args.path)
 
@@ -205,8 +204,10 @@ def run_ours(args):
     def measure(B, steps, warmup, with_e2e):
         host_q = torch.randn((B, DIM), generator=gq).pin_memory()
         dev_q = host_q.to(dev)
+        # one shard: the local search IS the answer (int32 rows); several: all-gather + merge (int64 rows)
+        search = (lambda qq, kk: local_search(qq, kk)) if world == 1 else searcher.search
         for _ in range(max(warmup, 3)):
-            searcher.search(dev_q, K_TOP)
+            search(dev_q, K_TOP)
         launches = scanner.last_launches + (1 if world > 1 else 0)   # + merge of the shard/merge layer
         path = scanner.last_path
         barrier()
@@ -215,7 +216,7 @@ def run_ours(args):
         if not args.no_graph:
             try:
                 from video_quierer_b200.graphs import GraphedSearch
-                graphed = GraphedSearch(lambda qq: searcher.search(qq, K_TOP), B, DIM, dev)
+                graphed = GraphedSearch(lambda qq: search(qq, K_TOP) + (last["bad"],), B, DIM, dev)
                 graphed.q.copy_(dev_q)
             except Exception as e:  # noqa: BLE001 — e.g. a collective that refuses capture: run eagerly
                 print(f"[bench] CUDA graph capture unavailable ({type(e).__name__}: {e}); eager launches", file=sys.stderr)
@@ -226,7 +227,7 @@ def run_ours(args):
             if graphed is not None:
                 graphed.graph.replay()
                 return graphed.out
-            return searcher.search(dev_q, K_TOP)
+            return search(dev_q, K_TOP)
 
         # -- timed region 1: device-resident queries, CUDA events on the launch stream
         if flush is None:
@@ -255,7 +256,7 @@ def run_ours(args):
             if flush is not None:
                 flush.zero_()
             scanner.scan(store.bf16 if two_stage else store.f32, store.n, DIM, dev_q,
-                         (32 if two_stage else K_TOP), _lib.NORM_EPS, args.path)
+                         (int(os.environ.get("VQ_KCAND", 0)) or 32) if two_stage else K_TOP, _lib.NORM_EPS, args.path)
             kern.append(lib.vq_profile_last_kernel_ms())
         lib.vq_profile_enable(0)
         kern = sorted(v for v in kern if v > 0)
@@ -263,28 +264,31 @@ def run_ours(args):
         e2e_ms = None
         if with_e2e:
             # -- timed region 2: end to end with HOST (pinned) buffers: H2D + search + D2H (+ fallback)
-            out_rows = torch.empty((B, K_TOP), dtype=torch.int64).pin_memory()
+            out_rows = torch.empty((B, K_TOP), dtype=torch.int64 if world > 1 else torch.int32).pin_memory()
             out_scores = torch.empty((B, K_TOP), dtype=torch.float32).pin_memory()
-            flag = torch.zeros((), dtype=torch.int64).pin_memory()
+            out_bad = torch.zeros((B,), dtype=torch.int32).pin_memory()
+            n_fallback = [0]
 
             def step_e2e():
-                uncertified.zero_()
                 if graphed is not None:
-                    s, r = graphed(host_q)                     # H2D of this step's inputs + one graph launch
+                    res = graphed(host_q)                      # H2D of this step's inputs + one graph launch
                     q = graphed.q
                 else:
                     q = host_q.to(dev, non_blocking=True)      # H2D of this step's inputs
-                    s, r = searcher.search(q, K_TOP)
+                    res = search(q, K_TOP) + (last["bad"],)
+                s, r, bad = res
                 out_scores.copy_(s, non_blocking=True)         # D2H of the step's result
                 out_rows.copy_(r, non_blocking=True)
-                flag.copy_(uncertified, non_blocking=True)
+                if bad is not None:
+                    out_bad.copy_(bad, non_blocking=True)      # + its per-query certificate
                 torch.cuda.synchronize()
-                if int(flag) and world == 1:                   # never on this data; kept for correctness
-                    s2, r2, bad = two_stage_search(scanner, store, q, K_TOP, args.path)
-                    idx = torch.nonzero(bad).flatten()
-                    sf, rf = exact_fallback(scanner, store, q, K_TOP, idx)
-                    out_scores[idx.cpu()] = sf.cpu()
-                    out_rows[idx.cpu()] = rf.cpu().long()
+                if bad is not None and world == 1 and bool(out_bad.any()):
+                    # queries whose two-stage result could not be certified: exact fp32 scan, inside the timing
+                    idx = torch.nonzero(out_bad).flatten()
+                    sf, rf = exact_fallback(scanner, store, q, K_TOP, idx.to(dev))
+                    out_scores[idx] = sf.cpu()
+                    out_rows[idx] = rf.cpu().to(out_rows.dtype)
+                    n_fallback[0] += len(idx)
 
             for _ in range(3):
                 step_e2e()
@@ -298,8 +302,9 @@ def run_ours(args):
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dev_ms, e2e_ms = (float(v) for v in t.cpu())
+        unc = int(last["bad"].sum().item()) if last["bad"] is not None else 0
         return {"B": B, "dev_ms": dev_ms, "e2e_ms": e2e_ms, "kernel_ms": kmed, "launches": launches, "path": path,
-                "graph": graphed is not None}
+                "graph": graphed is not None, "uncertified": unc}
 
     with ClockSampler(local) as clocks:
         main = measure(args.batch, args.steps, args.warmup, True)
@@ -308,7 +313,6 @@ def run_ours(args):
             for B in (1, 32, 1024):
                 if B != args.batch:
                     sweep.append(measure(B, min(args.steps, 30), 3, False))
-    n_unc = int(uncertified.item())
 
     if rank == 0:
         hbm_peak, tf_peak, peak_src = _peaks()
@@ -340,12 +344,13 @@ def run_ours(args):
             "config": dict(_config(B, world, main["path"], two_stage), launch="cuda-graph" if main["graph"] else "eager"),
             "clocks": clocks.summary(),
             "e2e": {"value": B * args.steps / (main["e2e_ms"] * 1e-3), "unit": "queries/s",
-                    "h2d_bytes_per_step": B * DIM * 4, "d2h_bytes_per_step": B * K_TOP * 12 + 8},
+                    "h2d_bytes_per_step": B * DIM * 4, "d2h_bytes_per_step": B * K_TOP * (12 if world > 1 else 8) + (B * 4 if two_stage else 0)},
             "gpu_launches": main["launches"] * args.steps,
             "roofline": roof(main),
-            "uncertified_queries": n_unc,
+            "uncertified_queries_per_batch": main["uncertified"],
             "sweep": [{"batch": m["B"], "value": m["B"] * min(args.steps, 30) / (m["dev_ms"] * 1e-3),
-                       "ms_per_step": m["dev_ms"] / min(args.steps, 30), "roofline": roof(m)} for m in sweep],
+                       "ms_per_step": m["dev_ms"] / min(args.steps, 30), "roofline": roof(m),
+                       "uncertified_queries_per_batch": m["uncertified"]} for m in sweep],
         }
         if cpu is not None:
             line["cpu_baseline"] = {"value": cpu[0], "unit": "queries/s", "cores": cpu[1], "kind": "port", "sample": cpu[2]}

@@ -113,6 +113,23 @@ int vq_rescore_topk(const float* store_f32, int64_t n, int dim, int ld,
                     float* out_scores, int32_t* out_rows,
                     void* workspace, size_t workspace_bytes, void* stream);
 
+/* Two-stage exact search in ONE call (throughput mode of (b)+(c)): the tensor-core scan of the bf16
+ * copy selects k_cand candidates per query, they are re-scored exactly (fp32 FMA, same arithmetic as
+ * vq_rescore_topk) from the fp32 copy of the SAME rows, and the best k by exact score are returned.
+ * Replaces the same reference code as vq_scan_topk (video_search_overhaul.py:40-64).
+ *   store_bf16 / store_f32  [n, ld] twins (same ld, ld % 64 == 0)
+ *   queries    [b, dim] raw fp32; query_norm as in vq_scan_topk
+ *   score_eps  bound on |bf16-operand score - fp32 score| (2^-8 * max row norm + slack)
+ *   out_uncertified [b] int32: 0 = the result is provably the exact top-k (every row outside the
+ *              candidate set has exact score <= k_cand-th candidate score + score_eps < k-th exact
+ *              score); 1 = could not be certified (near-duplicate heavy data): re-run that query with
+ *              vq_scan_topk on the fp32 store.                 [kernels: scan_mma_bf16, scan_finish] */
+size_t vq_search_two_stage_workspace_bytes(int64_t n, int dim, int ld, int b, int k_cand);
+int vq_search_two_stage(const void* store_bf16, const float* store_f32, int64_t n, int dim, int ld,
+                        const float* queries, int b, int k, int k_cand, int query_norm, float score_eps,
+                        float* out_scores, int32_t* out_rows, int32_t* out_uncertified,
+                        void* workspace, size_t workspace_bytes, void* stream);
+
 /* (d) HNSW greedy/beam search, one warp per query.                     [kernel: hnsw_search]
  * Replaces: HNSWIndex.search / OptimizedHNSWIndex.search, src/indexes/hnsw.py:238-280,
  * :488-528 and _search_layer :76-121 (same stop rule :103 and admit rule :113).

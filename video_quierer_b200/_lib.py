@@ -32,6 +32,9 @@ SIGNATURES = {
     "vq_profile_enable": (_i32, [_i32]),
     "vq_profile_last_kernel_ms": (C.c_float, []),
     "vq_rescore_topk": (_i32, [_vp, _i64, _i32, _i32, _vp, _i32, _vp, _i32, _i32, _vp, _vp, _vp, _sz, _vp]),
+    "vq_search_two_stage_workspace_bytes": (_sz, [_i64, _i32, _i32, _i32, _i32]),
+    "vq_search_two_stage": (_i32, [_vp, _vp, _i64, _i32, _i32, _vp, _i32, _i32, _i32, _i32, C.c_float,
+                                   _vp, _vp, _vp, _vp, _sz, _vp]),
     "vq_hnsw_workspace_bytes": (_sz, [_i32, _i32, _i32]),
     "vq_hnsw_search": (_i32, [_vp, _i64, _i32, _i32, _i32, _vp, _vp, _i32, _vp, _vp, _i32, _i32, _i32, _i32,
                               _vp, _i32, _i32, _i32, _vp, _vp, _vp, _i32, _vp, _sz, _vp]),

@@ -21,8 +21,8 @@ int vq_rescore_launch(const float* store, int ld, const float* queries, int qld,
 bool vq_scan_mma_supported(int64_t n, int dim, int ld, int store_dtype, int b, int k);
 size_t vq_scan_mma_workspace(int64_t n, int ld, int store_dtype, int b, int k);
 int vq_scan_mma_run(const void* store, int64_t n, int dim, int ld, int store_dtype, const float* queries, int query_norm,
-                    int b, int k, float* out_scores, int32_t* out_rows, void* ws, size_t ws_bytes, cudaStream_t stream,
-                    int* launches);
+                    int b, int k_sel, const float* store_f32, float eps, int k_out, float* out_scores, int32_t* out_rows,
+                    int32_t* out_bad, void* ws, size_t ws_bytes, cudaStream_t stream, int* launches);
 
 // ----------------------------------------------------------------------------- error state
 static thread_local char g_err[512] = "";
@@ -188,8 +188,8 @@ int vq_scan_topk(const void* store, int64_t n, int dim, int ld, int store_dtype,
     unsigned char* ws = (unsigned char*)workspace;
     if (use_mma) {
         int l2 = 0;
-        rc = vq_scan_mma_run(store, n, dim, ld, store_dtype, queries, query_norm, b, k, out_scores, out_rows, ws,
-                             workspace_bytes, stream, &l2);
+        rc = vq_scan_mma_run(store, n, dim, ld, store_dtype, queries, query_norm, b, k, nullptr, 0.f, k, out_scores,
+                             out_rows, nullptr, ws, workspace_bytes, stream, &l2);
         if (rc) return rc;
         vq_note_launch("scan_mma_bf16", l2);
         return VQ_OK;
@@ -255,6 +255,40 @@ int vq_rescore_topk(const float* store_f32, int64_t n, int dim, int ld, const fl
         rc = vq_topk_merge_launch(tmp, cand_rows, 1, (long long)b * k_cand, b, k_cand, nullptr, k, out_scores, out_rows, 0, 0, stream);
     vq_note_launch("rescore_rows", 2);
     return rc;
+}
+
+size_t vq_search_two_stage_workspace_bytes(int64_t n, int dim, int ld, int b, int k_cand) {
+    (void)dim;
+    if (n <= 0 || b <= 0 || k_cand <= 0) return 256;
+    return vq_scan_mma_workspace(n, ld, VQ_BF16, b, k_cand) + 256;
+}
+
+int vq_search_two_stage(const void* store_bf16, const float* store_f32, int64_t n, int dim, int ld,
+                        const float* queries, int b, int k, int k_cand, int query_norm, float score_eps,
+                        float* out_scores, int32_t* out_rows, int32_t* out_uncertified,
+                        void* workspace, size_t workspace_bytes, void* stream_v) {
+    cudaStream_t stream = (cudaStream_t)stream_v;
+    int rc = check_store(n, dim, ld, VQ_BF16);
+    if (rc) return rc;
+    VQ_CHECK_ARG(b >= 0 && k > 0 && k_cand >= k, "need b >= 0 and 0 < k <= k_cand (b=%d k=%d k_cand=%d)", b, k, k_cand);
+    VQ_CHECK_ARG(query_norm >= VQ_NORM_NONE && query_norm <= VQ_NORM_PLAIN, "bad query_norm %d", query_norm);
+    VQ_CHECK_ARG(score_eps >= 0.f, "score_eps must be >= 0");
+    if (b == 0) { vq_note_launch("none", 0); return VQ_OK; }
+    VQ_CHECK_ARG(n > 0, "two-stage search needs a non-empty store");
+    VQ_CHECK_ARG(store_bf16 && store_f32 && queries && out_scores && out_rows && out_uncertified && workspace,
+                 "NULL pointer argument");
+    VQ_CHECK_ARG(((uintptr_t)workspace & 255) == 0, "workspace must be 256-byte aligned");
+    VQ_CHECK_ARG(((uintptr_t)store_bf16 & 15) == 0 && ((uintptr_t)store_f32 & 15) == 0, "stores must be 16-byte aligned");
+    if (!vq_scan_mma_supported(n, dim, ld, VQ_BF16, b, k_cand)) {
+        vq_set_error("two-stage search does not support n=%lld dim=%d ld=%d b=%d k_cand=%d", (long long)n, dim, ld, b, k_cand);
+        return VQ_EUNSUPPORTED;
+    }
+    int launches = 0;
+    rc = vq_scan_mma_run(store_bf16, n, dim, ld, VQ_BF16, queries, query_norm, b, k_cand, store_f32, score_eps, k,
+                         out_scores, out_rows, out_uncertified, workspace, workspace_bytes, stream, &launches);
+    if (rc) return rc;
+    vq_note_launch("scan_mma_bf16+rescore", launches);
+    return VQ_OK;
 }
 
 }  // extern "C"

@@ -230,7 +230,8 @@ scan_mma_bf16_kernel(const __grid_constant__ CUtensorMap tmS,
                      const __nv_bfloat16* __restrict__ qbf,   // [b_pad, ld] normalised, zero padded
                      float* __restrict__ gtau,                // [b_pad] shared k-th best per query (-inf initialised)
                      int n, int ld, int nkb, int n_qt, int k, int stages, int b_pad,
-                     float* __restrict__ part_s, int* __restrict__ part_r, int dbg) {
+                     float* __restrict__ cand_s,              // [b_pad, cap] surviving candidates (BOOT: [tiles, b_pad] maxima)
+                     int* __restrict__ cand_r, int* __restrict__ cand_cnt, int cap, int dbg) {
     constexpr int B_KB_BYTES = NT * 128;
     constexpr uint32_t A_COL0 = 2 * NT;                         // first TMEM column of the query tile
     extern __shared__ unsigned char smem_raw[];
@@ -375,7 +376,7 @@ scan_mma_bf16_kernel(const __grid_constant__ CUtensorMap tmS,
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&tmem_empty[acc]);
-                part_s[(size_t)tile * b_pad + q] = m;
+                cand_s[(size_t)tile * b_pad + q] = m;
             }
         } else {
         // top-k list of this thread's query, in registers, WORST first: slots [0,k) are live and
@@ -422,12 +423,23 @@ scan_mma_bf16_kernel(const __grid_constant__ CUtensorMap tmS,
                 atomic_max_float(gtau + q, published);
             }
         }
-        const size_t dst = ((size_t)group * b_pad + q) * k;
+        // Write-out: only entries that can still belong to the global top-k, i.e. that reach the latest
+        // shared bound, are appended to the query's candidate buffer (one atomicAdd per thread).  The
+        // ~k..2k survivors per query replace groups*k list entries as the input of the final selection.
+        {
+            const float g = *reinterpret_cast<volatile float*>(gtau + q);
+            const float g_keep = (g == VQ_NEG_INF) ? g : nextafterf(g, VQ_NEG_INF);
+            int n_surv = 0;
 #pragma unroll
-        for (int i = 0; i < KL; ++i) {
-            if (i < k) {                                  // slot i is the (k-1-i)-th best
-                part_s[dst + (k - 1 - i)] = ls[i];
-                part_r[dst + (k - 1 - i)] = (lr[i] == VQ_EMPTY_ROW) ? -1 : lr[i];
+            for (int i = 0; i < KL; ++i) n_surv += (i < k && lr[i] != VQ_EMPTY_ROW && ls[i] > g_keep) ? 1 : 0;
+            int at = n_surv ? atomicAdd(cand_cnt + q, n_surv) : 0;
+            const size_t dst = (size_t)q * cap;
+#pragma unroll
+            for (int i = 0; i < KL; ++i) {
+                if (i < k && lr[i] != VQ_EMPTY_ROW && ls[i] > g_keep) {
+                    if (at < cap) { cand_s[dst + at] = ls[i]; cand_r[dst + at] = lr[i]; }
+                    ++at;
+                }
             }
         }
         }
@@ -444,12 +456,12 @@ scan_mma_bf16_kernel(const __grid_constant__ CUtensorMap tmS,
 // shared threshold array reset; one warp per row.
 __global__ void __launch_bounds__(256)
 prep_queries_bf16_kernel(const float* __restrict__ src, int b, int dim, int src_ld, __nv_bfloat16* __restrict__ dst, int ld,
-                         int b_pad, int mode, float* __restrict__ gtau) {
+                         int b_pad, int mode, float* __restrict__ gtau, int* __restrict__ cand_cnt) {
     const int lane = threadIdx.x & 31;
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= b_pad) return;
     __nv_bfloat16* o = dst + (size_t)row * ld;
-    if (lane == 0) gtau[row] = VQ_NEG_INF;
+    if (lane == 0) { gtau[row] = VQ_NEG_INF; cand_cnt[row] = 0; }
     if (row >= b) {
         for (int c = lane; c < ld; c += 32) o[c] = __float2bfloat16_rn(0.f);
         return;
@@ -469,40 +481,28 @@ prep_queries_bf16_kernel(const float* __restrict__ src, int b, int dim, int src_
 
 // Threshold bootstrap, step 2: the k-th largest of the n_t per-tile maxima of a query is reached by k
 // distinct store rows, i.e. it is a valid lower bound of the global k-th best score.  One warp per
-// query, n_t <= kMaxBootTiles values held 8 per lane, k rounds of "extract the maximum".
+// query: the maxima go to shared memory and every lane ranks its own values against all of them
+// (n_t <= kMaxBootTiles, no serial dependency chain); the value of rank k-1 is the bound.
 __global__ void __launch_bounds__(256)
 boot_select_kernel(const float* __restrict__ boot_max, int n_t, int b_pad, int k, float* __restrict__ gtau) {
-    const int lane = threadIdx.x & 31;
-    const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    __shared__ float vals[8][kMaxBootTiles];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int q = blockIdx.x * 8 + w;
     if (q >= b_pad) return;
-    constexpr int PER = kMaxBootTiles / 32;
-    float v[PER];
-#pragma unroll
-    for (int i = 0; i < PER; ++i) {
-        const int t = i * 32 + lane;
-        v[i] = t < n_t ? boot_max[(size_t)t * b_pad + q] : VQ_NEG_INF;
-    }
+    for (int t = lane; t < n_t; t += 32) vals[w][t] = boot_max[(size_t)t * b_pad + q];
+    __syncwarp();
     float kth = VQ_NEG_INF;
-    for (int r = 0; r < k; ++r) {
-        float m = v[0];
-#pragma unroll
-        for (int i = 1; i < PER; ++i) m = fmaxf(m, v[i]);
-        float wm = m;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) wm = fmaxf(wm, __shfl_xor_sync(0xffffffffu, wm, o));
-        kth = wm;
-        if (wm == VQ_NEG_INF) break;                       // fewer than k finite maxima (warp-uniform)
-        const unsigned owners = __ballot_sync(0xffffffffu, m == wm);
-        if (lane == __ffs(owners) - 1) {                   // remove ONE instance
-            bool done = false;
-#pragma unroll
-            for (int i = 0; i < PER; ++i) {
-                const bool hit = !done && v[i] == wm;
-                v[i] = hit ? VQ_NEG_INF : v[i];
-                done = done || hit;
-            }
+    for (int t = lane; t < n_t; t += 32) {
+        const float v = vals[w][t];
+        int rank = 0;                                      // values strictly better (ties broken by index)
+        for (int j = 0; j < n_t; ++j) {
+            const float o = vals[w][j];
+            rank += (o > v || (o == v && j < t)) ? 1 : 0;
         }
+        if (rank == k - 1) kth = v;                        // exactly one (t, lane) has this rank
     }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) kth = fmaxf(kth, __shfl_xor_sync(0xffffffffu, kth, o));
     if (lane == 0) gtau[q] = (n_t >= k) ? kth : VQ_NEG_INF;
 }
 
@@ -558,11 +558,15 @@ bool get_map_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint64_t ld
 }
 
 inline size_t align256(size_t v) { return (v + 255) / 256 * 256; }
+inline int pow2_ge(int v) { int p = 2; while (p < v) p <<= 1; return p; }
 
 struct MmaPlan {
     int nkb, nt, n_qt, b_pad, groups, grid, stages;
     int boot_tiles, boot_groups;                 // threshold bootstrap (0 = off)
-    size_t smem, qbf_bytes, tau_bytes, part_bytes, boot_bytes;
+    int cap;                                     // candidate slots per query (= groups * k, cannot overflow)
+    size_t smem;
+    // workspace layout
+    size_t off_tau, off_cnt, off_cand_s, off_cand_r, off_boot, off_qbf, total;
 };
 MmaPlan plan(int64_t n, int ld, int b, int k) {
     MmaPlan p;
@@ -588,17 +592,41 @@ MmaPlan plan(int64_t n, int ld, int b, int k) {
     static const bool boot_on = getenv("VQ_MMA_BOOT") ? atoi(getenv("VQ_MMA_BOOT")) != 0 : true;
     p.boot_tiles = (boot_on && p.nt && n_tiles >= 16LL * bt && bt >= k) ? bt : 0;
     p.boot_groups = p.boot_tiles ? (p.boot_tiles < (int)groups ? p.boot_tiles : (int)groups) : 0;
-    p.boot_bytes = align256((size_t)kMaxBootTiles * p.b_pad * 4);
     p.smem = 1024 + (size_t)p.stages * stage_bytes + 256;
-    p.qbf_bytes = align256((size_t)p.b_pad * ld * 2);
-    p.tau_bytes = align256((size_t)p.b_pad * 4);
-    p.part_bytes = align256((size_t)p.groups * p.b_pad * k * 4);
+    // candidate capacity is sized for the largest group count any batch <= b can get (the HNSW builder
+    // reuses one workspace for a shrinking last batch)
+    const int max_groups = sms > p.n_qt ? sms : p.n_qt;
+    p.cap = p.groups * k;
+    const size_t cand_bytes = align256((size_t)max_groups * QT * k * 4);
+    size_t o = 0;
+    p.off_tau = o;    o += align256((size_t)p.b_pad * 4);
+    p.off_cnt = o;    o += align256((size_t)p.b_pad * 4);
+    p.off_cand_s = o; o += cand_bytes;
+    p.off_cand_r = o; o += cand_bytes;
+    p.off_boot = o;   o += align256((size_t)kMaxBootTiles * p.b_pad * 4);
+    p.off_qbf = o;    o += align256((size_t)p.b_pad * ld * 2);
+    p.total = o;
     return p;
 }
 
+struct MmaWs {
+    float* gtau; int* cnt; float* cand_s; int* cand_r; float* boot_max; __nv_bfloat16* qbf;
+};
+MmaWs carve(const MmaPlan& p, void* ws_v) {
+    unsigned char* ws = (unsigned char*)ws_v;
+    MmaWs w;
+    w.gtau = (float*)(ws + p.off_tau);
+    w.cnt = (int*)(ws + p.off_cnt);
+    w.cand_s = (float*)(ws + p.off_cand_s);
+    w.cand_r = (int*)(ws + p.off_cand_r);
+    w.boot_max = (float*)(ws + p.off_boot);
+    w.qbf = (__nv_bfloat16*)(ws + p.off_qbf);
+    return w;
+}
+
 template <int KL, int NT, bool BOOT>
-cudaError_t launch_mma(const MmaPlan& p, const CUtensorMap& tmS, const __nv_bfloat16* qbf, float* gtau, int n, int ld, int k,
-                       float* part_s, int* part_r, int dbg, cudaStream_t stream) {
+cudaError_t launch_mma(const MmaPlan& p, const CUtensorMap& tmS, const __nv_bfloat16* qbf, const MmaWs& w, int n, int ld, int k,
+                       int dbg, cudaStream_t stream) {
     auto kern = scan_mma_bf16_kernel<KL, NT, BOOT>;
     static bool attr_done = false;
     if (!attr_done) {
@@ -607,37 +635,44 @@ cudaError_t launch_mma(const MmaPlan& p, const CUtensorMap& tmS, const __nv_bflo
         attr_done = true;
     }
     const int grid = BOOT ? p.boot_groups * p.n_qt : p.grid;
-    kern<<<grid, kThreads, p.smem, stream>>>(tmS, qbf, gtau, n, ld, p.nkb, p.n_qt, k, p.stages, p.b_pad, part_s, part_r, dbg);
+    kern<<<grid, kThreads, p.smem, stream>>>(tmS, qbf, w.gtau, n, ld, p.nkb, p.n_qt, k, p.stages, p.b_pad,
+                                             BOOT ? w.boot_max : w.cand_s, w.cand_r, w.cnt, p.cap, dbg);
     return cudaGetLastError();
 }
 
-int run_prepared(const MmaPlan& p, const CUtensorMap& tmS, const __nv_bfloat16* qbf, float* gtau, int n, int ld, int k,
-                 float* part_s, int* part_r, float* boot_max, cudaStream_t stream, int* launches) {
-    const int dbg = getenv("VQ_MMA_DEBUG") ? atoi(getenv("VQ_MMA_DEBUG")) : 0;
+// [boot pass ->] main pass; gtau / cnt must have been reset by the caller's prologue kernel.
+int run_scan(const MmaPlan& p, const void* store, int64_t n, int ld, const __nv_bfloat16* qbf, const MmaWs& w, int k,
+             cudaStream_t stream, int* launches) {
+    static const int dbg = getenv("VQ_MMA_DEBUG") ? atoi(getenv("VQ_MMA_DEBUG")) : 0;
+    CUtensorMap tmS;
+    if (!get_map_bf16(&tmS, store, (uint64_t)n, (uint64_t)ld, (uint32_t)p.nt)) {
+        vq_set_error("scan_mma: cuTensorMapEncodeTiled failed");
+        return VQ_ECUDA;
+    }
     cudaError_t e;
     *launches = 1;
     if (p.boot_tiles) {
         // sample pass over the first boot_tiles full tiles: per-tile maxima -> boot_max, then gtau
         const int n_boot = p.boot_tiles * p.nt;
-        e = p.nt == 128 ? launch_mma<1, 128, true>(p, tmS, qbf, gtau, n_boot, ld, k, boot_max, nullptr, dbg, stream)
-                        : launch_mma<1, 64, true>(p, tmS, qbf, gtau, n_boot, ld, k, boot_max, nullptr, dbg, stream);
+        e = p.nt == 128 ? launch_mma<1, 128, true>(p, tmS, qbf, w, n_boot, ld, k, dbg, stream)
+                        : launch_mma<1, 64, true>(p, tmS, qbf, w, n_boot, ld, k, dbg, stream);
         if (e != cudaSuccess) {
             vq_set_error("launch of scan_mma_bf16_kernel<boot> failed: %s", cudaGetErrorString(e));
             return VQ_ECUDA;
         }
-        boot_select_kernel<<<(p.b_pad + 7) / 8, 256, 0, stream>>>(boot_max, p.boot_tiles, p.b_pad, k, gtau);
+        boot_select_kernel<<<(p.b_pad + 7) / 8, 256, 0, stream>>>(w.boot_max, p.boot_tiles, p.b_pad, k, w.gtau);
         VQ_LAUNCH_CHECK("boot_select_kernel");
         *launches = 3;
     }
     vq_prof_begin(stream);
     if (p.nt == 128)
-        e = k <= 16 ? launch_mma<16, 128, false>(p, tmS, qbf, gtau, n, ld, k, part_s, part_r, dbg, stream)
-          : k <= 32 ? launch_mma<32, 128, false>(p, tmS, qbf, gtau, n, ld, k, part_s, part_r, dbg, stream)
-                    : launch_mma<64, 128, false>(p, tmS, qbf, gtau, n, ld, k, part_s, part_r, dbg, stream);
+        e = k <= 16 ? launch_mma<16, 128, false>(p, tmS, qbf, w, (int)n, ld, k, dbg, stream)
+          : k <= 32 ? launch_mma<32, 128, false>(p, tmS, qbf, w, (int)n, ld, k, dbg, stream)
+                    : launch_mma<64, 128, false>(p, tmS, qbf, w, (int)n, ld, k, dbg, stream);
     else
-        e = k <= 16 ? launch_mma<16, 64, false>(p, tmS, qbf, gtau, n, ld, k, part_s, part_r, dbg, stream)
-          : k <= 32 ? launch_mma<32, 64, false>(p, tmS, qbf, gtau, n, ld, k, part_s, part_r, dbg, stream)
-                    : launch_mma<64, 64, false>(p, tmS, qbf, gtau, n, ld, k, part_s, part_r, dbg, stream);
+        e = k <= 16 ? launch_mma<16, 64, false>(p, tmS, qbf, w, (int)n, ld, k, dbg, stream)
+          : k <= 32 ? launch_mma<32, 64, false>(p, tmS, qbf, w, (int)n, ld, k, dbg, stream)
+                    : launch_mma<64, 64, false>(p, tmS, qbf, w, (int)n, ld, k, dbg, stream);
     vq_prof_end(stream);
     if (e != cudaSuccess) {
         vq_set_error("launch of scan_mma_bf16_kernel failed: %s", cudaGetErrorString(e));
@@ -646,50 +681,17 @@ int run_prepared(const MmaPlan& p, const CUtensorMap& tmS, const __nv_bfloat16* 
     return VQ_OK;
 }
 
-__global__ void fill_neg_inf_kernel(float* p, int n) {
+__global__ void reset_scan_state_kernel(float* gtau, int* cnt, int n) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) p[i] = VQ_NEG_INF;
+    if (i < n) { gtau[i] = VQ_NEG_INF; cnt[i] = 0; }
 }
 
 }  // namespace
 
-bool vq_scan_mma_supported(int64_t n, int dim, int ld, int store_dtype, int b, int k);
-
-// Scan with queries that are ALREADY unit-norm bf16 rows [b_pad, ld] (b_pad % 128 == 0, rows >= b zero):
-// used by the HNSW builder, whose queries are the stored rows themselves.
-size_t vq_scan_mma_prepared_workspace(int64_t n, int ld, int b, int k) {
-    // valid for every batch <= b: groups * b_pad <= max(SMs, n_qt) * 128 whatever the batch
-    const MmaPlan p = plan(n, ld, b, k);
-    const size_t lists = (size_t)(vq_num_sms() > p.n_qt ? vq_num_sms() : p.n_qt) * QT;
-    return p.tau_bytes + 2 * align256(lists * k * 4) + p.boot_bytes + 256;
-}
-int vq_scan_mma_prepared(const void* store, int64_t n, int ld, const void* qbf, int b, int k, float* out_scores,
-                         int32_t* out_rows, void* ws_v, size_t ws_bytes, cudaStream_t stream) {
-    if (!vq_scan_mma_supported(n, ld, ld, VQ_BF16, b, k)) {
-        vq_set_error("scan_mma_prepared: unsupported shape n=%lld ld=%d b=%d k=%d", (long long)n, ld, b, k);
-        return VQ_EUNSUPPORTED;
-    }
-    const MmaPlan p = plan(n, ld, b, k);
-    if (ws_bytes < p.tau_bytes + 2 * p.part_bytes + p.boot_bytes) {
-        vq_set_error("scan_mma_prepared: workspace too small (%zu < %zu)", ws_bytes, p.tau_bytes + 2 * p.part_bytes + p.boot_bytes);
-        return VQ_EWORKSPACE;
-    }
-    unsigned char* ws = (unsigned char*)ws_v;
-    float* gtau = (float*)ws;
-    float* part_s = (float*)(ws + p.tau_bytes);
-    int* part_r = (int*)(ws + p.tau_bytes + p.part_bytes);
-    float* boot_max = (float*)(ws + p.tau_bytes + 2 * p.part_bytes);
-    fill_neg_inf_kernel<<<(p.b_pad + 255) / 256, 256, 0, stream>>>(gtau, p.b_pad);
-    CUtensorMap tmS;
-    if (!get_map_bf16(&tmS, store, (uint64_t)n, (uint64_t)ld, (uint32_t)p.nt)) {
-        vq_set_error("scan_mma: cuTensorMapEncodeTiled failed");
-        return VQ_ECUDA;
-    }
-    int nl = 0;
-    int rc = run_prepared(p, tmS, (const __nv_bfloat16*)qbf, gtau, (int)n, ld, k, part_s, part_r, boot_max, stream, &nl);
-    if (rc) return rc;
-    return vq_topk_merge_launch(part_s, part_r, p.groups, (long long)p.b_pad * k, b, k, nullptr, k, out_scores, out_rows, 0, 0, stream);
-}
+// scan_finish.cu: final selection out of the candidate buffers (+ optional exact fp32 re-score)
+int vq_scan_finish_launch(const float* cand_s, const int* cand_r, const int* cand_cnt, int cap, int b, int k_sel,
+                          const float* store_f32, int ld, int dim, const float* queries, int query_norm, float eps,
+                          int k_out, float* out_scores, int* out_rows, int* out_bad, cudaStream_t stream);
 
 bool vq_scan_mma_supported(int64_t n, int dim, int ld, int store_dtype, int b, int k) {
     (void)dim;
@@ -698,42 +700,61 @@ bool vq_scan_mma_supported(int64_t n, int dim, int ld, int store_dtype, int b, i
     return (b + QT - 1) / QT <= vq_num_sms();
 }
 
-size_t vq_scan_mma_workspace(int64_t n, int ld, int store_dtype, int b, int k) {
-    if (store_dtype != VQ_BF16 || b < 1 || k < 1 || k > kMaxK || n < 1 || ld > 768) return 0;
-    const MmaPlan p = plan(n, ld, b, k);
-    return p.qbf_bytes + p.tau_bytes + 2 * p.part_bytes + p.boot_bytes + 256;
+// Scan with queries that are ALREADY unit-norm bf16 rows [b_pad, ld] (b_pad % 128 == 0, rows >= b zero):
+// used by the HNSW builder, whose queries are the stored rows themselves.  The workspace of a batch b
+// is valid for every smaller batch.
+size_t vq_scan_mma_prepared_workspace(int64_t n, int ld, int b, int k) {
+    return plan(n, ld, b, k).total + 256;
 }
-
-// queries: raw fp32 [b, dim]; normalisation (query_norm) is fused into the bf16 conversion.
-int vq_scan_mma_run(const void* store, int64_t n, int dim, int ld, int store_dtype, const float* queries, int query_norm,
-                    int b, int k, float* out_scores, int32_t* out_rows, void* ws_v, size_t ws_bytes, cudaStream_t stream,
-                    int* launches) {
-    if (!vq_scan_mma_supported(n, dim, ld, store_dtype, b, k)) {
-        vq_set_error("scan_mma: unsupported shape");
+int vq_scan_mma_prepared(const void* store, int64_t n, int ld, const void* qbf, int b, int k, float* out_scores,
+                         int32_t* out_rows, void* ws_v, size_t ws_bytes, cudaStream_t stream) {
+    if (!vq_scan_mma_supported(n, ld, ld, VQ_BF16, b, k)) {
+        vq_set_error("scan_mma_prepared: unsupported shape n=%lld ld=%d b=%d k=%d", (long long)n, ld, b, k);
         return VQ_EUNSUPPORTED;
     }
     const MmaPlan p = plan(n, ld, b, k);
-    if (ws_bytes < p.qbf_bytes + p.tau_bytes + 2 * p.part_bytes + p.boot_bytes) {
-        vq_set_error("scan_mma: workspace too small");
+    if (ws_bytes < p.off_qbf) {                                // the caller supplies the bf16 queries
+        vq_set_error("scan_mma_prepared: workspace too small (%zu < %zu)", ws_bytes, p.off_qbf);
         return VQ_EWORKSPACE;
     }
-    unsigned char* ws = (unsigned char*)ws_v;
-    __nv_bfloat16* qbf = (__nv_bfloat16*)ws;
-    float* gtau = (float*)(ws + p.qbf_bytes);
-    float* part_s = (float*)(ws + p.qbf_bytes + p.tau_bytes);
-    int* part_r = (int*)(ws + p.qbf_bytes + p.tau_bytes + p.part_bytes);
-    float* boot_max = (float*)(ws + p.qbf_bytes + p.tau_bytes + 2 * p.part_bytes);
-    prep_queries_bf16_kernel<<<(p.b_pad + 7) / 8, 256, 0, stream>>>(queries, b, dim, dim, qbf, ld, p.b_pad, query_norm, gtau);
-    VQ_LAUNCH_CHECK("prep_queries_bf16_kernel");
-    CUtensorMap tmS;
-    if (!get_map_bf16(&tmS, store, (uint64_t)n, (uint64_t)ld, (uint32_t)p.nt)) {
-        vq_set_error("scan_mma: cuTensorMapEncodeTiled failed");
-        return VQ_ECUDA;
-    }
+    const MmaWs w = carve(p, ws_v);
+    reset_scan_state_kernel<<<(p.b_pad + 255) / 256, 256, 0, stream>>>(w.gtau, w.cnt, p.b_pad);
     int nl = 0;
-    int rc = run_prepared(p, tmS, qbf, gtau, (int)n, ld, k, part_s, part_r, boot_max, stream, &nl);
+    int rc = run_scan(p, store, n, ld, (const __nv_bfloat16*)qbf, w, k, stream, &nl);
     if (rc) return rc;
-    rc = vq_topk_merge_launch(part_s, part_r, p.groups, (long long)p.b_pad * k, b, k, nullptr, k, out_scores, out_rows, 0, 0, stream);
+    return vq_scan_finish_launch(w.cand_s, w.cand_r, w.cnt, p.cap, b, k, nullptr, ld, ld, nullptr, VQ_NORM_NONE, 0.f, k,
+                                 out_scores, out_rows, nullptr, stream);
+}
+
+size_t vq_scan_mma_workspace(int64_t n, int ld, int store_dtype, int b, int k) {
+    if (store_dtype != VQ_BF16 || b < 1 || k < 1 || k > kMaxK || n < 1 || ld > 768) return 0;
+    return plan(n, ld, b, k).total + 256;
+}
+
+// queries: raw fp32 [b, dim]; normalisation (query_norm) is fused into the bf16 conversion.
+// store_f32 == NULL: plain top-k of the bf16 scores.  store_f32 != NULL: two-stage exact search — the
+// scan selects k_sel candidates, they are re-scored from the fp32 copy, the best k_out are returned and
+// out_bad[q] says whether the result could NOT be certified (see vq_search_two_stage).
+int vq_scan_mma_run(const void* store, int64_t n, int dim, int ld, int store_dtype, const float* queries, int query_norm,
+                    int b, int k_sel, const float* store_f32, float eps, int k_out, float* out_scores, int32_t* out_rows,
+                    int32_t* out_bad, void* ws_v, size_t ws_bytes, cudaStream_t stream, int* launches) {
+    if (!vq_scan_mma_supported(n, dim, ld, store_dtype, b, k_sel)) {
+        vq_set_error("scan_mma: unsupported shape n=%lld dim=%d ld=%d b=%d k=%d", (long long)n, dim, ld, b, k_sel);
+        return VQ_EUNSUPPORTED;
+    }
+    const MmaPlan p = plan(n, ld, b, k_sel);
+    if (ws_bytes < p.total) {
+        vq_set_error("scan_mma: workspace too small (%zu < %zu)", ws_bytes, p.total);
+        return VQ_EWORKSPACE;
+    }
+    const MmaWs w = carve(p, ws_v);
+    prep_queries_bf16_kernel<<<(p.b_pad + 7) / 8, 256, 0, stream>>>(queries, b, dim, dim, w.qbf, ld, p.b_pad, query_norm, w.gtau, w.cnt);
+    VQ_LAUNCH_CHECK("prep_queries_bf16_kernel");
+    int nl = 0;
+    int rc = run_scan(p, store, n, ld, w.qbf, w, k_sel, stream, &nl);
+    if (rc) return rc;
+    rc = vq_scan_finish_launch(w.cand_s, w.cand_r, w.cnt, p.cap, b, k_sel, store_f32, ld, dim, queries, query_norm, eps, k_out,
+                               out_scores, out_rows, out_bad, stream);
     if (rc) return rc;
     *launches = 2 + nl;
     return VQ_OK;

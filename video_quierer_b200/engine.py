@@ -169,6 +169,32 @@ class Scanner:
                 self.last_launches = _lib.last_launch_count()
         return out_s, out_r
 
+    def two_stage(self, bf16: torch.Tensor, f32: torch.Tensor, n: int, dim: int, queries: torch.Tensor, k: int,
+                  k_cand: int, norm: int = _lib.NORM_EPS, score_eps: float = 2.0 ** -8 + 1e-5):
+        """`vq_search_two_stage`: tensor-core scan of the bf16 copy for k_cand candidates, exact fp32
+        re-score, best k, per-query certificate.  Returns (scores [b,k] f32, rows [b,k] i32,
+        uncertified [b] i32) device tensors."""
+        ld = bf16.stride(0)
+        if f32.stride(0) != ld:
+            raise ValueError("bf16 and fp32 copies must share the row stride")
+        b = queries.shape[0]
+        with torch.cuda.device(self.device):
+            out_s = torch.empty((b, k), dtype=torch.float32, device=self.device)
+            out_r = torch.empty((b, k), dtype=torch.int32, device=self.device)
+            bad = torch.zeros((b,), dtype=torch.int32, device=self.device)
+            if b == 0:
+                return out_s, out_r, bad
+            need = self.lib.vq_search_two_stage_workspace_bytes(n, dim, ld, b, k_cand)
+            with self.lock:
+                ws = self.ws.get(need)
+                rc = self.lib.vq_search_two_stage(_ptr(bf16), _ptr(f32), n, dim, ld, _ptr(queries), b, k, k_cand, norm,
+                                                  float(score_eps), _ptr(out_s), _ptr(out_r), _ptr(bad), _ptr(ws),
+                                                  ws.numel(), _stream(self.device))
+                _lib.check(rc, "vq_search_two_stage")
+                self.last_path = _lib.last_scan_path()
+                self.last_launches = _lib.last_launch_count()
+        return out_s, out_r, bad
+
     def rescore(self, f32: torch.Tensor, n: int, dim: int, queries_norm_padded: torch.Tensor,
                 cand_rows: torch.Tensor, k: int):
         b, kc = cand_rows.shape

@@ -17,6 +17,7 @@ records mutations; the device matrix is re-synchronised lazily before the next s
 from __future__ import annotations
 
 import logging
+import os
 import pickle
 import threading
 from pathlib import Path
@@ -86,29 +87,27 @@ class EmbeddingList(list):
 # rounded to 8 significant bits (relative 2^-9), products are exact, so
 # |delta| <= (2*2^-9 + 2^-18) * sum|q_i x_i| <= 2^-8 * |q| |x|  (Cauchy-Schwarz) plus fp32 accumulation noise.
 BF16_SCORE_EPS = 2.0 ** -8 + 1e-5
+MAX_TENSOR_K, MAX_TENSOR_LD = 64, 768        # limits of scan_mma_bf16_kernel (csrc/scan_mma.cu)
 
 
 def two_stage_search(scanner: Scanner, st: DeviceStore, q_dev: torch.Tensor, k: int, path: str = "auto",
                      max_row_norm: float = 1.0):
-    """Exact top-k from a bf16 scan: (1) the tensor-core scan of the bf16 copy selects k' candidates,
-    (2) they are re-scored exactly from the fp32 copy, (3) the result is *certified*: every row
-    outside the candidate set has exact score <= (k'-th bf16 score) + eps, so if the exact k-th
-    score is above that bound nothing was missed.  Returns ([b,k] f32, [b,k] i32, uncertified [b]
-    bool device tensor or None); the caller re-runs uncertified queries (near-duplicate heavy
-    data) with `exact_fallback` after its device->host read, so no extra sync is added here."""
-    kc = min(st.n, 32 if k <= 16 else max(2 * k, k + 22))
-    kc = max(kc, k)
-    s_lo, cand = scanner.scan(st.bf16, st.n, st.dim, q_dev, kc, _lib.NORM_EPS, path)
-    launches = scanner.last_launches
-    scan_path = scanner.last_path
-    qn = scanner.normalise_padded(q_dev, st.ld, _lib.NORM_EPS)
-    s_hi, rows = scanner.rescore(st.f32, st.n, st.dim, qn, cand, k)
-    bad = None
-    if kc < st.n:
-        bad = s_hi[:, k - 1] < (s_lo[:, kc - 1] + BF16_SCORE_EPS * max_row_norm)
-    scanner.last_launches = launches + 3
-    scanner.last_path = scan_path + "+rescore"
-    return s_hi, rows, bad
+    """Exact top-k from a bf16 scan, ONE C-ABI call (`vq_search_two_stage`): (1) the tensor-core
+    scan of the bf16 copy selects k' candidates, (2) they are re-scored exactly from the fp32 copy,
+    (3) the result is *certified*: every row outside the candidate set has exact score <=
+    (k'-th bf16 score) + eps, so if the exact k-th score is above that bound nothing was missed.
+    Returns ([b,k] f32, [b,k] i32, uncertified [b] bool device tensor or None); the caller re-runs
+    uncertified queries (near-duplicate heavy data) with `exact_fallback` after its device->host
+    read, so no extra sync is added here."""
+    kc = int(os.environ.get("VQ_KCAND", 0)) or (32 if k <= 16 else max(2 * k, k + 22))
+    kc = max(min(st.n, kc), k)
+    if kc > MAX_TENSOR_K or st.ld > MAX_TENSOR_LD:
+        # beyond the register top-k of the tensor path: the fp32 FMA scan is exact by itself
+        s, r = scanner.scan(st.f32, st.n, st.dim, q_dev, k, _lib.NORM_EPS, "fma")
+        return s, r, None
+    s_hi, rows, bad = scanner.two_stage(st.bf16, st.f32, st.n, st.dim, q_dev, k, kc, _lib.NORM_EPS,
+                                        BF16_SCORE_EPS * max_row_norm)
+    return s_hi, rows, (bad if kc < st.n else None)
 
 
 def exact_fallback(scanner: Scanner, st: DeviceStore, q_dev: torch.Tensor, k: int, idx: torch.Tensor):
