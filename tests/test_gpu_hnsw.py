@@ -102,12 +102,29 @@ def test_10k_reference_graph_and_gpu_build_recall_bar(built_lib, golden, name):
     b = B200HNSWIndex(dimension=d, M=16, ef_construction=200, ef_search=64, max_M=16)
     b.add_batch(list(store), list(range(n)))
     assert [b.levels[i] for i in range(50)] == [int(x) for x in g["levels"][:50]]     # same level stream
+    # (2a) on the golden's own 100 queries (1000 hits per ef: one hit = 0.001) the two graphs must
+    # agree within sampling noise ...
     for ef in (64, 128, 256):
         b.ef_search = ef
         _, rows = b.search_arrays(queries, 10)
         rec = compare.recall_at_k(rows, truth)
-        print(f"{name} ef={ef}: gpu-built recall@10={rec:.3f} reference={float(g[f'recall_ef{ef}']):.3f}")
-        assert rec >= float(g[f"recall_ef{ef}"]) - 1e-9
+        print(f"{name} ef={ef} (100 golden queries): gpu-built recall@10={rec:.3f} reference={float(g[f'recall_ef{ef}']):.3f}")
+        assert rec >= float(g[f"recall_ef{ef}"]) - 0.005
+    # (2b) ... and the bar itself — recall@10 >= the reference's at the same M / ef, no tolerance — is
+    # checked where it is statistically meaningful: 2000 fresh queries (20 000 hits per ef) searched by
+    # the same kernel on the REFERENCE-built graph (which part (1) showed reproduces the reference's
+    # ids) and on the GPU-built graph.
+    nq = 2000
+    big_q = synth.clip_like(nq, d, seed=77, n_store=n) if name == "clip" else synth.gauss(nq, d, seed=77)
+    big_truth = np.argsort(-(big_q @ stored.T), axis=1)[:, :10]
+    for ef in (64, 128, 256):
+        h.ef_search = b.ef_search = ef
+        _, rows_ref = h.search_arrays(big_q, 10)
+        _, rows_gpu = b.search_arrays(big_q, 10)
+        rec_ref = compare.recall_at_k(rows_ref, big_truth)
+        rec_gpu = compare.recall_at_k(rows_gpu, big_truth)
+        print(f"{name} ef={ef} ({nq} queries): gpu-built recall@10={rec_gpu:.4f} reference-built={rec_ref:.4f}")
+        assert rec_gpu >= rec_ref
     assert b.entry_point == int(g["entry"])
 
 
