@@ -60,6 +60,7 @@ constexpr int TMEM_COLS = 512;          // whole tensor memory: 2 accumulators +
 constexpr int kThreads = 256;
 constexpr int kMaxK = 64;
 constexpr int kGroup = 4;              // ring slots released per tcgen05.commit
+constexpr int kIssuers = 2;            // MMA-issuing warps (warps 1 and 2), alternating k-blocks
 constexpr int kMaxBootTiles = 256;     // sample tiles of the threshold bootstrap (8 per lane in boot_select)
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -242,7 +243,8 @@ scan_mma_bf16_kernel(const __grid_constant__ CUtensorMap tmS,
     uint64_t* a_full = empty + stages;
     uint64_t* tmem_full = a_full + 1;      // [2]
     uint64_t* tmem_empty = tmem_full + 2;  // [2]
-    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+    uint64_t* x_first = tmem_empty + 2;    // [2] issuer 0 has issued the overwriting MMA of the tile
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(x_first + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int q_tile = blockIdx.x % n_qt, group = blockIdx.x / n_qt, n_groups = gridDim.x / n_qt;
@@ -250,9 +252,9 @@ scan_mma_bf16_kernel(const __grid_constant__ CUtensorMap tmS,
 
     if (warp == 0 && lane == 0) tma_prefetch_desc(&tmS);
     if (warp == 1 && lane == 0) {
-        for (int s = 0; s < stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int s = 0; s < stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], kIssuers); }
         mbar_init(a_full, 4);
-        for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 4); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], kIssuers); mbar_init(&tmem_empty[a], 4); mbar_init(&x_first[a], 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -286,7 +288,14 @@ scan_mma_bf16_kernel(const __grid_constant__ CUtensorMap tmS,
                 if (++stage == stages) { stage = 0; phase ^= 1; }
             }
         }
-    } else if (warp == 1) {
+    } else if (warp == 1 || warp == 2) {
+        // Two issuing warps on two SM sub-partitions alternate the k-blocks of every tile (role 0: even,
+        // role 1: odd).  A UTCHMMA holds its warp's issue slot until the tensor pipe accepts it, so with
+        // one issuer the barrier waits and descriptor arithmetic between k-blocks leave the pipe idle
+        // (measured 89-117 cycles/MMA); with two, one warp's bookkeeping hides behind the other's MMAs
+        // (74 cycles/MMA in tools/mmabench.cu).  tcgen05.commit tracks the MMAs of the executing thread
+        // only, so BOTH issuers commit at every release point and the barriers count kIssuers arrivals.
+        const int role = warp - 1;
         const uint32_t idesc = umma_idesc_bf16(NT);
         const uint32_t sB_addr = smem_u32(sB);
         mbar_wait(a_full, 0);                          // query tile is in tensor memory
@@ -297,29 +306,44 @@ scan_mma_bf16_kernel(const __grid_constant__ CUtensorMap tmS,
         for (int tile = group; tile < n_tiles; tile += n_groups, ++it) {
             const int acc = it & 1;
             const uint32_t acc_phase = (it >> 1) & 1;
-            if (!(dbg & 64)) mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+            mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
             tc_fence_after();
+            if (role == 1) {        // the MMA that OVERWRITES the accumulator (k-block 0) must be ordered first
+                mbar_wait(&x_first[acc], acc_phase);
+                tc_fence_after();
+            }
             const uint32_t d_tmem = tmem_base + (uint32_t)acc * NT;
             for (int kb = 0; kb < nkb; ++kb) {
-                if (!(dbg & 32)) mbar_wait(&full[stage], phase);
-                tc_fence_after();
-                if (elect_one()) {
-                    const uint64_t bd0 = umma_desc_sw128(sB_addr + (uint32_t)((dbg & 8) ? 0 : stage) * B_KB_BYTES);
-                    const uint32_t a_tmem = tmem_base + A_COL0 + (uint32_t)((dbg & 16) ? 0 : kb) * (KB_ELEMS / 2);
-                    if (!(dbg & 1)) {
+                if ((kb & 1) == role) {
+                    mbar_wait(&full[stage], phase);
+                    tc_fence_after();
+                    if (elect_one() && !(dbg & 1)) {
+                        const uint64_t bd0 = umma_desc_sw128(sB_addr + (uint32_t)stage * B_KB_BYTES);
+                        const uint32_t a_tmem = tmem_base + A_COL0 + (uint32_t)kb * (KB_ELEMS / 2);
 #pragma unroll
                         for (int k4 = 0; k4 < KB_ELEMS / 16; ++k4)   // +32 bytes per K=16 step = +2 in the (addr >> 4) field
                             umma_bf16_ts(d_tmem, a_tmem + k4 * 8, bd0 + (uint64_t)(k4 * 2), idesc, (kb | k4) != 0 ? 1u : 0u);
                     }
-                    // ring slots are handed back kGroup at a time: every commit drains the tensor pipe
-                    if (stage % kGroup == kGroup - 1) umma_commit(&empty[stage / kGroup]);
-                    if (kb == nkb - 1) umma_commit(&tmem_full[acc]);      // accumulator complete
+                    __syncwarp();
+                    if (kb == 0) {                     // only role 0 gets here
+                        tc_fence_before();
+                        if (elect_one()) mbar_arrive(&x_first[acc]);
+                        __syncwarp();
+                    }
                 }
-                __syncwarp();
+                // ring slots are handed back kGroup at a time; the accumulator is published after the last k-block
+                const bool rel = stage % kGroup == kGroup - 1, last = kb == nkb - 1;
+                if (rel || last) {
+                    if (elect_one()) {
+                        if (rel) umma_commit(&empty[stage / kGroup]);
+                        if (last) umma_commit(&tmem_full[acc]);
+                    }
+                    __syncwarp();
+                }
                 if (++stage == stages) { stage = 0; phase ^= 1; }
             }
         }
-        if ((dbg & 128) && blockIdx.x == 0 && lane == 0) {
+        if ((dbg & 128) && blockIdx.x == 0 && lane == 0 && role == 0) {
             long long c1 = clock64(), t1;
             asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
             printf("[scan_mma dbg] issue loop: %d tiles, %lld cycles, %lld ns -> %.1f cycles/MMA, %.0f MHz\n", it, c1 - dbg_c0,
@@ -592,7 +616,7 @@ MmaPlan plan(int64_t n, int ld, int b, int k) {
     static const bool boot_on = getenv("VQ_MMA_BOOT") ? atoi(getenv("VQ_MMA_BOOT")) != 0 : true;
     p.boot_tiles = (boot_on && p.nt && n_tiles >= 16LL * bt && bt >= k) ? bt : 0;
     p.boot_groups = p.boot_tiles ? (p.boot_tiles < (int)groups ? p.boot_tiles : (int)groups) : 0;
-    p.smem = 1024 + (size_t)p.stages * stage_bytes + 256;
+    p.smem = 1024 + (size_t)p.stages * stage_bytes + 512;
     // candidate capacity is sized for the largest group count any batch <= b can get (the HNSW builder
     // reuses one workspace for a shrinking last batch)
     const int max_groups = sms > p.n_qt ? sms : p.n_qt;
