@@ -319,19 +319,26 @@ def run_ours(args):
         hbm_peak, tf_peak, peak_src = _peaks()
         n_local = hi - lo
 
+        traffic_tab = {}
+        tp = os.path.join(ROOT, "profiles", "r01_traffic.json")
+        if os.path.exists(tp) and world == 1 and two_stage:
+            traffic_tab = json.load(open(tp)).get("scan_mma_bf16_kernel", {})
+
         def roof(m):
             if m["kernel_ms"] is None:
                 return None
+            # DRAM bytes per launch from the committed ncu --set full capture of this kernel / batch class
+            traffic = traffic_tab.get("le128" if m["B"] <= 128 else str(m["B"]))
             bytes_ = n_local * store.ld * elem + min(m["B"], 128) * DIM * elem
             flops = 2.0 * m["B"] * n_local * DIM
             gbs = bytes_ / (m["kernel_ms"] * 1e-3) / 1e9
             tfs = flops / (m["kernel_ms"] * 1e-3) / 1e12
             if two_stage and flops / bytes_ > tf_peak * 1e12 / (hbm_peak * 1e9):
                 return {"bound": "tensor", "achieved": tfs, "peak": tf_peak, "unit": "TFLOP/s", "frac": tfs / tf_peak,
-                        "traffic": None, "kernel": "scan_mma_bf16_kernel", "kernel_ms": m["kernel_ms"],
+                        "traffic": traffic, "kernel": "scan_mma_bf16_kernel", "kernel_ms": m["kernel_ms"],
                         "peak_source": peak_src + " (bf16 burst)", "algorithmic_flops": flops}
             return {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
-                    "traffic": None, "kernel": "scan_mma_bf16_kernel" if two_stage else "scan_fma_kernel",
+                    "traffic": traffic, "kernel": "scan_mma_bf16_kernel" if two_stage else "scan_fma_kernel",
                     "kernel_ms": m["kernel_ms"], "peak_source": peak_src + " (copy bandwidth)",
                     "algorithmic_bytes": bytes_}
 
@@ -353,6 +360,19 @@ def run_ours(args):
                        "ms_per_step": m["dev_ms"] / min(args.steps, 30), "roofline": roof(m),
                        "uncertified_queries_per_batch": m["uncertified"]} for m in sweep],
         }
+        if world == 1 and not args.no_hnsw:
+            # BASELINE config 3 next to the headline: HNSW M=16 ef_construction=200 on 1M x 512 clustered
+            # (CLIP-like) rows, ef_search 64-256, recall@10 against the certified exact scan, QPS and the
+            # achieved gather bandwidth from the kernel's own evaluation / expansion counters
+            try:
+                from types import SimpleNamespace
+                from tools import bench_hnsw
+                h = bench_hnsw.measure(SimpleNamespace(n=N_ROWS, dim=DIM, queries=10000, kind="clip", efs="64,128,256",
+                                                       search_dtype="fp32"), dev)
+                line["hnsw"] = {"workload": "HNSW M=16 ef_construction=200 max_M=16, 1M x 512 clustered rows, 10000 queries, k=10",
+                                "build_s": h["build_s"], "hbm_peak_GBps": hbm_peak, "runs": h["runs"]}
+            except Exception as e:  # noqa: BLE001 — the headline line must survive a failure of the extra leg
+                line["hnsw"] = {"error": f"{type(e).__name__}: {e}"[:300]}
         if cpu is not None:
             line["cpu_baseline"] = {"value": cpu[0], "unit": "queries/s", "cores": cpu[1], "kind": "port", "sample": cpu[2]}
         print(json.dumps(line), flush=True)
@@ -372,6 +392,7 @@ def main():
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-sweep", action="store_true", help="skip the batch 1/32/1024 sweep")
+    ap.add_argument("--no-hnsw", action="store_true", help="skip the HNSW (BASELINE config 3) leg")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying a CUDA graph")
     ap.add_argument("--mode", default="exact2", choices=["exact2", "fp32"],
                     help="exact2: bf16 tensor scan + exact fp32 re-score (default); fp32: FMA scan of the fp32 store")

@@ -31,16 +31,9 @@ def device_rows(kind, n, dim, dev, seed):
     return torch.cat(out)
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--n", type=int, default=1_000_000)
-    ap.add_argument("--dim", type=int, default=512)
-    ap.add_argument("--queries", type=int, default=10000)
-    ap.add_argument("--kind", default="clip")
-    ap.add_argument("--efs", default="64,128,256")
-    ap.add_argument("--search-dtype", default="fp32")
-    a = ap.parse_args()
-    dev = torch.device("cuda", 0)
+def measure(a, dev=None):
+    """a: namespace with n, dim, queries, kind, efs, search_dtype.  Returns the result dict."""
+    dev = dev or torch.device("cuda", 0)
     x = device_rows(a.kind, a.n, a.dim, dev, 1)
     q = device_rows(a.kind, a.queries, a.dim, dev, 2)
     h = B200HNSWIndex(dimension=a.dim, M=16, ef_construction=200, ef_search=64, max_M=16, search_dtype=a.search_dtype)
@@ -83,7 +76,18 @@ def main():
                             "qps_wall": round(a.queries / wall), "kernel_ms": round(kms, 3),
                             "evals_per_query": round(st[:, 0].mean(), 1), "hops_per_query": round(st[:, 1].mean(), 1),
                             "gather_GBps": round(gbytes / (kms * 1e-3), 1), "overflow": int(st[:, 2].sum())})
-    print(json.dumps(res), flush=True)
+    return res
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--n", type=int, default=1_000_000)
+    ap.add_argument("--dim", type=int, default=512)
+    ap.add_argument("--queries", type=int, default=10000)
+    ap.add_argument("--kind", default="clip")
+    ap.add_argument("--efs", default="64,128,256")
+    ap.add_argument("--search-dtype", default="fp32")
+    print(json.dumps(measure(ap.parse_args())), flush=True)
 
 
 if __name__ == "__main__":
