@@ -1,5 +1,6 @@
 // C-ABI entry points (include/vq_search.h) for normalise / ingest / exact scan / merge / rescore.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "vq_common.cuh"
@@ -54,6 +55,13 @@ void vq_prof_end(cudaStream_t s) {
     if (!g_prof_on || !g_ev0) return;
     cudaEventRecord(g_ev1, s);
     g_ev_valid = true;
+}
+
+// PDL classes: 0 prep/reset, 1 boot scan, 2 boot_select, 3 main scan, 4 finish.  Default: off (measured
+// on B200 with the whole chain enabled: +35 us per step — see DESIGN.md); VQ_PDL=<mask> to experiment.
+int vq_pdl_mask() {
+    static const int mask = getenv("VQ_PDL") ? atoi(getenv("VQ_PDL")) : 0;
+    return mask;
 }
 
 int vq_num_sms() {

@@ -61,6 +61,8 @@ scan_finish_kernel(const float* __restrict__ cand_s, const int* __restrict__ can
     const int q = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const bool dbg_on = g_finish_dbg != 0;
     long long tmark[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    vq_pdl_wait();
+    vq_pdl_trigger();
     FDBG(0);
 
     int n = cand_cnt[q];
@@ -259,8 +261,11 @@ int vq_scan_finish_launch(const float* cand_s, const int* cand_r, const int* can
         VQ_CUDA(cudaFuncSetAttribute(scan_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
         attr_done = true;
     }
-    scan_finish_kernel<<<b, kThreads, smem, stream>>>(cand_s, cand_r, cand_cnt, cap, k_sel, store_f32, ld, dim, queries,
-                                                      query_norm, eps, k_out, out_scores, out_rows, out_bad, sort_cap);
-    VQ_LAUNCH_CHECK("scan_finish_kernel");
+    const cudaError_t e = vq_launch(4, scan_finish_kernel, dim3(b), dim3(kThreads), smem, stream, cand_s, cand_r, cand_cnt, cap, k_sel,
+                                    store_f32, ld, dim, queries, query_norm, eps, k_out, out_scores, out_rows, out_bad, sort_cap);
+    if (e != cudaSuccess) {
+        vq_set_error("launch of scan_finish_kernel failed: %s", cudaGetErrorString(e));
+        return VQ_ECUDA;
+    }
     return VQ_OK;
 }

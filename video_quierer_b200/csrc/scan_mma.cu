@@ -29,7 +29,7 @@
 //
 // Measured design rules (tools/mmabench.cu, B200): a lone tcgen05.mma M128 N128 K16 retires every
 // 64 cycles, but every tcgen05.commit drains the tensor pipe (~160 cycles): one commit per 4 MMAs
-// gives 105-120 cycles/MMA.  Ring slots are therefore released in GROUPS of kGroup k-blocks (one
+// gives 105-120 cycles/MMA.  Ring slots are therefore released in GROUPS of 2^grp_log2 k-blocks (one
 // commit per 16 MMAs) while TMA completion stays per k-block.
 //
 // Threshold bootstrap: the per-query insertion cost is ~k*(1+ln(rows per CTA / k)) serial list
@@ -59,7 +59,6 @@ constexpr int KB_ELEMS = 64;            // bf16 per k-block = one 128-byte swizz
 constexpr int TMEM_COLS = 512;          // whole tensor memory: 2 accumulators + resident query tile
 constexpr int kThreads = 256;
 constexpr int kMaxK = 64;
-constexpr int kGroup = 4;              // ring slots released per tcgen05.commit
 constexpr int kIssuers = 2;            // MMA-issuing warps (warps 1 and 2), alternating k-blocks
 constexpr int kMaxBootTiles = 256;     // sample tiles of the threshold bootstrap (8 per lane in boot_select)
 
@@ -230,7 +229,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 scan_mma_bf16_kernel(const __grid_constant__ CUtensorMap tmS,
                      const __nv_bfloat16* __restrict__ qbf,   // [b_pad, ld] normalised, zero padded
                      float* __restrict__ gtau,                // [b_pad] shared k-th best per query (-inf initialised)
-                     int n, int ld, int nkb, int n_qt, int k, int stages, int b_pad,
+                     int n, int ld, int nkb, int n_qt, int k, int stages, int grp_log2, int b_pad,
                      float* __restrict__ cand_s,              // [b_pad, cap] surviving candidates (BOOT: [tiles, b_pad] maxima)
                      int* __restrict__ cand_r, int* __restrict__ cand_cnt, int cap, int dbg) {
     constexpr int B_KB_BYTES = NT * 128;
@@ -249,6 +248,7 @@ scan_mma_bf16_kernel(const __grid_constant__ CUtensorMap tmS,
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int q_tile = blockIdx.x % n_qt, group = blockIdx.x / n_qt, n_groups = gridDim.x / n_qt;
     const int n_tiles = (n + NT - 1) / NT;
+    const int grp_mask = (1 << grp_log2) - 1;          // ring slots are released 2^grp_log2 at a time
 
     if (warp == 0 && lane == 0) tma_prefetch_desc(&tmS);
     if (warp == 1 && lane == 0) {
@@ -266,6 +266,9 @@ scan_mma_bf16_kernel(const __grid_constant__ CUtensorMap tmS,
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
+    // everything above touched no global memory: it overlaps the previous kernel of the stream (PDL)
+    vq_pdl_wait();
+    vq_pdl_trigger();
 
     // Producer and MMA warps run their loops with ALL lanes (addresses, counters and descriptors stay
     // in uniform registers) and elect one lane only for the asynchronous instruction itself: a loop
@@ -276,7 +279,7 @@ scan_mma_bf16_kernel(const __grid_constant__ CUtensorMap tmS,
         const uint32_t sB_addr = smem_u32(sB), full_addr = smem_u32(full);
         for (int tile = group; tile < n_tiles; tile += n_groups) {
             for (int kb = 0; kb < nkb; ++kb) {
-                if (stage % kGroup == 0) mbar_wait(&empty[stage / kGroup], phase ^ 1);   // whole group free
+                if ((stage & grp_mask) == 0) mbar_wait(&empty[stage >> grp_log2], phase ^ 1);   // whole group free
                 if (elect_one()) {
                     if (dbg & 2) { mbar_arrive(&full[stage]); }
                     else {
@@ -331,11 +334,11 @@ scan_mma_bf16_kernel(const __grid_constant__ CUtensorMap tmS,
                         __syncwarp();
                     }
                 }
-                // ring slots are handed back kGroup at a time; the accumulator is published after the last k-block
-                const bool rel = stage % kGroup == kGroup - 1, last = kb == nkb - 1;
+                // ring slots are handed back 2^grp_log2 at a time; the accumulator is published after the last k-block
+                const bool rel = (stage & grp_mask) == grp_mask, last = kb == nkb - 1;
                 if (rel || last) {
                     if (elect_one()) {
-                        if (rel) umma_commit(&empty[stage / kGroup]);
+                        if (rel) umma_commit(&empty[stage >> grp_log2]);
                         if (last) umma_commit(&tmem_full[acc]);
                     }
                     __syncwarp();
@@ -483,6 +486,8 @@ prep_queries_bf16_kernel(const float* __restrict__ src, int b, int dim, int src_
                          int b_pad, int mode, float* __restrict__ gtau, int* __restrict__ cand_cnt) {
     const int lane = threadIdx.x & 31;
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    vq_pdl_wait();                     // the previous search's kernels still read gtau / cand_cnt / dst
+    vq_pdl_trigger();
     if (row >= b_pad) return;
     __nv_bfloat16* o = dst + (size_t)row * ld;
     if (lane == 0) { gtau[row] = VQ_NEG_INF; cand_cnt[row] = 0; }
@@ -512,6 +517,8 @@ boot_select_kernel(const float* __restrict__ boot_max, int n_t, int b_pad, int k
     __shared__ float vals[8][kMaxBootTiles];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int q = blockIdx.x * 8 + w;
+    vq_pdl_wait();
+    vq_pdl_trigger();
     if (q >= b_pad) return;
     for (int t = lane; t < n_t; t += 32) vals[w][t] = boot_max[(size_t)t * b_pad + q];
     __syncwarp();
@@ -585,7 +592,7 @@ inline size_t align256(size_t v) { return (v + 255) / 256 * 256; }
 inline int pow2_ge(int v) { int p = 2; while (p < v) p <<= 1; return p; }
 
 struct MmaPlan {
-    int nkb, nt, n_qt, b_pad, groups, grid, stages;
+    int nkb, nt, n_qt, b_pad, groups, grid, stages, grp_log2;
     int boot_tiles, boot_groups;                 // threshold bootstrap (0 = off)
     int cap;                                     // candidate slots per query (= groups * k, cannot overflow)
     size_t smem;
@@ -608,7 +615,12 @@ MmaPlan plan(int64_t n, int ld, int b, int k) {
     p.grid = p.groups * p.n_qt;
     const size_t stage_bytes = (size_t)(p.nt ? p.nt : 128) * 128;
     int st = (int)((200 * 1024) / stage_bytes);
-    p.stages = (st > 12 ? 12 : st) / kGroup * kGroup;
+    // Release granularity of the ring: 4 slots per tcgen05.commit.  Finer release (1 or 2 slots, i.e. up
+    // to 11 loads in flight) was measured and does not speed up the memory-bound single-query-tile case
+    // (0.1945 / 0.1925 / 0.1905 ms at 1 / 2 / 4 slots, batch 32), and costs 9 % at batch 1024.
+    static const int grp_env = getenv("VQ_MMA_GROUP") ? atoi(getenv("VQ_MMA_GROUP")) : -1;
+    p.grp_log2 = grp_env >= 0 ? grp_env : 2;
+    p.stages = (st > 12 ? 12 : st) >> p.grp_log2 << p.grp_log2;
     // bootstrap the per-query threshold from a sample of tiles when the scan is long enough to pay for
     // two extra (tiny) launches: sample >= 4k tiles so that the k-th largest tile maximum is a strong bound
     int bt = sms > 4 * k ? sms : 4 * k;
@@ -659,9 +671,8 @@ cudaError_t launch_mma(const MmaPlan& p, const CUtensorMap& tmS, const __nv_bflo
         attr_done = true;
     }
     const int grid = BOOT ? p.boot_groups * p.n_qt : p.grid;
-    kern<<<grid, kThreads, p.smem, stream>>>(tmS, qbf, w.gtau, n, ld, p.nkb, p.n_qt, k, p.stages, p.b_pad,
-                                             BOOT ? w.boot_max : w.cand_s, w.cand_r, w.cnt, p.cap, dbg);
-    return cudaGetLastError();
+    return vq_launch(BOOT ? 1 : 3, kern, dim3(grid), dim3(kThreads), p.smem, stream, tmS, qbf, w.gtau, n, ld, p.nkb, p.n_qt, k, p.stages,
+                     p.grp_log2, p.b_pad, BOOT ? w.boot_max : w.cand_s, w.cand_r, w.cnt, p.cap, dbg);
 }
 
 // [boot pass ->] main pass; gtau / cnt must have been reset by the caller's prologue kernel.
@@ -684,8 +695,12 @@ int run_scan(const MmaPlan& p, const void* store, int64_t n, int ld, const __nv_
             vq_set_error("launch of scan_mma_bf16_kernel<boot> failed: %s", cudaGetErrorString(e));
             return VQ_ECUDA;
         }
-        boot_select_kernel<<<(p.b_pad + 7) / 8, 256, 0, stream>>>(w.boot_max, p.boot_tiles, p.b_pad, k, w.gtau);
-        VQ_LAUNCH_CHECK("boot_select_kernel");
+        e = vq_launch(2, boot_select_kernel, dim3((p.b_pad + 7) / 8), dim3(256), 0, stream, (const float*)w.boot_max, p.boot_tiles,
+                      p.b_pad, k, w.gtau);
+        if (e != cudaSuccess) {
+            vq_set_error("launch of boot_select_kernel failed: %s", cudaGetErrorString(e));
+            return VQ_ECUDA;
+        }
         *launches = 3;
     }
     vq_prof_begin(stream);
@@ -707,6 +722,8 @@ int run_scan(const MmaPlan& p, const void* store, int64_t n, int ld, const __nv_
 
 __global__ void reset_scan_state_kernel(float* gtau, int* cnt, int n) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    vq_pdl_wait();
+    vq_pdl_trigger();
     if (i < n) { gtau[i] = VQ_NEG_INF; cnt[i] = 0; }
 }
 
@@ -742,7 +759,10 @@ int vq_scan_mma_prepared(const void* store, int64_t n, int ld, const void* qbf, 
         return VQ_EWORKSPACE;
     }
     const MmaWs w = carve(p, ws_v);
-    reset_scan_state_kernel<<<(p.b_pad + 255) / 256, 256, 0, stream>>>(w.gtau, w.cnt, p.b_pad);
+    if (vq_launch(0, reset_scan_state_kernel, dim3((p.b_pad + 255) / 256), dim3(256), 0, stream, w.gtau, w.cnt, p.b_pad) != cudaSuccess) {
+        vq_set_error("launch of reset_scan_state_kernel failed");
+        return VQ_ECUDA;
+    }
     int nl = 0;
     int rc = run_scan(p, store, n, ld, (const __nv_bfloat16*)qbf, w, k, stream, &nl);
     if (rc) return rc;
@@ -772,8 +792,11 @@ int vq_scan_mma_run(const void* store, int64_t n, int dim, int ld, int store_dty
         return VQ_EWORKSPACE;
     }
     const MmaWs w = carve(p, ws_v);
-    prep_queries_bf16_kernel<<<(p.b_pad + 7) / 8, 256, 0, stream>>>(queries, b, dim, dim, w.qbf, ld, p.b_pad, query_norm, w.gtau, w.cnt);
-    VQ_LAUNCH_CHECK("prep_queries_bf16_kernel");
+    if (vq_launch(0, prep_queries_bf16_kernel, dim3((p.b_pad + 7) / 8), dim3(256), 0, stream, queries, b, dim, dim, w.qbf, ld,
+                  p.b_pad, query_norm, w.gtau, w.cnt) != cudaSuccess) {
+        vq_set_error("launch of prep_queries_bf16_kernel failed: %s", cudaGetErrorString(cudaGetLastError()));
+        return VQ_ECUDA;
+    }
     int nl = 0;
     int rc = run_scan(p, store, n, ld, w.qbf, w, k_sel, stream, &nl);
     if (rc) return rc;

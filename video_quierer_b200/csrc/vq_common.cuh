@@ -42,6 +42,31 @@ void vq_note_launch(const char* path_or_null, int launches);
     } while (0)
 
 int vq_num_sms();
+int vq_pdl_mask();           // bit i set: kernels of PDL class i are launched with the attribute
+
+// Launch with programmatic dependent launch (PDL): the kernel may start while the previous kernel of
+// the stream is still running; it must execute vq_pdl_wait() before touching anything an earlier
+// kernel wrote and vq_pdl_trigger() AFTER that wait (so that completion stays transitive along the
+// chain).  What overlaps is the launch latency and the kernel's prologue (barrier init, TMEM
+// allocation, descriptor prefetch).  Without the attribute both device calls are no-ops.
+template <typename... KArgs, typename... Args>
+cudaError_t vq_launch(int pdl_class, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = ((vq_pdl_mask() >> pdl_class) & 1) ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+#ifdef __CUDACC__
+__device__ __forceinline__ void vq_pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void vq_pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#endif
 void vq_prof_begin(cudaStream_t s);
 void vq_prof_end(cudaStream_t s);
 
