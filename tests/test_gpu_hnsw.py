@@ -211,3 +211,41 @@ def test_bf16_search_dtype_recall(built_lib):
     _, ra = a.search_arrays(queries, 10)
     _, rb = b.search_arrays(queries, 10)
     assert compare.recall_at_k(rb, ra) >= 0.9
+
+
+def test_sharded_subgraphs_merge(built_lib):
+    """per-shard sub-graphs searched with the same ef and merged with the shard
+    offsets (vq_topk_merge) — 4 logical shards on one GPU.  The merged result must be exactly the
+    best k of the union of the per-shard results, and its recall at least the per-shard average."""
+    import torch
+    from video_quierer_b200 import engine
+    from video_quierer_b200.hnsw_index import B200HNSWIndex
+    from video_quierer_b200.sharded import shard_range
+    n, d, g, k = 20000, 128, 4, 10
+    store = synth.clip_like(n, d, seed=71)
+    queries = synth.clip_like(64, d, seed=72, n_store=n)
+    stored = store / np.linalg.norm(store, axis=1, keepdims=True)
+    truth = np.argsort(-(queries @ stored.T), axis=1)[:, :k]
+    qd = torch.from_numpy(queries).cuda()
+    ss, rr, offs, per_shard = [], [], [], []
+    for r in range(g):
+        lo, hi = shard_range(n, g, r)
+        random.seed(r)
+        h = B200HNSWIndex(dimension=d, ef_search=64)
+        h.add_batch(list(store[lo:hi]), list(range(hi - lo)))
+        s, rows = h.as_local_search()(qd, k)
+        ss.append(s), rr.append(rows), offs.append(lo)
+        local_truth = np.argsort(-(queries @ stored[lo:hi].T), axis=1)[:, :k]
+        per_shard.append(compare.recall_at_k(rows.cpu().numpy(), local_truth))
+    scores, rows = torch.stack(ss).contiguous(), torch.stack(rr).contiguous()
+    ms, mr = engine.Scanner().merge(scores, rows, torch.tensor(offs, dtype=torch.int64, device="cuda"), k)
+    ms, mr = ms.cpu().numpy(), mr.cpu().numpy()
+    # exactly the best k of the union (score desc, global row asc)
+    for b in range(len(queries)):
+        cand = sorted((-float(scores[s_, b, j]), int(rows[s_, b, j]) + offs[s_]) for s_ in range(g) for j in range(k)
+                      if int(rows[s_, b, j]) >= 0)[:k]
+        assert [c[1] for c in cand] == mr[b].tolist()
+        assert np.allclose([-c[0] for c in cand], ms[b])
+    rec = compare.recall_at_k(mr, truth)
+    print(f"sharded HNSW: merged recall@10={rec:.3f}, per-shard {np.round(per_shard, 3)}")
+    assert rec >= np.mean(per_shard) - 0.02

@@ -41,6 +41,21 @@ def test_argument_validation_without_gpu(built_lib):
     assert lib.vq_scan_workspace_bytes(1000000, 512, 512, 0, 32, 10, 0) > 0
 
 
+def test_two_stage_argument_validation_without_gpu(built_lib):
+    lib = _lib.load()
+    # k_cand < k
+    rc = lib.vq_search_two_stage(None, None, 1000, 512, 512, None, 4, 10, 5, 1, 0.004, None, None, None, None, 0, None)
+    assert rc == -1 and b"k_cand" in lib.vq_last_error()
+    # bf16 stores need ld % 64 == 0
+    rc = lib.vq_search_two_stage(None, None, 1000, 500, 520, None, 4, 10, 32, 1, 0.004, None, None, None, None, 0, None)
+    assert rc == -1 and b"ld" in lib.vq_last_error()
+    # b == 0 is a no-op, NULL pointers with b > 0 are rejected
+    assert lib.vq_search_two_stage(None, None, 1000, 512, 512, None, 0, 10, 32, 1, 0.004, None, None, None, None, 0, None) == 0
+    rc = lib.vq_search_two_stage(None, None, 1000, 512, 512, None, 4, 10, 32, 1, 0.004, None, None, None, None, 0, None)
+    assert rc == -1 and b"NULL" in lib.vq_last_error()
+    assert lib.vq_search_two_stage_workspace_bytes(1000000, 512, 512, 1024, 32) > (1 << 20)
+
+
 def test_no_product_import_of_oracle():
     """The product package must never import the oracle (it is test infrastructure)."""
     pkg = os.path.join(ROOT, "video_quierer_b200")

@@ -305,6 +305,25 @@ class B200HNSWIndex:
     def size(self) -> int:
         return self.element_count
 
+    def as_local_search(self):
+        """Adapter for `sharded.ShardedSearcher` (one independent sub-graph per row
+        shard, searched with the same ef and merged like the exact path).  Returns a callable
+        (queries [b,dim] device tensor, k) -> (scores [b,k] fp32 = 1 - distance, best first; local rows
+        [b,k] int32, -1 = empty) on this index's device."""
+        def local_search(queries: torch.Tensor, k: int):
+            b = queries.shape[0]
+            scores = torch.full((b, k), float("-inf"), dtype=torch.float32, device=self.device)
+            rows = torch.full((b, k), -1, dtype=torch.int32, device=self.device)
+            if self.element_count == 0 or b == 0:
+                return scores, rows
+            dist, r = self._search_rows(queries, k)
+            kk = dist.shape[1]
+            ok = r >= 0
+            scores[:, :kk] = torch.from_numpy(np.where(ok, 1.0 - dist, -np.inf).astype(np.float32)).to(self.device)
+            rows[:, :kk] = torch.from_numpy(np.where(ok, r, -1).astype(np.int32)).to(self.device)
+            return scores, rows
+        return local_search
+
     # ------------------------------------------------------------------ reference-format views
     @property
     def data(self) -> Dict:
