@@ -240,16 +240,19 @@ def run_ours(args):
             barrier()
             dev_ms = e0.elapsed_time(e1)
         else:
-            dev_ms = 0.0
+            # shard small enough to sit in L2: a 256 MB buffer is overwritten before every step, outside
+            # the event pair of the step; all steps are queued first and synchronised once, so the GPU
+            # is never idle waiting for the host between the flush and the step
+            evs = []
             for _ in range(steps):
                 flush.zero_()
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
                 step_device()
                 e1.record()
-                torch.cuda.synchronize()
-                dev_ms += e0.elapsed_time(e1)
+                evs.append((e0, e1))
             barrier()
+            dev_ms = sum(a.elapsed_time(b) for a, b in evs)
         # -- dominant kernel alone: the library's own events around the scan kernel
         lib.vq_profile_enable(1)
         kern = []

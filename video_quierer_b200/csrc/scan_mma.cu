@@ -621,12 +621,16 @@ MmaPlan plan(int64_t n, int ld, int b, int k) {
     static const int grp_env = getenv("VQ_MMA_GROUP") ? atoi(getenv("VQ_MMA_GROUP")) : -1;
     p.grp_log2 = grp_env >= 0 ? grp_env : 2;
     p.stages = (st > 12 ? 12 : st) >> p.grp_log2 << p.grp_log2;
-    // bootstrap the per-query threshold from a sample of tiles when the scan is long enough to pay for
-    // two extra (tiny) launches: sample >= 4k tiles so that the k-th largest tile maximum is a strong bound
+    // Bootstrap the per-query threshold from a sample of tiles when the scan is long enough to pay for two
+    // extra (tiny) launches; the sample holds >= 4k tiles so that the k-th largest tile maximum is a strong
+    // bound.  With several query tiles per store tile the list insertions dominate short scans as well
+    // (125k rows x 1024 queries, one shard of 8: 0.26 ms cold vs the 0.07 ms of MMA work), so there the
+    // pass is already worth a quarter of the tiles.
     int bt = sms > 4 * k ? sms : 4 * k;
     if (bt > kMaxBootTiles) bt = kMaxBootTiles;
     static const bool boot_on = getenv("VQ_MMA_BOOT") ? atoi(getenv("VQ_MMA_BOOT")) != 0 : true;
-    p.boot_tiles = (boot_on && p.nt && n_tiles >= 16LL * bt && bt >= k) ? bt : 0;
+    const long long min_tiles = (p.n_qt >= 2 ? 4LL : 16LL) * bt;
+    p.boot_tiles = (boot_on && p.nt && n_tiles >= min_tiles && bt >= k) ? bt : 0;
     p.boot_groups = p.boot_tiles ? (p.boot_tiles < (int)groups ? p.boot_tiles : (int)groups) : 0;
     p.smem = 1024 + (size_t)p.stages * stage_bytes + 512;
     // candidate capacity is sized for the largest group count any batch <= b can get (the HNSW builder
