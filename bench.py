@@ -157,7 +157,7 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
     from video_quierer_b200 import _lib, engine
-    from video_quierer_b200.flat_index import exact_fallback, two_stage_search
+    from video_quierer_b200.flat_index import resolve_uncertified, two_stage_search
     from video_quierer_b200.sharded import ShardedSearcher, shard_range
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -287,9 +287,10 @@ def run_ours(args):
                     out_bad.copy_(bad, non_blocking=True)      # + its per-query certificate
                 torch.cuda.synchronize()
                 if bad is not None and world == 1 and bool(out_bad.any()):
-                    # queries whose two-stage result could not be certified: exact fp32 scan, inside the timing
+                    # queries whose two-stage result could not be certified: collect pass (+ fp32 scan on
+                    # overflow), inside the timing
                     idx = torch.nonzero(out_bad).flatten()
-                    sf, rf = exact_fallback(scanner, store, q, K_TOP, idx.to(dev))
+                    sf, rf = resolve_uncertified(scanner, store, q, K_TOP, idx.to(dev), s)
                     out_scores[idx] = sf.cpu()
                     out_rows[idx] = rf.cpu().to(out_rows.dtype)
                     n_fallback[0] += len(idx)

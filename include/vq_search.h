@@ -130,6 +130,21 @@ int vq_search_two_stage(const void* store_bf16, const float* store_f32, int64_t 
                         float* out_scores, int32_t* out_rows, int32_t* out_uncertified,
                         void* workspace, size_t workspace_bytes, void* stream);
 
+/* Collect pass — the exact answer for queries vq_search_two_stage could not certify, still at
+ * tensor-core speed: every row whose bf16-operand score reaches thresholds[q] is gathered (at most cap
+ * per query), ALL gathered rows are re-scored exactly from the fp32 copy and the best k by exact score
+ * are returned.  With thresholds[q] = s_k - score_eps, s_k being any lower bound of the exact k-th best
+ * score (e.g. the k-th score vq_search_two_stage returned), every row of the exact top-k is gathered:
+ * its exact score is >= s_k, so its bf16-operand score is >= s_k - score_eps.
+ *   thresholds   [b] fp32 (device);  cap: candidate slots per query (k <= cap <= 16384)
+ *   out_overflow [b] int32: 1 = more than cap rows reached the threshold, the result is incomplete
+ *                (re-run that query with vq_scan_topk on the fp32 store). [kernels: scan_mma_bf16<collect>, scan_finish] */
+size_t vq_search_collect_workspace_bytes(int64_t n, int dim, int ld, int b, int cap);
+int vq_search_collect(const void* store_bf16, const float* store_f32, int64_t n, int dim, int ld,
+                      const float* queries, int b, int k, int query_norm, const float* thresholds, int cap,
+                      float* out_scores, int32_t* out_rows, int32_t* out_overflow,
+                      void* workspace, size_t workspace_bytes, void* stream);
+
 /* (d) HNSW greedy/beam search, one warp per query.                     [kernel: hnsw_search]
  * Replaces: HNSWIndex.search / OptimizedHNSWIndex.search, src/indexes/hnsw.py:238-280,
  * :488-528 and _search_layer :76-121 (same stop rule :103 and admit rule :113).

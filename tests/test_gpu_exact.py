@@ -254,3 +254,55 @@ def test_two_stage_falls_back_when_it_cannot_certify(eng):
     ro, so = exact.exact_search_batch(store, q, 10)
     assert compare.check_topk_batch(r, s, ro, so) == []
     assert idx.stats["uncertified_queries"] >= 1
+
+
+def test_collect_pass_resolves_uncertified_and_overflows_to_fma(eng):
+    """vq_search_collect: (1) with the threshold s_k - eps it returns the exact top-k although hundreds
+    of rows sit inside the bf16 resolution; (2) more rows than `cap` above the threshold -> overflow
+    flag, and the facade then answers from the fp32 FMA scan."""
+    engine, _lib, torch = eng
+    from video_quierer_b200.flat_index import BF16_SCORE_EPS, B200FlatIndex
+    rng = np.random.default_rng(51)
+    base = synth.gauss(1, 256, seed=50)[0]
+    near = base[None, :] + 2e-4 * rng.standard_normal((6000, 256)).astype(np.float32)
+    near /= np.linalg.norm(near, axis=1, keepdims=True)
+    store = np.concatenate([synth.gauss(30000, 256, seed=52), near.astype(np.float32)])
+    rng.shuffle(store)
+    q = np.stack([base, synth.gauss(1, 256, seed=53)[0]])
+    ro, so = exact.exact_search_batch(store, q, 10)
+    st = engine.DeviceStore(256, keep_fp32=True, keep_bf16=True)
+    st.append(store)
+    sc = engine.Scanner()
+    qd = engine.as_device_queries(q, 256, st.device)
+    thr = torch.from_numpy(so[:, 9].astype(np.float32) - np.float32(BF16_SCORE_EPS)).to(st.device)
+    # (1) cap large enough for the 6000 near-duplicates
+    s, r, over = sc.collect(st.bf16, st.f32, st.n, 256, qd, 10, thr, cap=8192)
+    assert over.cpu().numpy().tolist() == [0, 0] and sc.last_path.startswith("scan_mma_bf16<collect>")
+    assert compare.check_topk_batch(r.cpu().numpy(), s.cpu().numpy(), ro, so) == []
+    # (2) cap too small for query 0 -> overflow flagged, query 1 still exact
+    s, r, over = sc.collect(st.bf16, st.f32, st.n, 256, qd, 10, thr, cap=1024)
+    assert over.cpu().numpy().tolist() == [1, 0]
+    assert compare.check_topk_batch(r.cpu().numpy()[1:], s.cpu().numpy()[1:], ro[1:], so[1:]) == []
+    # the facade: two-stage -> collect (cap 4096 overflows on query 0) -> fp32 FMA scan, still exact
+    idx = B200FlatIndex(store_dtype="bf16", rescore=True)
+    idx.add_frames(store, ["a.mp4"] * len(store), np.arange(len(store), dtype=float))
+    s2, r2 = idx.search_arrays(q, 10)
+    assert compare.check_topk_batch(r2, s2, ro, so) == []
+    assert idx.stats["uncertified_queries"] >= 1
+
+
+@pytest.mark.parametrize("gen", ["gauss", "clip"])
+def test_two_stage_k50_uses_tensor_path(eng, gen):
+    """k = 50 (the API maximum, src/api/routes.py:56-59): 64 candidates cannot certify most queries, the
+    collect pass resolves them; the fp32 FMA scan is not needed."""
+    engine, _lib, torch = eng
+    from video_quierer_b200.flat_index import B200FlatIndex
+    n, b, k = 40000, 24, 50
+    store = synth.gauss(n, 512, seed=61) if gen == "gauss" else synth.clip_like(n, 512, seed=61)
+    queries = synth.gauss(b, 512, seed=62) if gen == "gauss" else synth.clip_like(b, 512, seed=62, n_store=n)
+    idx = B200FlatIndex(store_dtype="bf16", rescore=True)
+    idx.add_frames(store, ["a.mp4"] * n, np.arange(n, dtype=float))
+    s, r = idx.search_arrays(queries, k)
+    ro, so = exact.exact_search_batch(store, queries, k)
+    assert compare.check_topk_batch(r, s, ro, so) == []
+    assert idx.last_scan_path.startswith("scan_mma_bf16")        # two-stage or collect, never scan_fma

@@ -25,6 +25,11 @@ int vq_scan_mma_run(const void* store, int64_t n, int dim, int ld, int store_dty
                     int b, int k_sel, const float* store_f32, float eps, int k_out, float* out_scores, int32_t* out_rows,
                     int32_t* out_bad, void* ws, size_t ws_bytes, cudaStream_t stream, int* launches);
 
+size_t vq_scan_mma_collect_workspace(int64_t n, int ld, int b, int cap);
+int vq_scan_mma_collect(const void* store_bf16, const float* store_f32, int64_t n, int dim, int ld, const float* queries,
+                        int query_norm, int b, const float* thresholds, int cap, int k, float* out_scores, int32_t* out_rows,
+                        int32_t* out_overflow, void* ws, size_t ws_bytes, cudaStream_t stream, int* launches);
+
 // ----------------------------------------------------------------------------- error state
 static thread_local char g_err[512] = "";
 static thread_local char g_path[64] = "";
@@ -296,6 +301,34 @@ int vq_search_two_stage(const void* store_bf16, const float* store_f32, int64_t 
                          out_scores, out_rows, out_uncertified, workspace, workspace_bytes, stream, &launches);
     if (rc) return rc;
     vq_note_launch("scan_mma_bf16+rescore", launches);
+    return VQ_OK;
+}
+
+size_t vq_search_collect_workspace_bytes(int64_t n, int dim, int ld, int b, int cap) {
+    (void)dim;
+    if (n <= 0 || b <= 0 || cap <= 0) return 256;
+    return vq_scan_mma_collect_workspace(n, ld, b, cap) + 256;
+}
+
+int vq_search_collect(const void* store_bf16, const float* store_f32, int64_t n, int dim, int ld,
+                      const float* queries, int b, int k, int query_norm, const float* thresholds, int cap,
+                      float* out_scores, int32_t* out_rows, int32_t* out_overflow,
+                      void* workspace, size_t workspace_bytes, void* stream_v) {
+    cudaStream_t stream = (cudaStream_t)stream_v;
+    int rc = check_store(n, dim, ld, VQ_BF16);
+    if (rc) return rc;
+    VQ_CHECK_ARG(b >= 0 && k > 0 && k <= 64 && cap >= k && cap <= 16384, "need b >= 0, 0 < k <= 64, k <= cap <= 16384 (b=%d k=%d cap=%d)", b, k, cap);
+    VQ_CHECK_ARG(query_norm >= VQ_NORM_NONE && query_norm <= VQ_NORM_PLAIN, "bad query_norm %d", query_norm);
+    if (b == 0) { vq_note_launch("none", 0); return VQ_OK; }
+    VQ_CHECK_ARG(n > 0, "collect pass needs a non-empty store");
+    VQ_CHECK_ARG(store_bf16 && store_f32 && queries && thresholds && out_scores && out_rows && out_overflow && workspace,
+                 "NULL pointer argument");
+    VQ_CHECK_ARG(((uintptr_t)workspace & 255) == 0, "workspace must be 256-byte aligned");
+    int launches = 0;
+    rc = vq_scan_mma_collect(store_bf16, store_f32, n, dim, ld, queries, query_norm, b, thresholds, cap, k, out_scores, out_rows,
+                             out_overflow, workspace, workspace_bytes, stream, &launches);
+    if (rc) return rc;
+    vq_note_launch("scan_mma_bf16<collect>+rescore", launches);
     return VQ_OK;
 }
 

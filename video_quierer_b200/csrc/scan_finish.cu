@@ -44,7 +44,8 @@ __device__ __forceinline__ float key_score(uint32_t k) {
 }
 
 __global__ void __launch_bounds__(kThreads)
-scan_finish_kernel(const float* __restrict__ cand_s, const int* __restrict__ cand_r, const int* __restrict__ cand_cnt,
+scan_finish_kernel(int mode,      // 0 plain top-k of the scan scores, 1 two-stage + certificate, 2 re-score ALL candidates
+                   const float* __restrict__ cand_s, const int* __restrict__ cand_r, const int* __restrict__ cand_cnt,
                    int cap, int k_sel, const float* __restrict__ store_f32, int ld, int dim,
                    const float* __restrict__ queries, int query_norm, float eps, int k_out,
                    float* __restrict__ out_s, int* __restrict__ out_r, int* __restrict__ out_bad, int sort_cap) {
@@ -67,7 +68,7 @@ scan_finish_kernel(const float* __restrict__ cand_s, const int* __restrict__ can
 
     int n = cand_cnt[q];
     n = n < cap ? n : cap;
-    if (tid == 0) { key_min = 0xffffffffu; key_max = 0u; sel_cnt = 0; if (out_bad) out_bad[q] = 0; }
+    if (tid == 0) { key_min = 0xffffffffu; key_max = 0u; sel_cnt = 0; if (out_bad && mode != 2) out_bad[q] = 0; }
     __syncthreads();
     // ---- load: candidates -> 64-bit keys in shared memory (+ their score-key range); meanwhile the
     // last warp normalises the query in fp32 (same arithmetic as ingest_rows_kernel)
@@ -82,8 +83,8 @@ scan_finish_kernel(const float* __restrict__ cand_s, const int* __restrict__ can
         if (query_norm != VQ_NORM_NONE) { d = sqrtf(sum); if (query_norm == VQ_NORM_EPS) d += 1e-10f; }
         for (int c = lane; c < ld; c += 32) qn[c] = c < dim ? (query_norm == VQ_NORM_NONE ? s[c] : s[c] / d) : 0.f;
     }
-    {
-        const size_t base = (size_t)q * cap;
+    const size_t base = (size_t)q * cap;
+    if (mode != 2) {
         unsigned mn = 0xffffffffu, mx = 0u;
         for (int i = tid; i < n; i += kThreads) {
             const unsigned kh = score_key(cand_s[base + i]);
@@ -98,6 +99,46 @@ scan_finish_kernel(const float* __restrict__ cand_s, const int* __restrict__ can
             mx = b > mx ? b : mx;
         }
         if (lane == 0 && n > 0) { atomicMin(&key_min, mn); atomicMax(&key_max, mx); }
+    } else {
+        // collect mode: the scan scores only selected the candidates; every one of them is re-scored
+        // exactly (4 rows per warp in flight) and the keys are built from the EXACT scores
+        __syncthreads();                                     // qn is complete
+        const float4* y = reinterpret_cast<const float4*>(qn);
+        unsigned mn = 0xffffffffu, mx = 0u;
+        for (int c0 = warp; c0 < n; c0 += 4 * (kThreads / 32)) {
+            float acc[4] = {0.f, 0.f, 0.f, 0.f};
+            int rr[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int c = c0 + u * (kThreads / 32);
+                rr[u] = c < n ? cand_r[base + c] : -1;
+            }
+            for (int j = lane; j < ld / 4; j += 32) {
+                float4 a[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    a[u] = rr[u] >= 0 ? reinterpret_cast<const float4*>(store_f32 + (size_t)rr[u] * ld)[j] : make_float4(0.f, 0.f, 0.f, 0.f);
+                const float4 bq = y[j];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    acc[u] = fmaf(a[u].x, bq.x, acc[u]); acc[u] = fmaf(a[u].y, bq.y, acc[u]);
+                    acc[u] = fmaf(a[u].z, bq.z, acc[u]); acc[u] = fmaf(a[u].w, bq.w, acc[u]);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const float t = vq_warp_sum(acc[u]);
+                const int c = c0 + u * (kThreads / 32);
+                if (c < n) {
+                    const unsigned kh = score_key(t);
+                    if (lane == 0) keys[c] = ((unsigned long long)kh << 32) | (unsigned)rr[u];
+                    mn = kh < mn ? kh : mn;
+                    mx = kh > mx ? kh : mx;
+                }
+            }
+        }
+        if (lane == 0 && n > 0) { atomicMin(&key_min, mn); atomicMax(&key_max, mx); }
+        if (tid == 0 && out_bad) out_bad[q] = cand_cnt[q] > cap ? 1 : 0;      // overflow: result incomplete
     }
     __syncthreads();
     FDBG(1);
@@ -168,7 +209,7 @@ scan_finish_kernel(const float* __restrict__ cand_s, const int* __restrict__ can
     FDBG(3);
     keys = sorted;                               // entries [0, min(n, k_sel)) are what follows needs
 
-    if (store_f32 == nullptr) {
+    if (mode != 1) {
         for (int i = tid; i < k_out; i += kThreads) {
             const bool ok = i < n;
             out_s[(size_t)q * k_out + i] = ok ? key_score((unsigned)(keys[i] >> 32)) : VQ_NEG_INF;
@@ -239,7 +280,7 @@ scan_finish_kernel(const float* __restrict__ cand_s, const int* __restrict__ can
 
 }  // namespace
 
-int vq_scan_finish_launch(const float* cand_s, const int* cand_r, const int* cand_cnt, int cap, int b, int k_sel,
+int vq_scan_finish_launch(int mode, const float* cand_s, const int* cand_r, const int* cand_cnt, int cap, int b, int k_sel,
                           const float* store_f32, int ld, int dim, const float* queries, int query_norm, float eps,
                           int k_out, float* out_scores, int* out_rows, int* out_bad, cudaStream_t stream) {
     if (b <= 0) return VQ_OK;
@@ -261,7 +302,7 @@ int vq_scan_finish_launch(const float* cand_s, const int* cand_r, const int* can
         VQ_CUDA(cudaFuncSetAttribute(scan_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
         attr_done = true;
     }
-    const cudaError_t e = vq_launch(4, scan_finish_kernel, dim3(b), dim3(kThreads), smem, stream, cand_s, cand_r, cand_cnt, cap, k_sel,
+    const cudaError_t e = vq_launch(4, scan_finish_kernel, dim3(b), dim3(kThreads), smem, stream, mode, cand_s, cand_r, cand_cnt, cap, k_sel,
                                     store_f32, ld, dim, queries, query_norm, eps, k_out, out_scores, out_rows, out_bad, sort_cap);
     if (e != cudaSuccess) {
         vq_set_error("launch of scan_finish_kernel failed: %s", cudaGetErrorString(e));

@@ -59,6 +59,7 @@ constexpr int KB_ELEMS = 64;            // bf16 per k-block = one 128-byte swizz
 constexpr int TMEM_COLS = 512;          // whole tensor memory: 2 accumulators + resident query tile
 constexpr int kThreads = 256;
 constexpr int kMaxK = 64;
+constexpr int kModeList = 0, kModeBoot = 1, kModeCollect = 2;   // epilogue of scan_mma_bf16_kernel
 constexpr int kIssuers = 2;            // MMA-issuing warps (warps 1 and 2), alternating k-blocks
 constexpr int kMaxBootTiles = 256;     // sample tiles of the threshold bootstrap (8 per lane in boot_select)
 
@@ -224,7 +225,7 @@ __device__ __forceinline__ void filter_insert(const uint32_t (&v)[32], int row_b
     }
 }
 
-template <int KL, int NT, bool BOOT>
+template <int KL, int NT, int MODE>
 __global__ void __launch_bounds__(kThreads, 1)
 scan_mma_bf16_kernel(const __grid_constant__ CUtensorMap tmS,
                      const __nv_bfloat16* __restrict__ qbf,   // [b_pad, ld] normalised, zero padded
@@ -383,7 +384,43 @@ scan_mma_bf16_kernel(const __grid_constant__ CUtensorMap tmS,
             __syncwarp();
             if (lane == 0) mbar_arrive(a_full);
         }
-        if (BOOT) {
+        if (MODE == kModeCollect) {
+            // collect pass: EVERY row whose score reaches the query's fixed threshold is appended to the
+            // query's candidate buffer (no lists).  Used to resolve queries the certificate rejected.
+            const float thr = gtau[q];
+            const size_t dst = (size_t)q * cap;
+            int it = 0;
+            for (int tile = group; tile < n_tiles; tile += n_groups, ++it) {
+                const int acc = it & 1;
+                const uint32_t acc_phase = (it >> 1) & 1;
+                mbar_wait(&tmem_full[acc], acc_phase);
+                tc_fence_after();
+                const int row0 = tile * NT;
+                const int valid = (n - row0) < NT ? (n - row0) : NT;
+#pragma unroll 1
+                for (int c0 = 0; c0 < NT; c0 += 32) {
+                    uint32_t v[32];
+                    tmem_ld32(lane_base + (uint32_t)(acc * NT + c0), v);
+                    unsigned mask = 0;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) mask |= (__uint_as_float(v[j]) >= thr) ? (1u << j) : 0u;
+                    const int left = valid - c0;
+                    if (left < 32) mask &= left > 0 ? ((1u << left) - 1u) : 0u;
+                    while (mask) {
+                        const int j = __ffs(mask) - 1;
+                        mask &= mask - 1;
+                        float sc = __uint_as_float(v[0]);
+#pragma unroll
+                        for (int jj = 1; jj < 32; ++jj) sc = (j == jj) ? __uint_as_float(v[jj]) : sc;
+                        const int at = atomicAdd(cand_cnt + q, 1);
+                        if (at < cap) { cand_s[dst + at] = sc; cand_r[dst + at] = row0 + c0 + j; }
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+            }
+        } else if (MODE == kModeBoot) {
             // threshold bootstrap: only the per-query maximum of every sample tile is kept
             int it = 0;
             for (int tile = group; tile < n_tiles; tile += n_groups, ++it) {
@@ -483,14 +520,15 @@ scan_mma_bf16_kernel(const __grid_constant__ CUtensorMap tmS,
 // shared threshold array reset; one warp per row.
 __global__ void __launch_bounds__(256)
 prep_queries_bf16_kernel(const float* __restrict__ src, int b, int dim, int src_ld, __nv_bfloat16* __restrict__ dst, int ld,
-                         int b_pad, int mode, float* __restrict__ gtau, int* __restrict__ cand_cnt) {
+                         int b_pad, int mode, float* __restrict__ gtau, int* __restrict__ cand_cnt,
+                         const float* __restrict__ thr_in) {   // collect pass: per-query thresholds (NULL otherwise)
     const int lane = threadIdx.x & 31;
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     vq_pdl_wait();                     // the previous search's kernels still read gtau / cand_cnt / dst
     vq_pdl_trigger();
     if (row >= b_pad) return;
     __nv_bfloat16* o = dst + (size_t)row * ld;
-    if (lane == 0) { gtau[row] = VQ_NEG_INF; cand_cnt[row] = 0; }
+    if (lane == 0) { gtau[row] = thr_in ? (row < b ? thr_in[row] : INFINITY) : VQ_NEG_INF; cand_cnt[row] = 0; }
     if (row >= b) {
         for (int c = lane; c < ld; c += 32) o[c] = __float2bfloat16_rn(0.f);
         return;
@@ -664,10 +702,11 @@ MmaWs carve(const MmaPlan& p, void* ws_v) {
     return w;
 }
 
-template <int KL, int NT, bool BOOT>
+template <int KL, int NT, int MODE>
 cudaError_t launch_mma(const MmaPlan& p, const CUtensorMap& tmS, const __nv_bfloat16* qbf, const MmaWs& w, int n, int ld, int k,
                        int dbg, cudaStream_t stream) {
-    auto kern = scan_mma_bf16_kernel<KL, NT, BOOT>;
+    auto kern = scan_mma_bf16_kernel<KL, NT, MODE>;
+    constexpr bool BOOT = MODE == kModeBoot;
     static bool attr_done = false;
     if (!attr_done) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
@@ -693,8 +732,8 @@ int run_scan(const MmaPlan& p, const void* store, int64_t n, int ld, const __nv_
     if (p.boot_tiles) {
         // sample pass over the first boot_tiles full tiles: per-tile maxima -> boot_max, then gtau
         const int n_boot = p.boot_tiles * p.nt;
-        e = p.nt == 128 ? launch_mma<1, 128, true>(p, tmS, qbf, w, n_boot, ld, k, dbg, stream)
-                        : launch_mma<1, 64, true>(p, tmS, qbf, w, n_boot, ld, k, dbg, stream);
+        e = p.nt == 128 ? launch_mma<1, 128, kModeBoot>(p, tmS, qbf, w, n_boot, ld, k, dbg, stream)
+                        : launch_mma<1, 64, kModeBoot>(p, tmS, qbf, w, n_boot, ld, k, dbg, stream);
         if (e != cudaSuccess) {
             vq_set_error("launch of scan_mma_bf16_kernel<boot> failed: %s", cudaGetErrorString(e));
             return VQ_ECUDA;
@@ -709,13 +748,13 @@ int run_scan(const MmaPlan& p, const void* store, int64_t n, int ld, const __nv_
     }
     vq_prof_begin(stream);
     if (p.nt == 128)
-        e = k <= 16 ? launch_mma<16, 128, false>(p, tmS, qbf, w, (int)n, ld, k, dbg, stream)
-          : k <= 32 ? launch_mma<32, 128, false>(p, tmS, qbf, w, (int)n, ld, k, dbg, stream)
-                    : launch_mma<64, 128, false>(p, tmS, qbf, w, (int)n, ld, k, dbg, stream);
+        e = k <= 16 ? launch_mma<16, 128, kModeList>(p, tmS, qbf, w, (int)n, ld, k, dbg, stream)
+          : k <= 32 ? launch_mma<32, 128, kModeList>(p, tmS, qbf, w, (int)n, ld, k, dbg, stream)
+                    : launch_mma<64, 128, kModeList>(p, tmS, qbf, w, (int)n, ld, k, dbg, stream);
     else
-        e = k <= 16 ? launch_mma<16, 64, false>(p, tmS, qbf, w, (int)n, ld, k, dbg, stream)
-          : k <= 32 ? launch_mma<32, 64, false>(p, tmS, qbf, w, (int)n, ld, k, dbg, stream)
-                    : launch_mma<64, 64, false>(p, tmS, qbf, w, (int)n, ld, k, dbg, stream);
+        e = k <= 16 ? launch_mma<16, 64, kModeList>(p, tmS, qbf, w, (int)n, ld, k, dbg, stream)
+          : k <= 32 ? launch_mma<32, 64, kModeList>(p, tmS, qbf, w, (int)n, ld, k, dbg, stream)
+                    : launch_mma<64, 64, kModeList>(p, tmS, qbf, w, (int)n, ld, k, dbg, stream);
     vq_prof_end(stream);
     if (e != cudaSuccess) {
         vq_set_error("launch of scan_mma_bf16_kernel failed: %s", cudaGetErrorString(e));
@@ -734,7 +773,7 @@ __global__ void reset_scan_state_kernel(float* gtau, int* cnt, int n) {
 }  // namespace
 
 // scan_finish.cu: final selection out of the candidate buffers (+ optional exact fp32 re-score)
-int vq_scan_finish_launch(const float* cand_s, const int* cand_r, const int* cand_cnt, int cap, int b, int k_sel,
+int vq_scan_finish_launch(int mode, const float* cand_s, const int* cand_r, const int* cand_cnt, int cap, int b, int k_sel,
                           const float* store_f32, int ld, int dim, const float* queries, int query_norm, float eps,
                           int k_out, float* out_scores, int* out_rows, int* out_bad, cudaStream_t stream);
 
@@ -770,7 +809,7 @@ int vq_scan_mma_prepared(const void* store, int64_t n, int ld, const void* qbf, 
     int nl = 0;
     int rc = run_scan(p, store, n, ld, (const __nv_bfloat16*)qbf, w, k, stream, &nl);
     if (rc) return rc;
-    return vq_scan_finish_launch(w.cand_s, w.cand_r, w.cnt, p.cap, b, k, nullptr, ld, ld, nullptr, VQ_NORM_NONE, 0.f, k,
+    return vq_scan_finish_launch(0, w.cand_s, w.cand_r, w.cnt, p.cap, b, k, nullptr, ld, ld, nullptr, VQ_NORM_NONE, 0.f, k,
                                  out_scores, out_rows, nullptr, stream);
 }
 
@@ -797,16 +836,71 @@ int vq_scan_mma_run(const void* store, int64_t n, int dim, int ld, int store_dty
     }
     const MmaWs w = carve(p, ws_v);
     if (vq_launch(0, prep_queries_bf16_kernel, dim3((p.b_pad + 7) / 8), dim3(256), 0, stream, queries, b, dim, dim, w.qbf, ld,
-                  p.b_pad, query_norm, w.gtau, w.cnt) != cudaSuccess) {
+                  p.b_pad, query_norm, w.gtau, w.cnt, (const float*)nullptr) != cudaSuccess) {
         vq_set_error("launch of prep_queries_bf16_kernel failed: %s", cudaGetErrorString(cudaGetLastError()));
         return VQ_ECUDA;
     }
     int nl = 0;
     int rc = run_scan(p, store, n, ld, w.qbf, w, k_sel, stream, &nl);
     if (rc) return rc;
-    rc = vq_scan_finish_launch(w.cand_s, w.cand_r, w.cnt, p.cap, b, k_sel, store_f32, ld, dim, queries, query_norm, eps, k_out,
-                               out_scores, out_rows, out_bad, stream);
+    rc = vq_scan_finish_launch(store_f32 ? 1 : 0, w.cand_s, w.cand_r, w.cnt, p.cap, b, k_sel, store_f32, ld, dim, queries, query_norm,
+                               eps, k_out, out_scores, out_rows, out_bad, stream);
     if (rc) return rc;
     *launches = 2 + nl;
+    return VQ_OK;
+}
+
+// Collect pass (resolves queries the two-stage certificate rejected): every row whose bf16-operand score
+// reaches thresholds[q] is gathered (at most `cap` per query), ALL of them are re-scored exactly from the
+// fp32 copy and the best k by exact score are returned.  With thresholds[q] = (a lower bound of the exact
+// k-th best score) - score_eps the gathered set contains the exact top-k by construction.
+// out_overflow[q] = 1 if more than `cap` rows reached the threshold (result incomplete).
+size_t vq_scan_mma_collect_workspace(int64_t n, int ld, int b, int cap) {
+    const MmaPlan p = plan(n, ld, b, 1);
+    return p.off_cand_s + 2 * align256((size_t)p.b_pad * cap * 4) + align256((size_t)p.b_pad * ld * 2) + 256;
+}
+int vq_scan_mma_collect(const void* store_bf16, const float* store_f32, int64_t n, int dim, int ld, const float* queries,
+                        int query_norm, int b, const float* thresholds, int cap, int k, float* out_scores, int32_t* out_rows,
+                        int32_t* out_overflow, void* ws_v, size_t ws_bytes, cudaStream_t stream, int* launches) {
+    if (!vq_scan_mma_supported(n, dim, ld, VQ_BF16, b, 1) || cap < k) {
+        vq_set_error("scan_mma_collect: unsupported shape n=%lld dim=%d ld=%d b=%d cap=%d k=%d", (long long)n, dim, ld, b, cap, k);
+        return VQ_EUNSUPPORTED;
+    }
+    MmaPlan p = plan(n, ld, b, 1);
+    if (ws_bytes < vq_scan_mma_collect_workspace(n, ld, b, cap) - 256) {
+        vq_set_error("scan_mma_collect: workspace too small");
+        return VQ_EWORKSPACE;
+    }
+    unsigned char* ws = (unsigned char*)ws_v;
+    MmaWs w;
+    w.gtau = (float*)(ws + p.off_tau);
+    w.cnt = (int*)(ws + p.off_cnt);
+    const size_t cand_bytes = align256((size_t)p.b_pad * cap * 4);
+    w.cand_s = (float*)(ws + p.off_cand_s);
+    w.cand_r = (int*)(ws + p.off_cand_s + cand_bytes);
+    w.boot_max = nullptr;
+    w.qbf = (__nv_bfloat16*)(ws + p.off_cand_s + 2 * cand_bytes);
+    p.cap = cap;
+    if (vq_launch(0, prep_queries_bf16_kernel, dim3((p.b_pad + 7) / 8), dim3(256), 0, stream, queries, b, dim, dim, w.qbf, ld,
+                  p.b_pad, query_norm, w.gtau, w.cnt, thresholds) != cudaSuccess) {
+        vq_set_error("launch of prep_queries_bf16_kernel failed");
+        return VQ_ECUDA;
+    }
+    static const int dbg = 0;
+    CUtensorMap tmS;
+    if (!get_map_bf16(&tmS, store_bf16, (uint64_t)n, (uint64_t)ld, (uint32_t)p.nt)) {
+        vq_set_error("scan_mma: cuTensorMapEncodeTiled failed");
+        return VQ_ECUDA;
+    }
+    const cudaError_t e = p.nt == 128 ? launch_mma<1, 128, kModeCollect>(p, tmS, w.qbf, w, (int)n, ld, 1, dbg, stream)
+                                      : launch_mma<1, 64, kModeCollect>(p, tmS, w.qbf, w, (int)n, ld, 1, dbg, stream);
+    if (e != cudaSuccess) {
+        vq_set_error("launch of scan_mma_bf16_kernel<collect> failed: %s", cudaGetErrorString(e));
+        return VQ_ECUDA;
+    }
+    const int rc = vq_scan_finish_launch(2, w.cand_s, w.cand_r, w.cnt, cap, b, k, store_f32, ld, dim, queries, query_norm, 0.f, k,
+                                         out_scores, out_rows, out_overflow, stream);
+    if (rc) return rc;
+    *launches = 3;
     return VQ_OK;
 }

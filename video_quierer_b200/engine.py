@@ -195,6 +195,30 @@ class Scanner:
                 self.last_launches = _lib.last_launch_count()
         return out_s, out_r, bad
 
+    def collect(self, bf16: torch.Tensor, f32: torch.Tensor, n: int, dim: int, queries: torch.Tensor, k: int,
+                thresholds: torch.Tensor, cap: int = 4096, norm: int = _lib.NORM_EPS):
+        """`vq_search_collect`: gather every row whose bf16 score reaches thresholds[q], re-score all of
+        them exactly, best k.  Returns (scores [b,k] f32, rows [b,k] i32, overflow [b] i32)."""
+        ld = bf16.stride(0)
+        b = queries.shape[0]
+        with torch.cuda.device(self.device):
+            out_s = torch.empty((b, k), dtype=torch.float32, device=self.device)
+            out_r = torch.empty((b, k), dtype=torch.int32, device=self.device)
+            over = torch.zeros((b,), dtype=torch.int32, device=self.device)
+            if b == 0:
+                return out_s, out_r, over
+            thresholds = thresholds.to(torch.float32).contiguous()
+            need = self.lib.vq_search_collect_workspace_bytes(n, dim, ld, b, cap)
+            with self.lock:
+                ws = self.ws.get(need)
+                rc = self.lib.vq_search_collect(_ptr(bf16), _ptr(f32), n, dim, ld, _ptr(queries), b, k, norm, _ptr(thresholds),
+                                                cap, _ptr(out_s), _ptr(out_r), _ptr(over), _ptr(ws), ws.numel(),
+                                                _stream(self.device))
+                _lib.check(rc, "vq_search_collect")
+                self.last_path = _lib.last_scan_path()
+                self.last_launches = _lib.last_launch_count()
+        return out_s, out_r, over
+
     def rescore(self, f32: torch.Tensor, n: int, dim: int, queries_norm_padded: torch.Tensor,
                 cand_rows: torch.Tensor, k: int):
         b, kc = cand_rows.shape

@@ -99,9 +99,13 @@ def two_stage_search(scanner: Scanner, st: DeviceStore, q_dev: torch.Tensor, k: 
     Returns ([b,k] f32, [b,k] i32, uncertified [b] bool device tensor or None); the caller re-runs
     uncertified queries (near-duplicate heavy data) with `exact_fallback` after its device->host
     read, so no extra sync is added here."""
+    # candidates per query: 32 for k <= 16, else max(2k, k+22), capped at the register top-k of the tensor
+    # kernel.  Where the cap bites (k > 42) the certificate mostly fails and the collect pass of
+    # `resolve_uncertified` delivers the exact answer — still two tensor-core passes instead of the
+    # fp32 FMA scan.
     kc = int(os.environ.get("VQ_KCAND", 0)) or (32 if k <= 16 else max(2 * k, k + 22))
-    kc = max(min(st.n, kc), k)
-    if kc > MAX_TENSOR_K or st.ld > MAX_TENSOR_LD:
+    kc = max(min(st.n, kc, MAX_TENSOR_K), min(k, st.n))
+    if k > MAX_TENSOR_K or st.ld > MAX_TENSOR_LD:
         # beyond the register top-k of the tensor path: the fp32 FMA scan is exact by itself
         s, r = scanner.scan(st.f32, st.n, st.dim, q_dev, k, _lib.NORM_EPS, "fma")
         return s, r, None
@@ -111,8 +115,29 @@ def two_stage_search(scanner: Scanner, st: DeviceStore, q_dev: torch.Tensor, k: 
 
 
 def exact_fallback(scanner: Scanner, st: DeviceStore, q_dev: torch.Tensor, k: int, idx: torch.Tensor):
-    """fp32 FMA scan for the queries `idx` whose two-stage result could not be certified."""
+    """fp32 FMA scan for the queries `idx` (last resort: always exact, any k)."""
     return scanner.scan(st.f32, st.n, st.dim, q_dev[idx].contiguous(), k, _lib.NORM_EPS, "fma")
+
+
+COLLECT_CAP = 4096
+
+
+def resolve_uncertified(scanner: Scanner, st: DeviceStore, q_dev: torch.Tensor, k: int, idx: torch.Tensor,
+                        s_two_stage: torch.Tensor, max_row_norm: float = 1.0):
+    """Exact top-k for the queries `idx` whose two-stage result was not certified (near-duplicate
+    heavy data).  The k-th exact score the two-stage pass returned is a lower bound s_k of the true
+    k-th best, so every row of the true top-k has bf16-operand score >= s_k - eps: a second
+    tensor-core pass gathers exactly those rows (`vq_search_collect`), re-scores ALL of them from
+    the fp32 copy and keeps the best k.  Only queries with more than COLLECT_CAP such rows (mass
+    duplicates) go to the fp32 FMA scan.  Returns (scores [m,k] f32, rows [m,k] i32) device tensors."""
+    qs = q_dev[idx].contiguous()
+    thr = s_two_stage[idx, k - 1] - BF16_SCORE_EPS * max_row_norm
+    s, r, over = scanner.collect(st.bf16, st.f32, st.n, st.dim, qs, k, thr, COLLECT_CAP)
+    over_h = torch.nonzero(over).flatten()
+    if len(over_h):
+        sf, rf = exact_fallback(scanner, st, qs, k, over_h)
+        s[over_h], r[over_h] = sf, rf
+    return s, r
 
 
 class B200FlatIndex:
@@ -133,7 +158,7 @@ class B200FlatIndex:
         self._scanner = Scanner(self.device)
         self._lock = threading.RLock()
         self.search_times: List[float] = []
-        self.stats = {"two_stage_queries": 0, "uncertified_queries": 0}
+        self.stats = {"two_stage_queries": 0, "uncertified_queries": 0}   # uncertified ones are resolved by the collect pass
 
     # ------------------------------------------------------------------ attribute surface
     @property
@@ -216,7 +241,7 @@ class B200FlatIndex:
                 if len(bad_h):
                     self.stats["uncertified_queries"] += len(bad_h)
                     idx = torch.from_numpy(bad_h).to(self.device)
-                    s2, r2 = exact_fallback(self._scanner, st, q, kk, idx)
+                    s2, r2 = resolve_uncertified(self._scanner, st, q, kk, idx, s)
                     s_h[bad_h], r_h[bad_h] = s2.cpu().numpy(), r2.cpu().numpy()
             return s_h, r_h
 
