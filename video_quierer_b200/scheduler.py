@@ -49,6 +49,18 @@ class BatchSearchScheduler:
         hits = self.search_vectors(vecs, k)
         return [{"query": q, "results": res, "count": len(res)} for q, res in zip(queries, hits)]
 
+    def single_response(self, query: str, k: int = 5, use_cache: bool = True) -> dict:
+        """Full JSON body of POST /api/search (routes.py:589-613): blank query -> ValueError (the handler
+        answers 400), `from_cache` echoes the request flag like the reference does."""
+        import uuid
+        query = query.strip()
+        if not query:
+            raise ValueError("No query provided")
+        t0 = time.time()
+        results = self.search_batch([query], k)[0]["results"]
+        return {"results": results, "search_time_ms": (time.time() - t0) * 1000, "from_cache": use_cache,
+                "query_id": str(uuid.uuid4()), "performance": {"results_count": len(results)}}
+
     def batch_response(self, queries: Sequence[str], k: int = 5) -> dict:
         """Full JSON body of the handler (routes.py:636-640)."""
         results = self.search_batch(queries, k)
