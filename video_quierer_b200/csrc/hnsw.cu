@@ -21,6 +21,8 @@
 // Here a layer is built in three data-parallel steps: exact k-nearest members of every member
 // (the fused scan + top-k kernels), reverse edges appended with atomics, and every list pruned
 // back to the closest m (the batch analogue of :197-223, "closest M" selection of :123-148).
+#include <stdlib.h>
+
 #include "vq_common.cuh"
 
 int vq_scan_fma_grid(int n, int bt);
@@ -82,6 +84,78 @@ __device__ __forceinline__ int list_insert_asc(float* d, int* id, int cnt, int c
     return ncnt;
 }
 
+
+// The same list held in REGISTERS, striped over the warp: entry i lives in lane i % 32, slot i / 32
+// (S slots per lane, capacity 32*S >= ef).  An insertion is S ballots to find the position and one
+// shuffle-shift per slot instead of a shared-memory shift loop with two warp barriers per 32 entries
+// (~5x fewer cycles at ef = 256, where the list work had grown as large as the row gathers).
+template <int S>
+struct RegList {
+    float d[S];
+    int id[S];
+    __device__ __forceinline__ void clear() {
+#pragma unroll
+        for (int s = 0; s < S; ++s) { d[s] = INFINITY; id[s] = -1; }
+    }
+    // value of entry `idx` (warp-uniform idx), broadcast to all lanes
+    __device__ __forceinline__ float dist_at(int idx) const {
+        float v = d[0];
+#pragma unroll
+        for (int s = 1; s < S; ++s) v = (idx >> 5) == s ? d[s] : v;
+        return __shfl_sync(kFull, v, idx & 31);
+    }
+    __device__ __forceinline__ int id_at(int idx) const {
+        int v = id[0];
+#pragma unroll
+        for (int s = 1; s < S; ++s) v = (idx >> 5) == s ? id[s] : v;
+        return __shfl_sync(kFull, v, idx & 31);
+    }
+    __device__ __forceinline__ void mark_expanded(int idx, int lane) {
+#pragma unroll
+        for (int s = 0; s < S; ++s)
+            if ((idx >> 5) == s && (idx & 31) == lane) id[s] |= kExpanded;
+    }
+    // first entry (< cnt) without the expanded flag, -1 if none
+    __device__ __forceinline__ int first_open(int cnt, int lane) const {
+        int pos = -1;
+#pragma unroll
+        for (int s = 0; s < S; ++s) {
+            const int i = s * 32 + lane;
+            const unsigned mk = __ballot_sync(kFull, i < cnt && !(id[s] & kExpanded));
+            if (pos < 0 && mk) pos = s * 32 + __ffs(mk) - 1;
+        }
+        return pos;
+    }
+    // ascending (distance, id) insert bounded by cap; returns the new count
+    __device__ __forceinline__ int insert(int cnt, int cap, float cd, int cid, int lane) {
+        int pos = 0;
+#pragma unroll
+        for (int s = 0; s < S; ++s) {
+            const int i = s * 32 + lane;
+            const int eid = id[s] & ~kExpanded;
+            const bool b = i < cnt && ((d[s] < cd) || (d[s] == cd && eid < cid));
+            pos += __popc(__ballot_sync(kFull, b));
+        }
+        if (pos >= cap) return cnt;
+        const int ncnt = cnt < cap ? cnt + 1 : cap;
+        float carry_d = 0.f; int carry_i = 0;              // lane 31 of the previous slot
+#pragma unroll
+        for (int s = 0; s < S; ++s) {
+            const float up_d = __shfl_up_sync(kFull, d[s], 1);
+            const int up_i = __shfl_up_sync(kFull, id[s], 1);
+            const float last_d = __shfl_sync(kFull, d[s], 31);
+            const int last_i = __shfl_sync(kFull, id[s], 31);
+            const float sh_d = lane == 0 ? carry_d : up_d;    // the entry that sat one index below
+            const int sh_i = lane == 0 ? carry_i : up_i;
+            const int i = s * 32 + lane;
+            if (i == pos) { d[s] = cd; id[s] = cid; }
+            else if (i > pos && i < ncnt) { d[s] = sh_d; id[s] = sh_i; }
+            carry_d = last_d; carry_i = last_i;
+        }
+        return ncnt;
+    }
+};
+
 template <bool BF16>
 __device__ __forceinline__ float row_dot_8lanes(const unsigned char* row, const float* q, int ld, int l8) {
     // 8 lanes cooperate on one row; lane l8 takes the 16-byte pieces l8, l8+8, ...
@@ -121,7 +195,7 @@ __device__ __forceinline__ float row_dot_8lanes(const unsigned char* row, const 
     return acc;
 }
 
-template <bool BF16>
+template <bool BF16, int S>        // S > 0: result list in registers (ef <= 32*S); S == 0: in shared memory
 __global__ void __launch_bounds__(128)
 hnsw_search_kernel(const void* __restrict__ store_v, int ld,
                    const int* __restrict__ adj0, int m0,
@@ -156,6 +230,8 @@ hnsw_search_kernel(const void* __restrict__ store_v, int ld,
     __syncwarp();
 
     unsigned evals = 0, hops = 0, overflow = 0;
+    RegList<(S > 0 ? S : 1)> rl;
+    rl.clear();
     int visited_cnt = 0;            // entries currently in the hash (all lanes hold the same value)
     int logged = 0;                 // slots recorded in the log (== visited_cnt while <= kLogCap)
 
@@ -193,8 +269,12 @@ hnsw_search_kernel(const void* __restrict__ store_v, int ld,
         }
         visited_cnt = 0; logged = 0;
         int cnt = 1;
+        if (S > 0) {
+            rl.clear();
+            if (lane == 0) { rl.d[0] = cur_d; rl.id[0] = cur; }
+        }
         if (lane == 0) {
-            w.ld_[0] = cur_d; w.li[0] = cur;
+            if (S == 0) { w.ld_[0] = cur_d; w.li[0] = cur; }
             int s; visit(cur, s);
             w.log[0] = (unsigned short)s;
         }
@@ -204,15 +284,23 @@ hnsw_search_kernel(const void* __restrict__ store_v, int ld,
         for (;;) {
             // first unexpanded entry of the list = closest open candidate
             int pos = -1;
-            for (int base0 = 0; base0 < cnt && pos < 0; base0 += 32) {
-                const int i = base0 + lane;
-                const unsigned mk = __ballot_sync(kFull, i < cnt && !(w.li[i] & kExpanded));
-                if (mk) pos = base0 + __ffs(mk) - 1;
+            int u;
+            if (S > 0) {
+                pos = rl.first_open(cnt, lane);
+                if (pos < 0) break;
+                u = rl.id_at(pos);
+                rl.mark_expanded(pos, lane);
+            } else {
+                for (int base0 = 0; base0 < cnt && pos < 0; base0 += 32) {
+                    const int i = base0 + lane;
+                    const unsigned mk = __ballot_sync(kFull, i < cnt && !(w.li[i] & kExpanded));
+                    if (mk) pos = base0 + __ffs(mk) - 1;
+                }
+                if (pos < 0) break;
+                u = w.li[pos];
+                __syncwarp();
+                if (lane == 0) w.li[pos] = u | kExpanded;
             }
-            if (pos < 0) break;
-            const int u = w.li[pos];
-            __syncwarp();
-            if (lane == 0) w.li[pos] = u | kExpanded;
             hops += 1;
             const int* arow = lv == 0 ? adj0 + (size_t)u * m0
                                       : upper_adj + ((size_t)upper_off[u] + lv - 1) * m;
@@ -242,15 +330,43 @@ hnsw_search_kernel(const void* __restrict__ store_v, int ld,
                 evals += nnew;
                 __syncwarp();
                 // admit in neighbour order (hnsw.py:113): not full, or strictly better than the worst kept
-                for (int i = 0; i < nnew; ++i) {
-                    const float d = w.nd[i];
-                    const int node = w.nbr[i];
-                    const bool admit = (cnt < ef_l) || (d < w.ld_[ef_l - 1]);
-                    if (admit) cnt = list_insert_asc(w.ld_, w.li, cnt, ef_l, d, node, lane);
+                if (S > 0) {
+                    float worst = rl.dist_at(ef_l - 1);
+                    for (int i = 0; i < nnew; ++i) {
+                        const float d = w.nd[i];
+                        const int node = w.nbr[i];
+                        if ((cnt < ef_l) || (d < worst)) {
+                            cnt = rl.insert(cnt, ef_l, d, node, lane);
+                            worst = rl.dist_at(ef_l - 1);
+                        }
+                    }
+                } else {
+                    for (int i = 0; i < nnew; ++i) {
+                        const float d = w.nd[i];
+                        const int node = w.nbr[i];
+                        const bool admit = (cnt < ef_l) || (d < w.ld_[ef_l - 1]);
+                        if (admit) cnt = list_insert_asc(w.ld_, w.li, cnt, ef_l, d, node, lane);
+                    }
                 }
                 __syncwarp();
             }
         }
+        if (S > 0) {
+            cur = rl.id_at(0) & ~kExpanded;
+            cur_d = rl.dist_at(0);
+            if (lv == 0) {
+#pragma unroll
+                for (int s2 = 0; s2 < S; ++s2) {
+                    const int i = s2 * 32 + lane;
+                    if (i < k) {
+                        const bool ok = i < cnt;
+                        out_dist[(size_t)qi * k + i] = ok ? rl.d[s2] : INFINITY;
+                        out_rows[(size_t)qi * k + i] = ok ? (rl.id[s2] & ~kExpanded) : -1;
+                    }
+                }
+                for (int i = S * 32 + lane; i < k; i += 32) { out_dist[(size_t)qi * k + i] = INFINITY; out_rows[(size_t)qi * k + i] = -1; }
+            }
+        } else {
         cur = w.li[0] & ~kExpanded;
         cur_d = w.ld_[0];
         if (lv == 0) {
@@ -259,6 +375,7 @@ hnsw_search_kernel(const void* __restrict__ store_v, int ld,
                 out_dist[(size_t)qi * k + i] = ok ? w.ld_[i] : INFINITY;
                 out_rows[(size_t)qi * k + i] = ok ? (w.li[i] & ~kExpanded) : -1;
             }
+        }
         }
         __syncwarp();
     }
@@ -557,17 +674,24 @@ int vq_hnsw_search(const void* store, int64_t n, int dim, int ld, int store_dtyp
     }
     const int grid = (b + p.warps - 1) / p.warps;
     vq_prof_begin(stream);
+    // result list in registers (32*S entries striped over the warp) up to ef = 256, in shared memory beyond
+    static const bool reg_list = getenv("VQ_HNSW_REGLIST") ? atoi(getenv("VQ_HNSW_REGLIST")) != 0 : true;
+    const int slots = !reg_list ? 0 : ef <= 64 ? 2 : ef <= 128 ? 4 : ef <= 256 ? 8 : 0;
+#define VQ_HNSW_LAUNCH(BF, SL)                                                                                          \
+    do {                                                                                                                \
+        VQ_CUDA(cudaFuncSetAttribute(hnsw_search_kernel<BF, SL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); \
+        hnsw_search_kernel<BF, SL><<<grid, p.warps * 32, p.smem, stream>>>(store, ld, adj0, m0, upper_off, upper_adj, m, entry, \
+                                                                          max_level, ef, p.cap, qn, b, k, out_dist, out_rows, \
+                                                                          out_stats, p.warp_bytes);                     \
+    } while (0)
     if (store_dtype == VQ_BF16) {
-        VQ_CUDA(cudaFuncSetAttribute(hnsw_search_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        hnsw_search_kernel<true><<<grid, p.warps * 32, p.smem, stream>>>(store, ld, adj0, m0, upper_off, upper_adj, m, entry,
-                                                                       max_level, ef, p.cap, qn, b, k, out_dist, out_rows,
-                                                                       out_stats, p.warp_bytes);
+        if (slots == 2) VQ_HNSW_LAUNCH(true, 2); else if (slots == 4) VQ_HNSW_LAUNCH(true, 4);
+        else if (slots == 8) VQ_HNSW_LAUNCH(true, 8); else VQ_HNSW_LAUNCH(true, 0);
     } else {
-        VQ_CUDA(cudaFuncSetAttribute(hnsw_search_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        hnsw_search_kernel<false><<<grid, p.warps * 32, p.smem, stream>>>(store, ld, adj0, m0, upper_off, upper_adj, m, entry,
-                                                                        max_level, ef, p.cap, qn, b, k, out_dist, out_rows,
-                                                                        out_stats, p.warp_bytes);
+        if (slots == 2) VQ_HNSW_LAUNCH(false, 2); else if (slots == 4) VQ_HNSW_LAUNCH(false, 4);
+        else if (slots == 8) VQ_HNSW_LAUNCH(false, 8); else VQ_HNSW_LAUNCH(false, 0);
     }
+#undef VQ_HNSW_LAUNCH
     vq_prof_end(stream);
     VQ_LAUNCH_CHECK("hnsw_search_kernel");
     vq_note_launch(store_dtype == VQ_BF16 ? "hnsw_search_bf16" : "hnsw_search_f32", 2);
