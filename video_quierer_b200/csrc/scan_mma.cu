@@ -193,7 +193,14 @@ __device__ __forceinline__ void tmem_ld_wait(uint32_t (&v)[32]) {
 template <int KL>
 __device__ __forceinline__ void filter_insert(const uint32_t (&v)[32], int row_base, int left, float g_keep, float& thr,
                                               float (&ls)[KL], int (&lr)[KL]) {
-    // branch-free filter (a stale threshold only lets more through; re-checked below)
+    // Once the lists are warm almost no chunk holds a candidate: one max-reduction (3-input max, ~16
+    // instructions) decides that, the per-score mask (64 instructions) is built only for the rare chunk
+    // that passes.  A stale threshold only lets more through; every candidate is re-checked below.
+    float m = __uint_as_float(v[0]);
+#pragma unroll
+    for (int j = 1; j + 1 < 32; j += 2) m = fmaxf(fmaxf(m, __uint_as_float(v[j])), __uint_as_float(v[j + 1]));
+    m = fmaxf(m, __uint_as_float(v[31]));
+    if (!(m > thr)) return;
     unsigned mask = 0;
 #pragma unroll
     for (int j = 0; j < 32; ++j) mask |= (__uint_as_float(v[j]) > thr) ? (1u << j) : 0u;
