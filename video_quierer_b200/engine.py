@@ -122,6 +122,46 @@ class DeviceStore:
                                                    norm, st), "vq_ingest_rows")
         self.n += m
 
+    # ------------------------------------------------------------------ raw persistence (rawstore.py)
+    def save_raw_arrays(self, writer):
+        """Chunked device-to-host copies of the [n, ld] matrices into the writer's memmaps."""
+        from . import rawstore
+        for name, t, dt, item in (("rows_f32", self.f32, "float32", 4), ("rows_bf16", self.bf16, "uint16", 2)):
+            if t is None:
+                continue
+            dst = writer.create(name, dt, (self.n, self.ld))
+            for lo, hi in rawstore.chunks(self.n, self.ld * item):
+                chunk = t[lo:hi]
+                if dt == "uint16":
+                    dst[lo:hi] = chunk.view(torch.int16).cpu().numpy().view(np.uint16)
+                else:
+                    dst[lo:hi] = chunk.cpu().numpy()
+
+    @classmethod
+    def from_raw_arrays(cls, dim: int, arrays, device=None):
+        """Rebuild a store from `rows_f32` / `rows_bf16` memmaps: chunked host-to-device copies straight
+        into the device matrices (rows are stored exactly as they sat in HBM: no ingest kernel)."""
+        from . import rawstore
+        f, b = arrays.get("rows_f32"), arrays.get("rows_bf16")
+        ref = f if f is not None else b
+        if ref is None:
+            raise ValueError("raw store holds neither rows_f32 nor rows_bf16")
+        n, ld = int(ref.shape[0]), int(ref.shape[1])
+        st = cls(dim, device, keep_fp32=f is not None, keep_bf16=b is not None, capacity=n)
+        if ld != st.ld:
+            raise ValueError(f"raw store row stride {ld} != {st.ld} expected for dimension {dim}")
+        for src, dst, item in ((f, st.f32, 4), (b, st.bf16, 2)):
+            if src is None:
+                continue
+            for lo, hi in rawstore.chunks(n, ld * item):
+                host = np.array(src[lo:hi])               # private writable copy of the read-only memmap slice
+                if item == 2:
+                    dst[lo:hi].view(torch.int16).copy_(torch.from_numpy(host.view(np.int16)))
+                else:
+                    dst[lo:hi].copy_(torch.from_numpy(host))
+        st.n = n
+        return st
+
     def truncate(self, n: int):
         self.n = min(self.n, max(0, int(n)))
 

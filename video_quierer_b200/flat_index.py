@@ -83,6 +83,51 @@ class EmbeddingList(list):
     # append / extend only add rows past valid_prefix → nothing to record
 
 
+class LazyRows:
+    """`embeddings` of an index loaded from a raw store: the rows stay in the memmap / on the device
+    instead of becoming one Python object each (hopeless at 100M rows).  Reads (`len`, indexing,
+    iteration, truthiness) work; `append` / `extend` work (new rows live in `tail` and are uploaded
+    incrementally); removing or replacing one of the stored rows needs the list form: call
+    `B200FlatIndex.materialise()` first (fine up to a few million rows)."""
+
+    def __init__(self, rows_f32, rows_bf16, dim: int):
+        self._f32, self._bf16, self._dim = rows_f32, rows_bf16, int(dim)
+        self.base_n = int((rows_f32 if rows_f32 is not None else rows_bf16).shape[0])
+        self.tail = EmbeddingList()
+
+    def __len__(self):
+        return self.base_n + len(self.tail)
+
+    def __bool__(self):
+        return len(self) > 0
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            return [self[j] for j in range(*i.indices(len(self)))]
+        if i < 0:
+            i += len(self)
+        if i >= self.base_n:
+            return self.tail[i - self.base_n]
+        if self._f32 is not None:
+            return np.array(self._f32[i, : self._dim])
+        return (self._bf16[i, : self._dim].astype(np.uint32) << 16).view(np.float32)      # widen bf16 exactly
+
+    def __iter__(self):
+        for i in range(len(self)):
+            yield self[i]
+
+    def append(self, v):
+        self.tail.append(v)
+
+    def extend(self, vs):
+        self.tail.extend(vs)
+
+    def _frozen(self, *a, **k):
+        raise NotImplementedError("rows of a raw-loaded store are immutable; call index.materialise() to get the "
+                                  "reference's mutable list form")
+    pop = __delitem__ = __setitem__ = insert = remove = clear = sort = reverse = _frozen
+
+
 # Worst-case |bf16-operand score - fp32 score| for unit-norm rows and queries: each operand is
 # rounded to 8 significant bits (relative 2^-9), products are exact, so
 # |delta| <= (2*2^-9 + 2^-18) * sum|q_i x_i| <= 2^-8 * |q| |x|  (Cauchy-Schwarz) plus fp32 accumulation noise.
@@ -169,6 +214,9 @@ class B200FlatIndex:
     def embeddings(self, value):
         # handlers rebind the attribute: `system.index.embeddings = []` (routes.py:979,1014)
         with self._lock:
+            if isinstance(value, LazyRows):
+                self._embeddings = value
+                return
             self._embeddings = value if isinstance(value, EmbeddingList) else EmbeddingList(value)
             self._embeddings.valid_prefix = 0
 
@@ -192,6 +240,16 @@ class B200FlatIndex:
 
     def _sync(self):
         emb = self._embeddings
+        if isinstance(emb, LazyRows):            # stored rows are already on the device; only the tail moves
+            st, tail = self._store, emb.tail
+            keep = min(tail.valid_prefix, st.n - emb.base_n, len(tail))
+            if keep == len(tail) and st.n == len(emb):
+                return
+            st.truncate(emb.base_n + keep)
+            for s0 in range(keep, len(tail), 1 << 16):
+                st.append(np.stack(tail[s0: s0 + (1 << 16)]).astype(np.float32, copy=False), _lib.NORM_NONE)
+            tail.valid_prefix = len(tail)
+            return
         n = len(emb)
         if n == 0:
             if self._store is not None:
@@ -310,6 +368,44 @@ class B200FlatIndex:
         except Exception as e:  # noqa: BLE001 — (:104-106)
             logger.error("Failed to load cache: %s", e)
             return False
+
+    # ------------------------------------------------------------------ raw persistence
+    def save_raw(self, path) -> bool:
+        """Write the device matrices as they are + metadata to a raw store directory (rawstore.py)."""
+        from . import rawstore
+        with self._lock:
+            self._sync()
+            if self._store is None or self._store.n == 0:
+                raise ValueError("nothing to save: the index is empty")
+            st = self._store
+            w = rawstore.RawWriter(str(path), "flat", {"n": st.n, "dim": st.dim, "ld": st.ld,
+                                                      "store_dtype": self.store_dtype, "rescore": self.rescore})
+            st.save_raw_arrays(w)
+            w.put_objects({"metadata": self.metadata, "video_hashes": self.video_hashes})
+            w.close()
+        return True
+
+    def load_raw(self, path, verify: bool = True) -> bool:
+        """Load a raw store: memmap + chunked copies into the device matrix; `embeddings` becomes a
+        `LazyRows` view (no per-row Python objects).  Raises ValueError on a damaged store."""
+        from . import rawstore
+        attrs, arrays, objects = rawstore.open_raw(str(path), "flat", verify)
+        with self._lock:
+            self.store_dtype = attrs["store_dtype"]
+            self.rescore = bool(attrs["rescore"])
+            self._store = DeviceStore.from_raw_arrays(int(attrs["dim"]), arrays, self.device)
+            self._embeddings = LazyRows(arrays.get("rows_f32"), arrays.get("rows_bf16"), int(attrs["dim"]))
+            self.metadata = objects["metadata"]
+            self.video_hashes = objects["video_hashes"]
+        return True
+
+    def materialise(self):
+        """Turn a raw-loaded index back into the reference's list form (one array per frame)."""
+        with self._lock:
+            if isinstance(self._embeddings, LazyRows):
+                rows = EmbeddingList(list(self._embeddings))
+                self._embeddings = rows
+                self._embeddings.valid_prefix = len(rows) if self._store is not None and self._store.n == len(rows) else 0
 
     # ------------------------------------------------------------------ introspection
     @property

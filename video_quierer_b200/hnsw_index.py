@@ -410,6 +410,50 @@ class B200HNSWIndex:
             self._entry_row = self._row_of[self.entry_point]
             self._graph = self._graph_from_dicts(graph)
 
+    # ------------------------------------------------------------------ raw persistence
+    def save_raw(self, path) -> None:
+        """Vectors and graph exactly as they sit in HBM (+ ids / parameters); see rawstore.py.  The
+        pickle of `save()` stays the interchange format with the reference; this one scales."""
+        from . import rawstore
+        with self.lock:
+            self._ensure_graph()
+            if self._graph is None:
+                raise ValueError("nothing to save: the index is empty")
+            if self._store.n > self._graph.n:
+                self.build()                       # fold the delta rows into the graph first
+            g, st = self._graph, self._store
+            w = rawstore.RawWriter(str(path), "hnsw", {
+                "dimension": self.dimension, "M": self.M, "max_M": self.max_M, "ef_construction": self.ef_construction,
+                "ef_search": self.ef_search, "level_generation_factor": self.level_generation_factor,
+                "search_dtype": self.search_dtype, "n": st.n, "entry_row": g.entry, "max_level": g.max_level,
+                "element_count": self.element_count})
+            st.save_raw_arrays(w)
+            for name, t in (("levels", g.levels), ("adj0", g.adj0), ("upper_off", g.upper_off), ("upper_adj", g.upper_adj)):
+                w.put(name, t.cpu().numpy().astype(np.int32))
+            w.put_objects({"ids": self._ids, "dead": sorted(self._dead)})
+            w.close()
+
+    def load_raw(self, path, verify: bool = True) -> None:
+        from . import rawstore
+        attrs, arrays, objects = rawstore.open_raw(str(path), "hnsw", verify)
+        with self.lock:
+            for key in ("dimension", "M", "max_M", "ef_construction", "ef_search", "level_generation_factor", "search_dtype",
+                        "element_count"):
+                setattr(self, key, attrs[key])
+            self._store = DeviceStore.from_raw_arrays(self.dimension, arrays, self.device)
+            self._ids = list(objects["ids"])
+            self._row_of = {nid: r for r, nid in enumerate(self._ids)}
+            self._dead = set(objects["dead"])
+            lv = np.asarray(arrays["levels"])
+            self._level_list = [int(x) for x in lv]
+            self.levels = {nid: l for nid, l in zip(self._ids, self._level_list)}
+            self._pending = []
+            self._entry_row = int(attrs["entry_row"])
+            self.entry_point = self._ids[self._entry_row]
+            self._graph = DeviceGraph.from_numpy(lv, np.asarray(arrays["adj0"]), np.asarray(arrays["upper_off"]),
+                                                 np.asarray(arrays["upper_adj"]), self._entry_row, int(attrs["max_level"]),
+                                                 self.device)
+
     def _graph_from_dicts(self, graph) -> DeviceGraph:
         n = len(self._ids)
         lv_np = np.asarray(self._level_list, dtype=np.int32)
