@@ -306,3 +306,46 @@ def test_two_stage_k50_uses_tensor_path(eng, gen):
     ro, so = exact.exact_search_batch(store, queries, k)
     assert compare.check_topk_batch(r, s, ro, so) == []
     assert idx.last_scan_path.startswith("scan_mma_bf16")        # two-stage or collect, never scan_fma
+
+
+def test_query_similarity_cache_probe_matches_reference_semantics(eng):
+    """B200QueryResultCache vs a straight restatement of the reference loop (cache.py:447-478)."""
+    from video_quierer_b200.query_cache import B200QueryResultCache
+
+    class DictCache:
+        def __init__(self): self.d = {}
+        def get(self, k): return self.d.get(k)
+        def put(self, k, v, ttl=None): self.d[k] = v; return True
+        def clear(self): self.d.clear()
+
+    rng = np.random.default_rng(71)
+    base = synth.gauss(300, 512, seed=70)
+    qc = B200QueryResultCache(DictCache(), similarity_threshold=0.95)
+    for i, v in enumerate(base):
+        qc.cache_results(v, 5, [{"video_id": f"v{i}"}])
+    qc.cache_results(base[7], 10, [{"video_id": "k10"}])                       # another k: separate pool
+    assert qc.get_cached_results(base[3], 5) == [{"video_id": "v3"}]           # exact key hit, no probe
+    assert qc.probes == 0
+    near = base[42] + 0.1 * rng.standard_normal(512).astype(np.float32) / np.sqrt(512)    # cosine ~0.995
+    far = base[42] + 0.6 * rng.standard_normal(512).astype(np.float32) / np.sqrt(512)     # cosine ~0.86
+    def ref_probe(q, k):
+        best, out = 0, None
+        for key, v in qc.query_vectors.items():
+            if not key.endswith(f":{k}"):
+                continue
+            sim = np.dot(q, v) / (np.linalg.norm(q) * np.linalg.norm(v))
+            if sim > 0.95 and sim > best and qc.cache.get(key) is not None:
+                best, out = sim, qc.cache.get(key)
+        return out
+    assert qc.get_cached_results(near * 3.0, 5) == ref_probe(near * 3.0, 5) == [{"video_id": "v42"}]
+    assert qc.get_cached_results(far, 5) is None and ref_probe(far, 5) is None
+    assert qc.get_cached_results(base[7] * 1.0001, 10) == [{"video_id": "k10"}]
+    assert qc.get_cached_results(near, 7) is None                              # no pool for k = 7
+    # best candidate evicted from the backing cache -> the next best above the threshold is used
+    twin = base[42] + 0.05 * rng.standard_normal(512).astype(np.float32) / np.sqrt(512)
+    qc.cache_results(twin, 5, [{"video_id": "twin"}])
+    key42 = [k for k, v in qc.query_vectors.items() if v is base[42] or np.array_equal(v, base[42])][0]
+    del qc.cache.d[key42]
+    assert qc.get_cached_results(near, 5) == ref_probe(near, 5) == [{"video_id": "twin"}]
+    qc.invalidate_results("v1")
+    assert qc.get_cached_results(near, 5) is None and qc.query_vectors == {}
