@@ -95,6 +95,21 @@ __device__ __forceinline__ void tma_load_2d_addr(uint32_t dst, const CUtensorMap
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
         ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
 }
+// multicast variants for a 2-CTA cluster that shares the store tiles (each CTA loads half a box and
+// writes it into both CTAs' shared memory; a released ring group is signalled to both CTAs)
+__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, uint16_t mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"(mask) : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 // one lane of the (converged) warp; always the same lane, so tcgen05.commit sees the MMAs it tracks
 __device__ __forceinline__ bool elect_one() {
     uint32_t pred;
@@ -237,7 +252,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 scan_mma_bf16_kernel(const __grid_constant__ CUtensorMap tmS,
                      const __nv_bfloat16* __restrict__ qbf,   // [b_pad, ld] normalised, zero padded
                      float* __restrict__ gtau,                // [b_pad] shared k-th best per query (-inf initialised)
-                     int n, int ld, int nkb, int n_qt, int k, int stages, int grp_log2, int b_pad,
+                     int n, int ld, int nkb, int n_qt, int k, int stages, int grp_log2, int cl, int b_pad,
                      float* __restrict__ cand_s,              // [b_pad, cap] surviving candidates (BOOT: [tiles, b_pad] maxima)
                      int* __restrict__ cand_r, int* __restrict__ cand_cnt, int cap, int dbg) {
     constexpr int B_KB_BYTES = NT * 128;
@@ -260,7 +275,7 @@ scan_mma_bf16_kernel(const __grid_constant__ CUtensorMap tmS,
 
     if (warp == 0 && lane == 0) tma_prefetch_desc(&tmS);
     if (warp == 1 && lane == 0) {
-        for (int s = 0; s < stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], kIssuers); }
+        for (int s = 0; s < stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], kIssuers * cl); }
         mbar_init(a_full, 4);
         for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], kIssuers); mbar_init(&tmem_empty[a], 4); mbar_init(&x_first[a], 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -271,9 +286,11 @@ scan_mma_bf16_kernel(const __grid_constant__ CUtensorMap tmS,
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     tc_fence_before();
-    __syncthreads();
+    if (cl > 1) cluster_sync_all(); else __syncthreads();     // the peer's barriers are live before anything lands on them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
+    const uint32_t cl_rank = cl > 1 ? cluster_ctarank() : 0u;
+    const uint16_t cl_mask = (uint16_t)((1u << cl) - 1u);
     // everything above touched no global memory: it overlaps the previous kernel of the stream (PDL)
     vq_pdl_wait();
     vq_pdl_trigger();
@@ -291,8 +308,12 @@ scan_mma_bf16_kernel(const __grid_constant__ CUtensorMap tmS,
                 if (elect_one()) {
                     if (dbg & 2) { mbar_arrive(&full[stage]); }
                     else {
-                        mbar_expect_tx(&full[stage], B_KB_BYTES);
-                        tma_load_2d_addr(sB_addr + (uint32_t)stage * B_KB_BYTES, &tmS, full_addr + (uint32_t)stage * 8, kb * KB_ELEMS, tile * NT);
+                        mbar_expect_tx(&full[stage], B_KB_BYTES);          // the whole box: own part + the peer's multicast
+                        if (cl > 1)
+                            tma_load_2d_mc(sB_addr + (uint32_t)stage * B_KB_BYTES + cl_rank * (B_KB_BYTES / 2), &tmS,
+                                           full_addr + (uint32_t)stage * 8, kb * KB_ELEMS, tile * NT + (int)cl_rank * (NT / 2), cl_mask);
+                        else
+                            tma_load_2d_addr(sB_addr + (uint32_t)stage * B_KB_BYTES, &tmS, full_addr + (uint32_t)stage * 8, kb * KB_ELEMS, tile * NT);
                     }
                 }
                 __syncwarp();
@@ -346,7 +367,7 @@ scan_mma_bf16_kernel(const __grid_constant__ CUtensorMap tmS,
                 const bool rel = (stage & grp_mask) == grp_mask, last = kb == nkb - 1;
                 if (rel || last) {
                     if (elect_one()) {
-                        if (rel) umma_commit(&empty[stage >> grp_log2]);
+                        if (rel) { if (cl > 1) umma_commit_mc(&empty[stage >> grp_log2], cl_mask); else umma_commit(&empty[stage >> grp_log2]); }
                         if (last) umma_commit(&tmem_full[acc]);
                     }
                     __syncwarp();
@@ -516,7 +537,7 @@ scan_mma_bf16_kernel(const __grid_constant__ CUtensorMap tmS,
         }
     }
     tc_fence_before();
-    __syncthreads();
+    if (cl > 1) cluster_sync_all(); else __syncthreads();     // no CTA leaves while its peer may still write into it
     if (warp == 2) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS) : "memory");
@@ -637,7 +658,7 @@ inline size_t align256(size_t v) { return (v + 255) / 256 * 256; }
 inline int pow2_ge(int v) { int p = 2; while (p < v) p <<= 1; return p; }
 
 struct MmaPlan {
-    int nkb, nt, n_qt, b_pad, groups, grid, stages, grp_log2;
+    int nkb, nt, n_qt, b_pad, groups, grid, stages, grp_log2, cl;
     int boot_tiles, boot_groups;                 // threshold bootstrap (0 = off)
     int cap;                                     // candidate slots per query (= groups * k, cannot overflow)
     size_t smem;
@@ -666,6 +687,10 @@ MmaPlan plan(int64_t n, int ld, int b, int k) {
     static const int grp_env = getenv("VQ_MMA_GROUP") ? atoi(getenv("VQ_MMA_GROUP")) : -1;
     p.grp_log2 = grp_env >= 0 ? grp_env : 2;
     p.stages = (st > 12 ? 12 : st) >> p.grp_log2 << p.grp_log2;
+    // an even number of query tiles: two CTAs with neighbouring query tiles form a cluster and share every
+    // store tile (each loads half a box and multicasts it), halving the L2 -> SM traffic per FLOP
+    static const int cl_env = getenv("VQ_MMA_CLUSTER") ? atoi(getenv("VQ_MMA_CLUSTER")) : 0;
+    p.cl = (cl_env == 2 && p.n_qt % 2 == 0) ? 2 : 1;
     // Bootstrap the per-query threshold from a sample of tiles when the scan is long enough to pay for two
     // extra (tiny) launches; the sample holds >= 4k tiles so that the k-th largest tile maximum is a strong
     // bound.  With several query tiles per store tile the list insertions dominate short scans as well
@@ -721,8 +746,9 @@ cudaError_t launch_mma(const MmaPlan& p, const CUtensorMap& tmS, const __nv_bflo
         attr_done = true;
     }
     const int grid = BOOT ? p.boot_groups * p.n_qt : p.grid;
-    return vq_launch(BOOT ? 1 : 3, kern, dim3(grid), dim3(kThreads), p.smem, stream, tmS, qbf, w.gtau, n, ld, p.nkb, p.n_qt, k, p.stages,
-                     p.grp_log2, p.b_pad, BOOT ? w.boot_max : w.cand_s, w.cand_r, w.cnt, p.cap, dbg);
+    const int cl = MODE == kModeList ? p.cl : 1;
+    return vq_launch_cluster(BOOT ? 1 : 3, cl, kern, dim3(grid), dim3(kThreads), p.smem, stream, tmS, qbf, w.gtau, n, ld, p.nkb, p.n_qt,
+                             k, p.stages, p.grp_log2, cl, p.b_pad, BOOT ? w.boot_max : w.cand_s, w.cand_r, w.cnt, p.cap, dbg);
 }
 
 // [boot pass ->] main pass; gtau / cnt must have been reset by the caller's prologue kernel.
@@ -753,15 +779,20 @@ int run_scan(const MmaPlan& p, const void* store, int64_t n, int ld, const __nv_
         }
         *launches = 3;
     }
+    CUtensorMap tmM = tmS;                       // main pass: half-height boxes when two CTAs share a tile
+    if (p.cl > 1 && !get_map_bf16(&tmM, store, (uint64_t)n, (uint64_t)ld, (uint32_t)(p.nt / p.cl))) {
+        vq_set_error("scan_mma: cuTensorMapEncodeTiled failed");
+        return VQ_ECUDA;
+    }
     vq_prof_begin(stream);
     if (p.nt == 128)
-        e = k <= 16 ? launch_mma<16, 128, kModeList>(p, tmS, qbf, w, (int)n, ld, k, dbg, stream)
-          : k <= 32 ? launch_mma<32, 128, kModeList>(p, tmS, qbf, w, (int)n, ld, k, dbg, stream)
-                    : launch_mma<64, 128, kModeList>(p, tmS, qbf, w, (int)n, ld, k, dbg, stream);
+        e = k <= 16 ? launch_mma<16, 128, kModeList>(p, tmM, qbf, w, (int)n, ld, k, dbg, stream)
+          : k <= 32 ? launch_mma<32, 128, kModeList>(p, tmM, qbf, w, (int)n, ld, k, dbg, stream)
+                    : launch_mma<64, 128, kModeList>(p, tmM, qbf, w, (int)n, ld, k, dbg, stream);
     else
-        e = k <= 16 ? launch_mma<16, 64, kModeList>(p, tmS, qbf, w, (int)n, ld, k, dbg, stream)
-          : k <= 32 ? launch_mma<32, 64, kModeList>(p, tmS, qbf, w, (int)n, ld, k, dbg, stream)
-                    : launch_mma<64, 64, kModeList>(p, tmS, qbf, w, (int)n, ld, k, dbg, stream);
+        e = k <= 16 ? launch_mma<16, 64, kModeList>(p, tmM, qbf, w, (int)n, ld, k, dbg, stream)
+          : k <= 32 ? launch_mma<32, 64, kModeList>(p, tmM, qbf, w, (int)n, ld, k, dbg, stream)
+                    : launch_mma<64, 64, kModeList>(p, tmM, qbf, w, (int)n, ld, k, dbg, stream);
     vq_prof_end(stream);
     if (e != cudaSuccess) {
         vq_set_error("launch of scan_mma_bf16_kernel failed: %s", cudaGetErrorString(e));

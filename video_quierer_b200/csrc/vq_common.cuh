@@ -50,18 +50,34 @@ int vq_pdl_mask();           // bit i set: kernels of PDL class i are launched w
 // chain).  What overlaps is the launch latency and the kernel's prologue (barrier init, TMEM
 // allocation, descriptor prefetch).  Without the attribute both device calls are no-ops.
 template <typename... KArgs, typename... Args>
-cudaError_t vq_launch(int pdl_class, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args) {
+cudaError_t vq_launch_cluster(int pdl_class, int cluster, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                              cudaStream_t stream, Args... args) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid;
     cfg.blockDim = block;
     cfg.dynamicSmemBytes = smem;
     cfg.stream = stream;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cudaLaunchAttribute at[2];
+    int na = 0;
+    if ((vq_pdl_mask() >> pdl_class) & 1) {
+        at[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[na].val.programmaticStreamSerializationAllowed = 1;
+        ++na;
+    }
+    if (cluster > 1) {                         // thread-block cluster of `cluster` consecutive CTAs along x
+        at[na].id = cudaLaunchAttributeClusterDimension;
+        at[na].val.clusterDim.x = (unsigned)cluster;
+        at[na].val.clusterDim.y = 1;
+        at[na].val.clusterDim.z = 1;
+        ++na;
+    }
     cfg.attrs = at;
-    cfg.numAttrs = ((vq_pdl_mask() >> pdl_class) & 1) ? 1 : 0;
+    cfg.numAttrs = na;
     return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+template <typename... KArgs, typename... Args>
+cudaError_t vq_launch(int pdl_class, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args) {
+    return vq_launch_cluster(pdl_class, 1, kernel, grid, block, smem, stream, args...);
 }
 #ifdef __CUDACC__
 __device__ __forceinline__ void vq_pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
