@@ -480,12 +480,17 @@ scan_mma_bf16_kernel(const __grid_constant__ CUtensorMap tmS,
         for (int i = 0; i < KL; ++i) { ls[i] = i < k ? VQ_NEG_INF : INFINITY; lr[i] = VQ_EMPTY_ROW; }
         float published = VQ_NEG_INF;
         int it = 0;
+        // k-th best any CTA has published for this query (or the bootstrap bound).  It is (re)loaded one
+        // tile ahead so that the L2 round trip never sits between an accumulator becoming ready and
+        // its first filter step; a bound that is one tile stale only lets a few more rows through.
+        float g_next = *reinterpret_cast<volatile float*>(gtau + q);
         for (int tile = group; tile < n_tiles; tile += n_groups, ++it) {
             const int acc = it & 1;
             const uint32_t acc_phase = (it >> 1) & 1;
-            // k-th best any CTA has published for this query (or the bootstrap bound); ties with it are
-            // kept (>=) so the (score desc, row asc) rule still sees every candidate it needs
-            const float g = *reinterpret_cast<volatile float*>(gtau + q);
+            // ties with the bound are kept (>=) so the (score desc, row asc) rule still sees every
+            // candidate it needs
+            const float g = g_next;
+            g_next = *reinterpret_cast<volatile float*>(gtau + q);
             const float g_keep = (g == VQ_NEG_INF) ? g : nextafterf(g, VQ_NEG_INF);
             float thr = fmaxf(ls[0], g_keep);
             mbar_wait(&tmem_full[acc], acc_phase);
