@@ -136,7 +136,11 @@ int vq_search_two_stage(const void* store_bf16, const float* store_f32, int64_t 
  * are returned.  With thresholds[q] = s_k - score_eps, s_k being any lower bound of the exact k-th best
  * score (e.g. the k-th score vq_search_two_stage returned), every row of the exact top-k is gathered:
  * its exact score is >= s_k, so its bf16-operand score is >= s_k - score_eps.
- *   thresholds   [b] fp32 (device);  cap: candidate slots per query (k <= cap <= 16384)
+ *   thresholds   [b] fp32 (device), or NULL: derived from the store itself (the k-th largest per-tile
+ *                maximum of up to 256 sample tiles, reached by k distinct rows, k <= 256) — at least k
+ *                rows are gathered, and the k-th exact score returned is a lower bound of the k-th best of
+ *                any store containing these rows (step 1 of the large-k search);
+ *   cap          candidate slots per query (k <= cap <= 16384), k <= 1024
  *   out_overflow [b] int32: 1 = more than cap rows reached the threshold, the result is incomplete
  *                (re-run that query with vq_scan_topk on the fp32 store). [kernels: scan_mma_bf16<collect>, scan_finish] */
 size_t vq_search_collect_workspace_bytes(int64_t n, int dim, int ld, int b, int cap);

@@ -349,3 +349,20 @@ def test_query_similarity_cache_probe_matches_reference_semantics(eng):
     assert qc.get_cached_results(near, 5) == ref_probe(near, 5) == [{"video_id": "twin"}]
     qc.invalidate_results("v1")
     assert qc.get_cached_results(near, 5) is None and qc.query_vectors == {}
+
+
+@pytest.mark.parametrize("gen,n,dim,k", [("gauss", 120000, 768, 100), ("clip", 90000, 512, 100), ("gauss", 120000, 256, 200)])
+def test_large_k_sampled_collect_is_exact(eng, gen, n, dim, k):
+    """k beyond the register lists (BASELINE config 4: k = 100, dim 768): sampled fp32 bound + one
+    tensor-core collect pass + fp32 re-score of everything gathered == the oracle."""
+    engine, _lib, torch = eng
+    from video_quierer_b200.flat_index import two_stage_search
+    store = synth.gauss(n, dim, seed=91) if gen == "gauss" else synth.clip_like(n, dim, seed=91)
+    q = synth.gauss(12, dim, seed=92) if gen == "gauss" else synth.clip_like(12, dim, seed=92, n_store=n)
+    st = engine.DeviceStore(dim, keep_fp32=True, keep_bf16=True)
+    st.append(store)
+    sc = engine.Scanner()
+    s, r, bad = two_stage_search(sc, st, engine.as_device_queries(q, dim, st.device), k)
+    assert bad is None and sc.last_path.startswith("scan_mma_bf16<collect>")
+    ro, so = exact.exact_search_batch(store, q, k)
+    assert compare.check_topk_batch(r.cpu().numpy(), s.cpu().numpy(), ro, so) == []

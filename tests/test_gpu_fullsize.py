@@ -123,7 +123,7 @@ def test_config4_10m_x_768_k100_shards(eng):
     n, dim, b, k = 10_000_000, 768, 4, 100
     q = _queries(eng, b, dim, seed=6)
     planted = {0: q[0], 4_999_999: q[1], 9_999_999: q[2]}
-    st = _fill_store(eng, n, dim, True, False, planted, seed=2000)
+    st = _fill_store(eng, n, dim, True, True, planted, seed=2000)
     sc = engine.Scanner()
     s, r = sc.scan(st.f32, st.n, dim, q, k, _lib.NORM_EPS, "auto")
     torch.cuda.synchronize()
@@ -143,6 +143,11 @@ def test_config4_10m_x_768_k100_shards(eng):
         ms, mr = _sharded(eng, lambda lo, hi: sc.scan(st.f32[lo:hi], hi - lo, dim, q, k, _lib.NORM_EPS, "auto"), n, g, b, k)
         assert np.array_equal(mr.cpu().numpy(), r_h.astype(np.int64)), g
         assert np.array_equal(ms.cpu().numpy(), s_h), g
+    # the tensor-core route for k > 64 (sampled fp32 bound + collect pass + fp32 re-score) agrees with the fp32 scan
+    from video_quierer_b200.flat_index import two_stage_search
+    s3, r3, _ = two_stage_search(sc, st, q, k)
+    assert sc.last_path.startswith("scan_mma_bf16<collect>")
+    assert compare.check_topk_batch(r3.cpu().numpy(), s3.cpu().numpy(), r_h, s_h) == []
 
 
 def test_config5_100m_x_512_bf16_batch_4096(eng):

@@ -18,6 +18,9 @@ int vq_ingest_launch(const float* src, long long rows, int dim, int src_ld, void
                      int dst_ld, int mode, cudaStream_t stream);
 int vq_rescore_launch(const float* store, int ld, const float* queries, int qld, const int* cand, int b,
                       int k_cand, float* out_scores, cudaStream_t stream);
+bool vq_scan_finish_lists_supported(int g, int k_in, int k_out);
+int vq_scan_finish_lists_launch(const float* scores, const int* rows, int g, long long g_stride, int b, int k_in, int k_out,
+                                float* out_scores, int* out_rows, cudaStream_t stream);
 // tcgen05 path (scan_mma.cu)
 bool vq_scan_mma_supported(int64_t n, int dim, int ld, int store_dtype, int b, int k);
 size_t vq_scan_mma_workspace(int64_t n, int ld, int store_dtype, int b, int k);
@@ -104,6 +107,9 @@ static ScanPlan fma_plan(int64_t n, int ld, int b, int k, int force_bt) {
     // shrink the tile until its shared memory fits
     while (p.bt > 1 && vq_scan_fma_smem(p.bt, ld, k) > 200 * 1024) p.bt >>= 1;
     p.grid = vq_scan_fma_grid((int)n, p.bt);
+    // the per-CTA lists are reduced by scan_finish (bisection select, one CTA per query) when they fit its
+    // shared-memory key pool; for large k the grid is trimmed to make them fit (never below 128 CTAs)
+    if ((long long)p.grid * k > 16384 && 16384 / k >= 128) p.grid = 16384 / k;
     const int b_pad = (int)align_up((size_t)b, (size_t)p.bt);
     p.q_bytes = align_up((size_t)b_pad * ld * 4, 256);
     p.part_bytes = align_up((size_t)p.grid * p.bt * k * 4, 256);
@@ -222,13 +228,18 @@ int vq_scan_topk(const void* store, int64_t n, int dim, int ld, int store_dtype,
         int bt = p.bt;
         const int left = b - q0;
         if (left < bt) bt = pow2_at_least(left);            // padded queries are all-zero rows of qn
-        const int grid = vq_scan_fma_grid((int)n, bt);
+        int grid = vq_scan_fma_grid((int)n, bt);
+        if (grid > p.grid) grid = p.grid;
         if (q0 == 0) vq_prof_begin(stream);
         rc = vq_scan_fma_launch(store, (int)n, ld, store_dtype, qn + (size_t)q0 * ld, bt, k, part_s, part_r, grid, stream);
         if (q0 == 0) vq_prof_end(stream);
         if (rc) return rc;
-        rc = vq_topk_merge_launch(part_s, part_r, grid, (long long)bt * k, left < bt ? left : bt, k, nullptr, k,
-                                  out_scores + (size_t)q0 * k, out_rows + (size_t)q0 * k, 0, 0, stream);
+        if (vq_scan_finish_lists_supported(grid, k, k))
+            rc = vq_scan_finish_lists_launch(part_s, part_r, grid, (long long)bt * k, left < bt ? left : bt, k, k,
+                                             out_scores + (size_t)q0 * k, out_rows + (size_t)q0 * k, stream);
+        else
+            rc = vq_topk_merge_launch(part_s, part_r, grid, (long long)bt * k, left < bt ? left : bt, k, nullptr, k,
+                                      out_scores + (size_t)q0 * k, out_rows + (size_t)q0 * k, 0, 0, stream);
         if (rc) return rc;
         launches += 2;
     }
@@ -317,12 +328,12 @@ int vq_search_collect(const void* store_bf16, const float* store_f32, int64_t n,
     cudaStream_t stream = (cudaStream_t)stream_v;
     int rc = check_store(n, dim, ld, VQ_BF16);
     if (rc) return rc;
-    VQ_CHECK_ARG(b >= 0 && k > 0 && k <= 64 && cap >= k && cap <= 16384, "need b >= 0, 0 < k <= 64, k <= cap <= 16384 (b=%d k=%d cap=%d)", b, k, cap);
+    VQ_CHECK_ARG(b >= 0 && k > 0 && k <= 1024 && cap >= k && cap <= 16384, "need b >= 0, 0 < k <= 1024, k <= cap <= 16384 (b=%d k=%d cap=%d)", b, k, cap);
     VQ_CHECK_ARG(query_norm >= VQ_NORM_NONE && query_norm <= VQ_NORM_PLAIN, "bad query_norm %d", query_norm);
     if (b == 0) { vq_note_launch("none", 0); return VQ_OK; }
     VQ_CHECK_ARG(n > 0, "collect pass needs a non-empty store");
-    VQ_CHECK_ARG(store_bf16 && store_f32 && queries && thresholds && out_scores && out_rows && out_overflow && workspace,
-                 "NULL pointer argument");
+    VQ_CHECK_ARG(store_bf16 && store_f32 && queries && out_scores && out_rows && out_overflow && workspace,
+                 "NULL pointer argument");                       // thresholds may be NULL (derived from the store)
     VQ_CHECK_ARG(((uintptr_t)workspace & 255) == 0, "workspace must be 256-byte aligned");
     int launches = 0;
     rc = vq_scan_mma_collect(store_bf16, store_f32, n, dim, ld, queries, query_norm, b, thresholds, cap, k, out_scores, out_rows,

@@ -46,6 +46,7 @@ __device__ __forceinline__ float key_score(uint32_t k) {
 __global__ void __launch_bounds__(kThreads)
 scan_finish_kernel(int mode,      // 0 plain top-k of the scan scores, 1 two-stage + certificate, 2 re-score ALL candidates
                    const float* __restrict__ cand_s, const int* __restrict__ cand_r, const int* __restrict__ cand_cnt,
+                   int k_in, long long g_stride,   // g_stride > 0: candidates are cap/k_in lists [list][query][k_in] (FMA scan)
                    int cap, int k_sel, const float* __restrict__ store_f32, int ld, int dim,
                    const float* __restrict__ queries, int query_norm, float eps, int k_out,
                    float* __restrict__ out_s, int* __restrict__ out_r, int* __restrict__ out_bad, int sort_cap) {
@@ -58,7 +59,7 @@ scan_finish_kernel(int mode,      // 0 plain top-k of the scan scores, 1 two-sta
     int* ex_r = reinterpret_cast<int*>(ex_s + kMaxSel);                                   // [kMaxSel]
     __shared__ int part[2][kThreads / 32];
     __shared__ unsigned key_min, key_max;
-    __shared__ int sel_cnt;
+    __shared__ int sel_cnt, n_valid_s;
     const int q = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const bool dbg_on = g_finish_dbg != 0;
     long long tmark[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -66,9 +67,9 @@ scan_finish_kernel(int mode,      // 0 plain top-k of the scan scores, 1 two-sta
     vq_pdl_trigger();
     FDBG(0);
 
-    int n = cand_cnt[q];
-    n = n < cap ? n : cap;
-    if (tid == 0) { key_min = 0xffffffffu; key_max = 0u; sel_cnt = 0; if (out_bad && mode != 2) out_bad[q] = 0; }
+    int n = cap;                               // list layout: every slot is read, empty ones (row < 0) sort last
+    if (g_stride == 0) { n = cand_cnt[q]; n = n < cap ? n : cap; }
+    if (tid == 0) { key_min = 0xffffffffu; key_max = 0u; sel_cnt = 0; n_valid_s = 0; if (out_bad && mode != 2) out_bad[q] = 0; }
     __syncthreads();
     // ---- load: candidates -> 64-bit keys in shared memory (+ their score-key range); meanwhile the
     // last warp normalises the query in fp32 (same arithmetic as ingest_rows_kernel)
@@ -86,19 +87,28 @@ scan_finish_kernel(int mode,      // 0 plain top-k of the scan scores, 1 two-sta
     const size_t base = (size_t)q * cap;
     if (mode != 2) {
         unsigned mn = 0xffffffffu, mx = 0u;
+        int valid = 0;
         for (int i = tid; i < n; i += kThreads) {
-            const unsigned kh = score_key(cand_s[base + i]);
-            keys[i] = ((unsigned long long)kh << 32) | (unsigned)cand_r[base + i];
-            mn = kh < mn ? kh : mn;
-            mx = kh > mx ? kh : mx;
+            const size_t at = g_stride > 0 ? (size_t)(i / k_in) * (size_t)g_stride + (size_t)q * k_in + (size_t)(i % k_in) : base + i;
+            const int row = cand_r[at];
+            unsigned long long key = ~0ull;
+            if (row >= 0) {
+                const unsigned kh = score_key(cand_s[at]);
+                key = ((unsigned long long)kh << 32) | (unsigned)row;
+                mn = kh < mn ? kh : mn;
+                mx = kh > mx ? kh : mx;
+                ++valid;
+            }
+            keys[i] = key;
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
             const unsigned a = __shfl_xor_sync(0xffffffffu, mn, o), b = __shfl_xor_sync(0xffffffffu, mx, o);
             mn = a < mn ? a : mn;
             mx = b > mx ? b : mx;
+            valid += __shfl_xor_sync(0xffffffffu, valid, o);
         }
-        if (lane == 0 && n > 0) { atomicMin(&key_min, mn); atomicMax(&key_max, mx); }
+        if (lane == 0 && valid > 0) { atomicMin(&key_min, mn); atomicMax(&key_max, mx); atomicAdd(&n_valid_s, valid); }
     } else {
         // collect mode: the scan scores only selected the candidates; every one of them is re-scored
         // exactly (4 rows per warp in flight) and the keys are built from the EXACT scores
@@ -138,6 +148,7 @@ scan_finish_kernel(int mode,      // 0 plain top-k of the scan scores, 1 two-sta
             }
         }
         if (lane == 0 && n > 0) { atomicMin(&key_min, mn); atomicMax(&key_max, mx); }
+        if (tid == 0) n_valid_s = n;
         if (tid == 0 && out_bad) out_bad[q] = cand_cnt[q] > cap ? 1 : 0;      // overflow: result incomplete
     }
     __syncthreads();
@@ -148,10 +159,11 @@ scan_finish_kernel(int mode,      // 0 plain top-k of the scan scores, 1 two-sta
     // k_sel) lie below the pivot: one block-wide count and one barrier per step.
     int m = n;                                   // number of keys that take part in the final sort
     unsigned long long* pool = keys;
-    if (n > kSelStop && n > k_sel) {
-        unsigned lo = key_min, hi = key_max;     // invariant: count(key_hi <= hi) = cnt_hi >= k_sel
-        int cnt_hi = n, it = 0;
-        while (lo < hi && cnt_hi > kSelStop) {
+    const int sel_stop = k_sel > kSelStop ? k_sel : kSelStop;
+    if (n > sel_stop) {
+        unsigned lo = key_min, hi = key_max;     // invariant: count(key_hi <= hi) = cnt_hi >= min(k_sel, valid)
+        int cnt_hi = n_valid_s, it = 0;
+        while (lo < hi && cnt_hi > sel_stop) {
             const unsigned mid = lo + ((hi - lo) >> 1);
             int c = 0;
             for (int i = tid; i < n; i += kThreads) c += ((unsigned)(keys[i] >> 32) <= mid) ? 1 : 0;
@@ -210,8 +222,9 @@ scan_finish_kernel(int mode,      // 0 plain top-k of the scan scores, 1 two-sta
     keys = sorted;                               // entries [0, min(n, k_sel)) are what follows needs
 
     if (mode != 1) {
+        const int n_valid = n_valid_s;
         for (int i = tid; i < k_out; i += kThreads) {
-            const bool ok = i < n;
+            const bool ok = i < n_valid;
             out_s[(size_t)q * k_out + i] = ok ? key_score((unsigned)(keys[i] >> 32)) : VQ_NEG_INF;
             out_r[(size_t)q * k_out + i] = ok ? (int)(unsigned)keys[i] : -1;
         }
@@ -219,7 +232,7 @@ scan_finish_kernel(int mode,      // 0 plain top-k of the scan scores, 1 two-sta
     }
 
     // ---- two-stage: exact fp32 re-score of the best k_sel candidates
-    const int n_sel = n < k_sel ? n : k_sel;
+    const int n_sel = n_valid_s < k_sel ? n_valid_s : k_sel;
     FDBG(4);
     // one warp per candidate row (rescore_rows_kernel's fp32 FMA chain); 4 rows of a warp are loaded
     // together so that their HBM latencies overlap
@@ -269,7 +282,7 @@ scan_finish_kernel(int mode,      // 0 plain top-k of the scan scores, 1 two-sta
         }
         if (rank == k_out - 1 && out_bad) {
             // rows were dropped only if at least k_sel candidates exist; the dropped ones score <= the k_sel-th
-            out_bad[q] = (n >= k_sel && ms < key_score((unsigned)(keys[k_sel - 1] >> 32)) + eps) ? 1 : 0;
+            out_bad[q] = (n_valid_s >= k_sel && ms < key_score((unsigned)(keys[k_sel - 1] >> 32)) + eps) ? 1 : 0;
         }
     }
     FDBG(6);
@@ -280,12 +293,15 @@ scan_finish_kernel(int mode,      // 0 plain top-k of the scan scores, 1 two-sta
 
 }  // namespace
 
-int vq_scan_finish_launch(int mode, const float* cand_s, const int* cand_r, const int* cand_cnt, int cap, int b, int k_sel,
+static int finish_launch(int mode, const float* cand_s, const int* cand_r, const int* cand_cnt, int k_in, long long g_stride,
+                         int cap, int b, int k_sel,
                           const float* store_f32, int ld, int dim, const float* queries, int query_norm, float eps,
                           int k_out, float* out_scores, int* out_rows, int* out_bad, cudaStream_t stream) {
     if (b <= 0) return VQ_OK;
-    if (k_sel > kMaxSel || k_out > k_sel) {
-        vq_set_error("scan_finish: need k_out <= k_sel <= %d (k_sel=%d k_out=%d)", kMaxSel, k_sel, k_out);
+    // modes 0 / 1 rank their k_sel exact scores with one thread each out of a 64-entry buffer; mode 2 (collect)
+    // selects straight from the sorted keys and goes up to the sort pool
+    if (k_sel > (mode != 1 ? kSelMax : kMaxSel) || k_out > k_sel) {
+        vq_set_error("scan_finish: need k_out <= k_sel <= %d (k_sel=%d k_out=%d)", mode != 1 ? kSelMax : kMaxSel, k_sel, k_out);
         return VQ_EUNSUPPORTED;
     }
     int sort_cap = 2;
@@ -302,11 +318,27 @@ int vq_scan_finish_launch(int mode, const float* cand_s, const int* cand_r, cons
         VQ_CUDA(cudaFuncSetAttribute(scan_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
         attr_done = true;
     }
-    const cudaError_t e = vq_launch(4, scan_finish_kernel, dim3(b), dim3(kThreads), smem, stream, mode, cand_s, cand_r, cand_cnt, cap, k_sel,
+    const cudaError_t e = vq_launch(4, scan_finish_kernel, dim3(b), dim3(kThreads), smem, stream, mode, cand_s, cand_r, cand_cnt, k_in, g_stride, cap, k_sel,
                                     store_f32, ld, dim, queries, query_norm, eps, k_out, out_scores, out_rows, out_bad, sort_cap);
     if (e != cudaSuccess) {
         vq_set_error("launch of scan_finish_kernel failed: %s", cudaGetErrorString(e));
         return VQ_ECUDA;
     }
     return VQ_OK;
+}
+
+int vq_scan_finish_launch(int mode, const float* cand_s, const int* cand_r, const int* cand_cnt, int cap, int b, int k_sel,
+                          const float* store_f32, int ld, int dim, const float* queries, int query_norm, float eps,
+                          int k_out, float* out_scores, int* out_rows, int* out_bad, cudaStream_t stream) {
+    return finish_launch(mode, cand_s, cand_r, cand_cnt, 1, 0, cap, b, k_sel, store_f32, ld, dim, queries, query_norm, eps, k_out,
+                         out_scores, out_rows, out_bad, stream);
+}
+
+// Best k_out of g sorted-or-not candidate lists per query laid out [list][query][k_in] (the per-CTA lists of
+// the FMA scan): the same bisection select + rank sort, one CTA per query.  g * k_in <= 16384.
+bool vq_scan_finish_lists_supported(int g, int k_in, int k_out) { return (long long)g * k_in <= 16384 && k_out <= kSelMax; }
+int vq_scan_finish_lists_launch(const float* scores, const int* rows, int g, long long g_stride, int b, int k_in, int k_out,
+                                float* out_scores, int* out_rows, cudaStream_t stream) {
+    return finish_launch(0, scores, rows, nullptr, k_in, g_stride, g * k_in, b, k_out, nullptr, 32, 32, nullptr, VQ_NORM_NONE, 0.f,
+                         k_out, out_scores, out_rows, nullptr, stream);
 }

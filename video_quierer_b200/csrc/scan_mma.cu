@@ -60,6 +60,7 @@ constexpr int TMEM_COLS = 512;          // whole tensor memory: 2 accumulators +
 constexpr int kThreads = 256;
 constexpr int kMaxK = 64;
 constexpr int kModeList = 0, kModeBoot = 1, kModeCollect = 2;   // epilogue of scan_mma_bf16_kernel
+constexpr int kStage = 8;               // collect mode: candidates a thread stages in shared memory per global atomic
 constexpr int kIssuers = 2;            // MMA-issuing warps (warps 1 and 2), alternating k-blocks
 constexpr int kMaxBootTiles = 256;     // sample tiles of the threshold bootstrap (8 per lane in boot_select)
 
@@ -417,6 +418,18 @@ scan_mma_bf16_kernel(const __grid_constant__ CUtensorMap tmS,
             // query's candidate buffer (no lists).  Used to resolve queries the certificate rejected.
             const float thr = gtau[q];
             const size_t dst = (size_t)q * cap;
+            // candidates are staged kStage at a time in this thread's slice of shared memory and flushed
+            // with ONE atomicAdd: waiting for a global atomic per candidate (an L2 round trip inside the
+            // tile loop, hit by some lane in almost every 32-score chunk) cost as much as the MMAs
+            float* stage_s = reinterpret_cast<float*>(smem + (size_t)stages * B_KB_BYTES + 512) + (size_t)(ew * 32 + lane) * kStage;
+            int* stage_r = reinterpret_cast<int*>(smem + (size_t)stages * B_KB_BYTES + 512 + (size_t)QT * kStage * 4) + (size_t)(ew * 32 + lane) * kStage;
+            int staged = 0;
+            auto flush = [&]() {
+                const int at = atomicAdd(cand_cnt + q, staged);
+                for (int i = 0; i < staged; ++i)
+                    if (at + i < cap) { cand_s[dst + at + i] = stage_s[i]; cand_r[dst + at + i] = stage_r[i]; }
+                staged = 0;
+            };
             int it = 0;
             for (int tile = group; tile < n_tiles; tile += n_groups, ++it) {
                 const int acc = it & 1;
@@ -440,14 +453,16 @@ scan_mma_bf16_kernel(const __grid_constant__ CUtensorMap tmS,
                         float sc = __uint_as_float(v[0]);
 #pragma unroll
                         for (int jj = 1; jj < 32; ++jj) sc = (j == jj) ? __uint_as_float(v[jj]) : sc;
-                        const int at = atomicAdd(cand_cnt + q, 1);
-                        if (at < cap) { cand_s[dst + at] = sc; cand_r[dst + at] = row0 + c0 + j; }
+                        stage_s[staged] = sc;
+                        stage_r[staged] = row0 + c0 + j;
+                        if (++staged == kStage) flush();
                     }
                 }
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&tmem_empty[acc]);
             }
+            if (staged) flush();
         } else if (MODE == kModeBoot) {
             // threshold bootstrap: only the per-query maximum of every sample tile is kept
             int it = 0;
@@ -584,7 +599,7 @@ prep_queries_bf16_kernel(const float* __restrict__ src, int b, int dim, int src_
 // query: the maxima go to shared memory and every lane ranks its own values against all of them
 // (n_t <= kMaxBootTiles, no serial dependency chain); the value of rank k-1 is the bound.
 __global__ void __launch_bounds__(256)
-boot_select_kernel(const float* __restrict__ boot_max, int n_t, int b_pad, int k, float* __restrict__ gtau) {
+boot_select_kernel(const float* __restrict__ boot_max, int n_t, int b, int b_pad, int k, float* __restrict__ gtau) {
     __shared__ float vals[8][kMaxBootTiles];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int q = blockIdx.x * 8 + w;
@@ -605,7 +620,8 @@ boot_select_kernel(const float* __restrict__ boot_max, int n_t, int b_pad, int k
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) kth = fmaxf(kth, __shfl_xor_sync(0xffffffffu, kth, o));
-    if (lane == 0) gtau[q] = (n_t >= k) ? kth : VQ_NEG_INF;
+    // padding queries (zero vectors) must not keep or gather anything: their bound is +inf
+    if (lane == 0) gtau[q] = q >= b ? INFINITY : (n_t >= k) ? kth : VQ_NEG_INF;
 }
 
 // ------------------------------------------------------------------------------------ host
@@ -707,7 +723,7 @@ MmaPlan plan(int64_t n, int ld, int b, int k) {
     const long long min_tiles = (p.n_qt >= 2 ? 4LL : 16LL) * bt;
     p.boot_tiles = (boot_on && p.nt && n_tiles >= min_tiles && bt >= k) ? bt : 0;
     p.boot_groups = p.boot_tiles ? (p.boot_tiles < (int)groups ? p.boot_tiles : (int)groups) : 0;
-    p.smem = 1024 + (size_t)p.stages * stage_bytes + 512;
+    p.smem = 1024 + (size_t)p.stages * stage_bytes + 512 + (size_t)QT * kStage * 8;
     // candidate capacity is sized for the largest group count any batch <= b can get (the HNSW builder
     // reuses one workspace for a shrinking last batch)
     const int max_groups = sms > p.n_qt ? sms : p.n_qt;
@@ -757,7 +773,7 @@ cudaError_t launch_mma(const MmaPlan& p, const CUtensorMap& tmS, const __nv_bflo
 }
 
 // [boot pass ->] main pass; gtau / cnt must have been reset by the caller's prologue kernel.
-int run_scan(const MmaPlan& p, const void* store, int64_t n, int ld, const __nv_bfloat16* qbf, const MmaWs& w, int k,
+int run_scan(const MmaPlan& p, const void* store, int64_t n, int ld, const __nv_bfloat16* qbf, const MmaWs& w, int b, int k,
              cudaStream_t stream, int* launches) {
     static const int dbg = getenv("VQ_MMA_DEBUG") ? atoi(getenv("VQ_MMA_DEBUG")) : 0;
     CUtensorMap tmS;
@@ -777,7 +793,7 @@ int run_scan(const MmaPlan& p, const void* store, int64_t n, int ld, const __nv_
             return VQ_ECUDA;
         }
         e = vq_launch(2, boot_select_kernel, dim3((p.b_pad + 7) / 8), dim3(256), 0, stream, (const float*)w.boot_max, p.boot_tiles,
-                      p.b_pad, k, w.gtau);
+                      b, p.b_pad, k, w.gtau);
         if (e != cudaSuccess) {
             vq_set_error("launch of boot_select_kernel failed: %s", cudaGetErrorString(e));
             return VQ_ECUDA;
@@ -850,7 +866,7 @@ int vq_scan_mma_prepared(const void* store, int64_t n, int ld, const void* qbf, 
         return VQ_ECUDA;
     }
     int nl = 0;
-    int rc = run_scan(p, store, n, ld, (const __nv_bfloat16*)qbf, w, k, stream, &nl);
+    int rc = run_scan(p, store, n, ld, (const __nv_bfloat16*)qbf, w, b, k, stream, &nl);
     if (rc) return rc;
     return vq_scan_finish_launch(0, w.cand_s, w.cand_r, w.cnt, p.cap, b, k, nullptr, ld, ld, nullptr, VQ_NORM_NONE, 0.f, k,
                                  out_scores, out_rows, nullptr, stream);
@@ -884,7 +900,7 @@ int vq_scan_mma_run(const void* store, int64_t n, int dim, int ld, int store_dty
         return VQ_ECUDA;
     }
     int nl = 0;
-    int rc = run_scan(p, store, n, ld, w.qbf, w, k_sel, stream, &nl);
+    int rc = run_scan(p, store, n, ld, w.qbf, w, b, k_sel, stream, &nl);
     if (rc) return rc;
     rc = vq_scan_finish_launch(store_f32 ? 1 : 0, w.cand_s, w.cand_r, w.cnt, p.cap, b, k_sel, store_f32, ld, dim, queries, query_norm,
                                eps, k_out, out_scores, out_rows, out_bad, stream);
@@ -900,8 +916,13 @@ int vq_scan_mma_run(const void* store, int64_t n, int dim, int ld, int store_dty
 // out_overflow[q] = 1 if more than `cap` rows reached the threshold (result incomplete).
 size_t vq_scan_mma_collect_workspace(int64_t n, int ld, int b, int cap) {
     const MmaPlan p = plan(n, ld, b, 1);
-    return p.off_cand_s + 2 * align256((size_t)p.b_pad * cap * 4) + align256((size_t)p.b_pad * ld * 2) + 256;
+    return p.off_cand_s + 2 * align256((size_t)p.b_pad * cap * 4) + align256((size_t)p.b_pad * ld * 2) +
+           align256((size_t)kMaxBootTiles * p.b_pad * 4) + 256;
 }
+// thresholds == NULL: the threshold of every query is derived from the store itself — a boot pass scores
+// min(256, tiles) sample tiles and the k-th largest tile maximum (reached by k distinct rows) is used, so at
+// least k rows are gathered.  The exact top-k of THOSE rows is then a set of k real rows: its k-th exact
+// score is a valid lower bound of the k-th best of any store that contains them (large-k search, step 1).
 int vq_scan_mma_collect(const void* store_bf16, const float* store_f32, int64_t n, int dim, int ld, const float* queries,
                         int query_norm, int b, const float* thresholds, int cap, int k, float* out_scores, int32_t* out_rows,
                         int32_t* out_overflow, void* ws_v, size_t ws_bytes, cudaStream_t stream, int* launches) {
@@ -921,8 +942,8 @@ int vq_scan_mma_collect(const void* store_bf16, const float* store_f32, int64_t 
     const size_t cand_bytes = align256((size_t)p.b_pad * cap * 4);
     w.cand_s = (float*)(ws + p.off_cand_s);
     w.cand_r = (int*)(ws + p.off_cand_s + cand_bytes);
-    w.boot_max = nullptr;
     w.qbf = (__nv_bfloat16*)(ws + p.off_cand_s + 2 * cand_bytes);
+    w.boot_max = (float*)(ws + p.off_cand_s + 2 * cand_bytes + align256((size_t)p.b_pad * ld * 2));
     p.cap = cap;
     if (vq_launch(0, prep_queries_bf16_kernel, dim3((p.b_pad + 7) / 8), dim3(256), 0, stream, queries, b, dim, dim, w.qbf, ld,
                   p.b_pad, query_norm, w.gtau, w.cnt, thresholds) != cudaSuccess) {
@@ -935,8 +956,30 @@ int vq_scan_mma_collect(const void* store_bf16, const float* store_f32, int64_t 
         vq_set_error("scan_mma: cuTensorMapEncodeTiled failed");
         return VQ_ECUDA;
     }
-    const cudaError_t e = p.nt == 128 ? launch_mma<1, 128, kModeCollect>(p, tmS, w.qbf, w, (int)n, ld, 1, dbg, stream)
-                                      : launch_mma<1, 64, kModeCollect>(p, tmS, w.qbf, w, (int)n, ld, 1, dbg, stream);
+    cudaError_t e;
+    *launches = 3;
+    if (thresholds == nullptr) {
+        const long long full_tiles = n / p.nt;
+        p.boot_tiles = (int)(full_tiles < kMaxBootTiles ? full_tiles : kMaxBootTiles);
+        if (p.boot_tiles < k) {
+            vq_set_error("scan_mma_collect: automatic thresholds need at least k=%d full tiles of %d rows (n=%lld)", k, p.nt, (long long)n);
+            return VQ_EUNSUPPORTED;
+        }
+        p.boot_groups = p.boot_tiles < p.groups ? p.boot_tiles : p.groups;
+        const int n_boot = p.boot_tiles * p.nt;
+        e = p.nt == 128 ? launch_mma<1, 128, kModeBoot>(p, tmS, w.qbf, w, n_boot, ld, k, dbg, stream)
+                        : launch_mma<1, 64, kModeBoot>(p, tmS, w.qbf, w, n_boot, ld, k, dbg, stream);
+        if (e == cudaSuccess)
+            e = vq_launch(2, boot_select_kernel, dim3((p.b_pad + 7) / 8), dim3(256), 0, stream, (const float*)w.boot_max, p.boot_tiles,
+                          b, p.b_pad, k, w.gtau);
+        if (e != cudaSuccess) {
+            vq_set_error("launch of the boot pass failed: %s", cudaGetErrorString(e));
+            return VQ_ECUDA;
+        }
+        *launches = 5;
+    }
+    e = p.nt == 128 ? launch_mma<1, 128, kModeCollect>(p, tmS, w.qbf, w, (int)n, ld, 1, dbg, stream)
+                    : launch_mma<1, 64, kModeCollect>(p, tmS, w.qbf, w, (int)n, ld, 1, dbg, stream);
     if (e != cudaSuccess) {
         vq_set_error("launch of scan_mma_bf16_kernel<collect> failed: %s", cudaGetErrorString(e));
         return VQ_ECUDA;
@@ -944,6 +987,5 @@ int vq_scan_mma_collect(const void* store_bf16, const float* store_f32, int64_t 
     const int rc = vq_scan_finish_launch(2, w.cand_s, w.cand_r, w.cnt, cap, b, k, store_f32, ld, dim, queries, query_norm, 0.f, k,
                                          out_scores, out_rows, out_overflow, stream);
     if (rc) return rc;
-    *launches = 3;
     return VQ_OK;
 }

@@ -121,6 +121,7 @@ class DeviceStore:
                 _lib.check(self.lib.vq_ingest_rows(_ptr(src), m, self.dim, self.dim, _ptr(dst), _lib.BF16, self.ld,
                                                    norm, st), "vq_ingest_rows")
         self.n += m
+        self._sample = None
 
     # ------------------------------------------------------------------ raw persistence (rawstore.py)
     def save_raw_arrays(self, writer):
@@ -164,6 +165,19 @@ class DeviceStore:
 
     def truncate(self, n: int):
         self.n = min(self.n, max(0, int(n)))
+        self._sample = None
+
+    def sample_f32(self, stride: int) -> torch.Tensor:
+        """Compact (fp32, bf16) copies of every `stride`-th row (rows 0, stride, 2*stride, ...), cached
+        until the store changes: the k-th best exact score found inside this sample is a lower bound of
+        the k-th best of the whole store (used by the large-k search to seed its collect pass)."""
+        key = (self.n, int(stride))
+        if getattr(self, "_sample", None) is None or self._sample[0] != key:
+            with torch.cuda.device(self.device):
+                f = self.f32[: self.n: stride].contiguous()
+                b = self.bf16[: self.n: stride].contiguous() if self.bf16 is not None else None
+                self._sample = (key, f, b)
+        return self._sample[1], self._sample[2]
 
     def view(self, dtype: str = "fp32") -> torch.Tensor:
         t = self.f32 if _DT[dtype] == _lib.F32 else self.bf16
@@ -247,7 +261,8 @@ class Scanner:
             over = torch.zeros((b,), dtype=torch.int32, device=self.device)
             if b == 0:
                 return out_s, out_r, over
-            thresholds = thresholds.to(torch.float32).contiguous()
+            if thresholds is not None:
+                thresholds = thresholds.to(torch.float32).contiguous()
             need = self.lib.vq_search_collect_workspace_bytes(n, dim, ld, b, cap)
             with self.lock:
                 ws = self.ws.get(need)

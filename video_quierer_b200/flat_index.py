@@ -151,9 +151,7 @@ def two_stage_search(scanner: Scanner, st: DeviceStore, q_dev: torch.Tensor, k: 
     kc = int(os.environ.get("VQ_KCAND", 0)) or (32 if k <= 16 else max(2 * k, k + 22))
     kc = max(min(st.n, kc, MAX_TENSOR_K), min(k, st.n))
     if k > MAX_TENSOR_K or st.ld > MAX_TENSOR_LD:
-        # beyond the register top-k of the tensor path: the fp32 FMA scan is exact by itself
-        s, r = scanner.scan(st.f32, st.n, st.dim, q_dev, k, _lib.NORM_EPS, "fma")
-        return s, r, None
+        return large_k_search(scanner, st, q_dev, k, max_row_norm) + (None,)
     s_hi, rows, bad = scanner.two_stage(st.bf16, st.f32, st.n, st.dim, q_dev, k, kc, _lib.NORM_EPS,
                                         BF16_SCORE_EPS * max_row_norm)
     return s_hi, rows, (bad if kc < st.n else None)
@@ -165,6 +163,36 @@ def exact_fallback(scanner: Scanner, st: DeviceStore, q_dev: torch.Tensor, k: in
 
 
 COLLECT_CAP = 4096
+LARGE_K_CAP = 16384
+
+
+def large_k_search(scanner: Scanner, st: DeviceStore, q_dev: torch.Tensor, k: int, max_row_norm: float = 1.0):
+    """Exact top-k beyond the register lists of the tensor kernel (64 < k <= 256; BASELINE config 4:
+    k = 100), in two tensor-core collect passes:
+      1. over a STRIDED SAMPLE of the store (a compact copy of every `stride`-th row, cached with the
+         store) with thresholds derived from the sample itself (k-th largest per-tile maximum): at
+         least k rows are gathered and re-scored in fp32; the k-th exact score among them, s_k, is
+         reached by k real rows, so it is a lower bound of the k-th best of the whole store;
+      2. over the whole store with threshold s_k - eps: every row of the true top-k is gathered
+         (about k * stride rows per query), all are re-scored in fp32, the best k are returned.
+    Exact by construction.  Queries whose gather overflows, and stores that are too small or too
+    wide for the tensor kernel, are answered by the fp32 FMA scan."""
+    tile = 128 if st.ld <= 512 else 64
+    # the sample must hold k + 1 full tiles (the derived threshold is the k-th largest tile maximum); the
+    # second pass gathers ~k * stride rows per query, which has to stay well inside LARGE_K_CAP
+    stride = min(64, LARGE_K_CAP // (3 * k), st.n // ((k + 1) * tile)) if k <= 256 else 0
+    if st.bf16 is None or st.ld > MAX_TENSOR_LD or stride < 2:
+        return scanner.scan(st.f32, st.n, st.dim, q_dev, k, _lib.NORM_EPS, "fma")
+    smp_f32, smp_bf16 = st.sample_f32(stride)       # rows 0, stride, 2*stride, ...
+    s1, _, over1 = scanner.collect(smp_bf16, smp_f32, smp_f32.shape[0], st.dim, q_dev, k, None, LARGE_K_CAP)
+    thr = s1[:, k - 1] - BF16_SCORE_EPS * max_row_norm
+    thr = torch.where(over1 > 0, torch.full_like(thr, float("-inf")), thr)      # incomplete sample answer: no bound
+    s, r, over = scanner.collect(st.bf16, st.f32, st.n, st.dim, q_dev, k, thr, LARGE_K_CAP)
+    over_h = torch.nonzero(over).flatten()
+    if len(over_h):
+        sf, rf = exact_fallback(scanner, st, q_dev, k, over_h)
+        s[over_h], r[over_h] = sf, rf
+    return s, r
 
 
 def resolve_uncertified(scanner: Scanner, st: DeviceStore, q_dev: torch.Tensor, k: int, idx: torch.Tensor,
