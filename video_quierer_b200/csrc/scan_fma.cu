@@ -190,7 +190,7 @@ cudaError_t launch(const void* store, int n, int ld, const float* q, int k, floa
 }  // namespace
 
 // Rows per CTA step for a query tile of `bt`.
-int vq_scan_fma_tile_rows(int bt) { return bt <= 16 ? 128 : 64; }
+int vq_scan_fma_tile_rows(int bt) { return bt <= 2 ? 256 : bt <= 16 ? 128 : 64; }
 
 size_t vq_scan_fma_smem(int bt, int ld, int k) {
     const int tile = vq_scan_fma_tile_rows(bt);
@@ -220,8 +220,8 @@ int vq_scan_fma_launch(const void* store, int n, int ld, int store_dtype, const 
                : launch<BT_, R_, false>(store, n, ld, q, k, part_scores, part_rows, grid, smem, stream); \
         break;
     switch (bt) {
-        VQ_CASE(1, 4)
-        VQ_CASE(2, 4)
+        VQ_CASE(1, 8)
+        VQ_CASE(2, 8)
         VQ_CASE(4, 4)
         VQ_CASE(8, 4)
         VQ_CASE(16, 4)
