@@ -613,7 +613,6 @@ merge_fwd_rev_kernel(const int* __restrict__ fwd, const int* __restrict__ rev_cn
 }
 
 inline size_t align256(size_t v) { return (v + 255) / 256 * 256; }
-inline int pow2_ge(int v) { int p = 1; while (p < v) p <<= 1; return p; }
 
 struct SearchPlan { int cap, warp_bytes, warps; size_t smem; };
 SearchPlan plan_search(int ld, int ef, int visited_capacity) {

@@ -86,11 +86,6 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
             "}" : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
     } while (!done);
 }
-__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
-}
 __device__ __forceinline__ void tma_load_2d_addr(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
     asm volatile(
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
@@ -676,7 +671,6 @@ bool get_map_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint64_t ld
 }
 
 inline size_t align256(size_t v) { return (v + 255) / 256 * 256; }
-inline int pow2_ge(int v) { int p = 2; while (p < v) p <<= 1; return p; }
 
 struct MmaPlan {
     int nkb, nt, n_qt, b_pad, groups, grid, stages, grp_log2, cl;
