@@ -248,7 +248,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 scan_mma_bf16_kernel(const __grid_constant__ CUtensorMap tmS,
                      const __nv_bfloat16* __restrict__ qbf,   // [b_pad, ld] normalised, zero padded
                      float* __restrict__ gtau,                // [b_pad] shared k-th best per query (-inf initialised)
-                     int n, int ld, int nkb, int n_qt, int k, int stages, int grp_log2, int cl, int b_pad,
+                     int n, int ld, int nkb, int n_qt, int k, int stages, int grp_log2, int cl, int tile_mul, int b_pad,
                      float* __restrict__ cand_s,              // [b_pad, cap] surviving candidates (BOOT: [tiles, b_pad] maxima)
                      int* __restrict__ cand_r, int* __restrict__ cand_cnt, int cap, int dbg) {
     constexpr int B_KB_BYTES = NT * 128;
@@ -309,7 +309,8 @@ scan_mma_bf16_kernel(const __grid_constant__ CUtensorMap tmS,
                             tma_load_2d_mc(sB_addr + (uint32_t)stage * B_KB_BYTES + cl_rank * (B_KB_BYTES / 2), &tmS,
                                            full_addr + (uint32_t)stage * 8, kb * KB_ELEMS, tile * NT + (int)cl_rank * (NT / 2), cl_mask);
                         else
-                            tma_load_2d_addr(sB_addr + (uint32_t)stage * B_KB_BYTES, &tmS, full_addr + (uint32_t)stage * 8, kb * KB_ELEMS, tile * NT);
+                            tma_load_2d_addr(sB_addr + (uint32_t)stage * B_KB_BYTES, &tmS, full_addr + (uint32_t)stage * 8, kb * KB_ELEMS,
+                                             tile * tile_mul * NT);   // boot pass: sample tile j is store tile j * tile_mul
                     }
                 }
                 __syncwarp();
@@ -674,7 +675,7 @@ inline size_t align256(size_t v) { return (v + 255) / 256 * 256; }
 
 struct MmaPlan {
     int nkb, nt, n_qt, b_pad, groups, grid, stages, grp_log2, cl;
-    int boot_tiles, boot_groups;                 // threshold bootstrap (0 = off)
+    int boot_tiles, boot_groups, boot_mul;       // threshold bootstrap (0 = off); sample tile j = store tile j * boot_mul
     int cap;                                     // candidate slots per query (= groups * k, cannot overflow)
     size_t smem;
     // workspace layout
@@ -717,6 +718,10 @@ MmaPlan plan(int64_t n, int ld, int b, int k) {
     const long long min_tiles = (p.n_qt >= 2 ? 4LL : 16LL) * bt;
     p.boot_tiles = (boot_on && p.nt && n_tiles >= min_tiles && bt >= k) ? bt : 0;
     p.boot_groups = p.boot_tiles ? (p.boot_tiles < (int)groups ? p.boot_tiles : (int)groups) : 0;
+    // the sample tiles are spread evenly over the FULL tiles of the store: frames of a video sit next to
+    // each other, a prefix of the store would only know the first few videos
+    p.boot_mul = p.boot_tiles ? (int)((n / p.nt) / p.boot_tiles) : 1;
+    if (p.boot_mul < 1) p.boot_mul = 1;
     p.smem = 1024 + (size_t)p.stages * stage_bytes + 512 + (size_t)QT * kStage * 8;
     // candidate capacity is sized for the largest group count any batch <= b can get (the HNSW builder
     // reuses one workspace for a shrinking last batch)
@@ -763,7 +768,7 @@ cudaError_t launch_mma(const MmaPlan& p, const CUtensorMap& tmS, const __nv_bflo
     const int grid = BOOT ? p.boot_groups * p.n_qt : p.grid;
     const int cl = MODE == kModeList ? p.cl : 1;
     return vq_launch_cluster(BOOT ? 1 : 3, cl, kern, dim3(grid), dim3(kThreads), p.smem, stream, tmS, qbf, w.gtau, n, ld, p.nkb, p.n_qt,
-                             k, p.stages, p.grp_log2, cl, p.b_pad, BOOT ? w.boot_max : w.cand_s, w.cand_r, w.cnt, p.cap, dbg);
+                             k, p.stages, p.grp_log2, cl, BOOT ? p.boot_mul : 1, p.b_pad, BOOT ? w.boot_max : w.cand_s, w.cand_r, w.cnt, p.cap, dbg);
 }
 
 // [boot pass ->] main pass; gtau / cnt must have been reset by the caller's prologue kernel.
@@ -778,7 +783,7 @@ int run_scan(const MmaPlan& p, const void* store, int64_t n, int ld, const __nv_
     cudaError_t e;
     *launches = 1;
     if (p.boot_tiles) {
-        // sample pass over the first boot_tiles full tiles: per-tile maxima -> boot_max, then gtau
+        // sample pass over boot_tiles full tiles spread over the store: per-tile maxima -> boot_max, then gtau
         const int n_boot = p.boot_tiles * p.nt;
         e = p.nt == 128 ? launch_mma<1, 128, kModeBoot>(p, tmS, qbf, w, n_boot, ld, k, dbg, stream)
                         : launch_mma<1, 64, kModeBoot>(p, tmS, qbf, w, n_boot, ld, k, dbg, stream);
@@ -960,6 +965,7 @@ int vq_scan_mma_collect(const void* store_bf16, const float* store_f32, int64_t 
             return VQ_EUNSUPPORTED;
         }
         p.boot_groups = p.boot_tiles < p.groups ? p.boot_tiles : p.groups;
+        p.boot_mul = (int)(full_tiles / p.boot_tiles);
         const int n_boot = p.boot_tiles * p.nt;
         e = p.nt == 128 ? launch_mma<1, 128, kModeBoot>(p, tmS, w.qbf, w, n_boot, ld, k, dbg, stream)
                         : launch_mma<1, 64, kModeBoot>(p, tmS, w.qbf, w, n_boot, ld, k, dbg, stream);
