@@ -366,3 +366,23 @@ def test_large_k_sampled_collect_is_exact(eng, gen, n, dim, k):
     assert bad is None and sc.last_path.startswith("scan_mma_bf16<collect>")
     ro, so = exact.exact_search_batch(store, q, k)
     assert compare.check_topk_batch(r.cpu().numpy(), s.cpu().numpy(), ro, so) == []
+
+
+def test_facade_chunks_very_large_batches(eng):
+    """More queries than one launch chain takes (MAX_BATCH): the facade chunks, results unchanged."""
+    from video_quierer_b200 import flat_index
+    from video_quierer_b200.flat_index import B200FlatIndex
+    store = synth.gauss(3000, 64, seed=95)
+    q = synth.gauss(700, 64, seed=96)
+    idx = B200FlatIndex(store_dtype="bf16", rescore=True)
+    idx.add_frames(store, ["a.mp4"] * len(store), np.arange(len(store), dtype=float))
+    s0, r0 = idx.search_arrays(q, 5)
+    old = flat_index.MAX_BATCH
+    try:
+        flat_index.MAX_BATCH = 256
+        s1, r1 = idx.search_arrays(q, 5)
+    finally:
+        flat_index.MAX_BATCH = old
+    assert np.array_equal(r0, r1) and np.array_equal(s0, s1)
+    ro, so = exact.exact_search_batch(store, q, 5)
+    assert compare.check_topk_batch(r1, s1, ro, so) == []

@@ -133,6 +133,7 @@ class LazyRows:
 # |delta| <= (2*2^-9 + 2^-18) * sum|q_i x_i| <= 2^-8 * |q| |x|  (Cauchy-Schwarz) plus fp32 accumulation noise.
 BF16_SCORE_EPS = 2.0 ** -8 + 1e-5
 MAX_TENSOR_K, MAX_TENSOR_LD = 64, 768        # limits of scan_mma_bf16_kernel (csrc/scan_mma.cu)
+MAX_BATCH = 8192                             # queries per launch chain of the facade (64 query tiles)
 
 
 def two_stage_search(scanner: Scanner, st: DeviceStore, q_dev: torch.Tensor, k: int, path: str = "auto",
@@ -311,25 +312,32 @@ class B200FlatIndex:
                 b = 1 if np.ndim(queries) == 1 else len(queries)
                 return np.zeros((b, 0), np.float32), np.zeros((b, 0), np.int32)
             st = self._store
-            q = as_device_queries(queries, st.dim, self.device)
+            q_all = as_device_queries(queries, st.dim, self.device)
             kk = min(int(k), n)
-            if self.store_dtype != "bf16":
-                s, r = self._scanner.scan(st.f32, st.n, st.dim, q, kk, _lib.NORM_EPS, self.path)
-                return s.cpu().numpy(), r.cpu().numpy()
-            if not self.rescore:
-                s, r = self._scanner.scan(st.bf16, st.n, st.dim, q, kk, _lib.NORM_EPS, self.path)
-                return s.cpu().numpy(), r.cpu().numpy()
-            s, r, bad = two_stage_search(self._scanner, st, q, kk, self.path)
-            s_h, r_h = s.cpu().numpy(), r.cpu().numpy()
-            self.stats["two_stage_queries"] += int(q.shape[0])
-            if bad is not None:
-                bad_h = np.nonzero(bad.cpu().numpy())[0]
-                if len(bad_h):
-                    self.stats["uncertified_queries"] += len(bad_h)
-                    idx = torch.from_numpy(bad_h).to(self.device)
-                    s2, r2 = resolve_uncertified(self._scanner, st, q, kk, idx, s)
-                    s_h[bad_h], r_h[bad_h] = s2.cpu().numpy(), r2.cpu().numpy()
-            return s_h, r_h
+            if q_all.shape[0] > MAX_BATCH:          # one launch covers at most #SMs query tiles: chunk beyond
+                parts = [self._search_chunk(st, q_all[i: i + MAX_BATCH].contiguous(), kk)
+                         for i in range(0, q_all.shape[0], MAX_BATCH)]
+                return np.concatenate([p[0] for p in parts]), np.concatenate([p[1] for p in parts])
+            return self._search_chunk(st, q_all, kk)
+
+    def _search_chunk(self, st, q, kk):
+        if self.store_dtype != "bf16":
+            s, r = self._scanner.scan(st.f32, st.n, st.dim, q, kk, _lib.NORM_EPS, self.path)
+            return s.cpu().numpy(), r.cpu().numpy()
+        if not self.rescore:
+            s, r = self._scanner.scan(st.bf16, st.n, st.dim, q, kk, _lib.NORM_EPS, self.path)
+            return s.cpu().numpy(), r.cpu().numpy()
+        s, r, bad = two_stage_search(self._scanner, st, q, kk, self.path)
+        s_h, r_h = s.cpu().numpy(), r.cpu().numpy()
+        self.stats["two_stage_queries"] += int(q.shape[0])
+        if bad is not None:
+            bad_h = np.nonzero(bad.cpu().numpy())[0]
+            if len(bad_h):
+                self.stats["uncertified_queries"] += len(bad_h)
+                idx = torch.from_numpy(bad_h).to(self.device)
+                s2, r2 = resolve_uncertified(self._scanner, st, q, kk, idx, s)
+                s_h[bad_h], r_h[bad_h] = s2.cpu().numpy(), r2.cpu().numpy()
+        return s_h, r_h
 
     def search(self, query_embedding: np.ndarray, k: int = 5) -> List[Dict]:
         """video_search_overhaul.py:40-64: list of metadata copies + 'score', best first."""
