@@ -147,8 +147,8 @@ def _config(batch, gpus, path, two_stage=False):
             "store_dtype": "fp32 master + bf16 scan copy (tensor-core scan selects 32 candidates, exact fp32 "
                            "re-score, certified)" if two_stage else "fp32",
             "scan_path": path,
-            "l2": "scanned shard > 300 MB > 126 MB L2, no flush needed between steps" if N_ROWS // gpus * DIM * elem > 300e6
-                  else "scanned shard could sit in L2: a 256 MB buffer is written between timed steps",
+            "l2": "scanned shard > 1.5 x the 126 MB L2: it evicts itself between steps" if N_ROWS // gpus * DIM * elem > 190e6
+                  else "scanned shard could sit in L2: consecutive steps scan different identical copies of it (>= 500 MB in rotation)",
             "parallelism": f"rows/{gpus}"}
 
 
@@ -172,29 +172,38 @@ def run_ours(args):
 
     # ---- synthetic store shard, generated on the device (S-gauss, fixed seed per 64k-row block)
     lo, hi = shard_range(N_ROWS, world, rank)
-    store = engine.DeviceStore(DIM, dev, keep_fp32=True, keep_bf16=two_stage, capacity=hi - lo)
-    blk = 1 << 16
-    for b0 in range(lo // blk * blk, hi, blk):           # block b0 is the same whatever the sharding
-        g = torch.Generator(device=dev).manual_seed(1000 + b0 // blk)
-        x = torch.randn((blk, DIM), device=dev, generator=g)
-        s, e = max(lo, b0), min(hi, b0 + blk)
-        store.append(x[s - b0: e - b0], _lib.NORM_PLAIN)  # kernel (a): L2-normalise on ingest
-    scanner = engine.Scanner(dev)
     elem = 2 if two_stage else 4
+    # L2 rule: the rows a step scans must not be L2-resident from the step before.  A shard larger than
+    # 1.5 x L2 evicts itself; a smaller one (8-way sharding: 128 MB) is kept in several identical copies
+    # and consecutive steps scan different copies, so that the working set between two uses of a copy
+    # exceeds L2 (126 MB) several times — no flush kernel inside the loop, one timing method for every N.
+    shard_bytes = (hi - lo) * DIM * elem
+    n_copies = 1 if shard_bytes > 190e6 else int(500e6 // max(shard_bytes, 1)) + 1
+    stores = []
+    for _c in range(n_copies):
+        st_c = engine.DeviceStore(DIM, dev, keep_fp32=True, keep_bf16=two_stage, capacity=hi - lo)
+        blk = 1 << 16
+        for b0 in range(lo // blk * blk, hi, blk):           # block b0 is the same whatever the sharding
+            g = torch.Generator(device=dev).manual_seed(1000 + b0 // blk)
+            x = torch.randn((blk, DIM), device=dev, generator=g)
+            s, e = max(lo, b0), min(hi, b0 + blk)
+            st_c.append(x[s - b0: e - b0], _lib.NORM_PLAIN)  # kernel (a): L2-normalise on ingest
+        stores.append(st_c)
+    store = stores[0]
+    scanner = engine.Scanner(dev)
     last = {"bad": None}            # certificate of the most recent local search ([b] int32 on the device)
+    cur = {"i": 0}                  # which copy of the shard the next search scans
 
     def local_search(q, k):
+        st_i = stores[cur["i"]]
         if two_stage:
-            s, r, bad = two_stage_search(scanner, store, q, k, args.path)
+            s, r, bad = two_stage_search(scanner, st_i, q, k, args.path)
             last["bad"] = bad
             return s, r
-        return scanner.scan(store.f32, store.n, DIM, q, k, _lib.NORM_EPS, args.path)
+        return scanner.scan(st_i.f32, st_i.n, DIM, q, k, _lib.NORM_EPS, args.path)
 
     searcher = ShardedSearcher(local_search, N_ROWS, device=dev)
     gq = torch.Generator(device="cpu").manual_seed(7)
-    flush = None
-    if (hi - lo) * DIM * elem <= 300e6:
-        flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
     def barrier():
         torch.cuda.synchronize()
@@ -213,53 +222,52 @@ def run_ours(args):
         path = scanner.last_path
         barrier()
         # the serving path for a fixed batch shape: the whole step captured once as a CUDA graph
-        graphed = None
+        graphs = None
         if not args.no_graph:
             try:
                 from video_quierer_b200.graphs import GraphedSearch
-                graphed = GraphedSearch(lambda qq: search(qq, K_TOP) + (last["bad"],), B, DIM, dev)
-                graphed.q.copy_(dev_q)
+                graphs = []
+                for c in range(n_copies):                  # one captured step per copy of the shard
+                    cur["i"] = c
+                    gs = GraphedSearch(lambda qq: search(qq, K_TOP) + (last["bad"],), B, DIM, dev)
+                    gs.q.copy_(dev_q)
+                    graphs.append(gs)
             except Exception as e:  # noqa: BLE001 — e.g. a collective that refuses capture: run eagerly
                 print(f"[bench] CUDA graph capture unavailable ({type(e).__name__}: {e}); eager launches", file=sys.stderr)
-                graphed = None
+                graphs = None
             barrier()
+        graphed = graphs[0] if graphs else None
+        step_no = [0]
 
         def step_device():
-            if graphed is not None:
-                graphed.graph.replay()
-                return graphed.out
+            c = step_no[0] % n_copies
+            step_no[0] += 1
+            if graphs is not None:
+                graphs[c].graph.replay()
+                return graphs[c].out
+            cur["i"] = c
             return search(dev_q, K_TOP)
 
         # -- timed region 1: device-resident queries, CUDA events on the launch stream
-        if flush is None:
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            for _ in range(steps):
-                step_device()
-            e1.record()
-            barrier()
-            dev_ms = e0.elapsed_time(e1)
-        else:
-            # shard small enough to sit in L2: a 256 MB buffer is overwritten before every step, outside
-            # the event pair of the step; all steps are queued first and synchronised once, so the GPU
-            # is never idle waiting for the host between the flush and the step
-            evs = []
-            for _ in range(steps):
-                flush.zero_()
-                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                e0.record()
-                step_device()
-                e1.record()
-                evs.append((e0, e1))
-            barrier()
-            dev_ms = sum(a.elapsed_time(b) for a, b in evs)
+        # steps are queued back to back; with a collective inside the step the queue is drained every
+        # `sync_every` steps (measured on 8 GPUs: an unbounded queue of graph replays that contain an NCCL
+        # all-gather runs 3x slower per step than the same replays with a shallow queue)
+        sync_every = int(os.environ.get("VQ_BENCH_SYNC_EVERY", "0")) or (steps if world == 1 else 4)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            step_device()
+            if (i + 1) % sync_every == 0 and i + 1 < steps:
+                torch.cuda.synchronize()
+        e1.record()
+        barrier()
+        dev_ms = e0.elapsed_time(e1)
         # -- dominant kernel alone: the library's own events around the scan kernel
         lib.vq_profile_enable(1)
         kern = []
-        for _ in range(min(steps, 20)):
-            if flush is not None:
-                flush.zero_()
-            scanner.scan(store.bf16 if two_stage else store.f32, store.n, DIM, dev_q,
+        for it_k in range(min(steps, 20)):
+            st_k = stores[it_k % n_copies]
+            scanner.scan(st_k.bf16 if two_stage else st_k.f32, st_k.n, DIM, dev_q,
                          (int(os.environ.get("VQ_KCAND", 0)) or 32) if two_stage else K_TOP, _lib.NORM_EPS, args.path)
             kern.append(lib.vq_profile_last_kernel_ms())
         lib.vq_profile_enable(0)
@@ -274,9 +282,12 @@ def run_ours(args):
             n_fallback = [0]
 
             def step_e2e():
-                if graphed is not None:
-                    res = graphed(host_q)                      # H2D of this step's inputs + one graph launch
-                    q = graphed.q
+                c = step_no[0] % n_copies
+                step_no[0] += 1
+                cur["i"] = c
+                if graphs is not None:
+                    res = graphs[c](host_q)                    # H2D of this step's inputs + one graph launch
+                    q = graphs[c].q
                 else:
                     q = host_q.to(dev, non_blocking=True)      # H2D of this step's inputs
                     res = search(q, K_TOP) + (last["bad"],)
@@ -290,7 +301,7 @@ def run_ours(args):
                     # queries whose two-stage result could not be certified: collect pass (+ fp32 scan on
                     # overflow), inside the timing
                     idx = torch.nonzero(out_bad).flatten()
-                    sf, rf = resolve_uncertified(scanner, store, q, K_TOP, idx.to(dev), s)
+                    sf, rf = resolve_uncertified(scanner, stores[c], q, K_TOP, idx.to(dev), s)
                     out_scores[idx] = sf.cpu()
                     out_rows[idx] = rf.cpu().to(out_rows.dtype)
                     n_fallback[0] += len(idx)
