@@ -202,7 +202,7 @@ def run_ours(args):
             return s, r
         return scanner.scan(st_i.f32, st_i.n, DIM, q, k, _lib.NORM_EPS, args.path)
 
-    searcher = ShardedSearcher(local_search, N_ROWS, device=dev)
+    searcher = ShardedSearcher(local_search, N_ROWS, device=dev, exchange=args.exchange)
     gq = torch.Generator(device="cpu").manual_seed(7)
 
     def barrier():
@@ -319,6 +319,7 @@ def run_ours(args):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dev_ms, e2e_ms = (float(v) for v in t.cpu())
         unc = int(last["bad"].sum().item()) if last["bad"] is not None else 0
+        searcher.check()                                # a peer-exchange wait that timed out voids the run
         return {"B": B, "dev_ms": dev_ms, "e2e_ms": e2e_ms, "kernel_ms": kmed, "launches": launches, "path": path,
                 "graph": graphed is not None, "uncertified": unc}
 
@@ -364,7 +365,9 @@ def run_ours(args):
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": main["dev_ms"] / args.steps,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "bf16 scan + f32 rescore" if two_stage else "f32", "data": "synthetic",
-            "config": dict(_config(B, world, main["path"], two_stage), launch="cuda-graph" if main["graph"] else "eager"),
+            "config": dict(_config(B, world, main["path"], two_stage), launch="cuda-graph" if main["graph"] else "eager",
+                           **({"exchange": "peer-memory push + merge kernel over NVLink (vq_peer_exchange_merge)"
+                               if searcher._peer is not None else "nccl all-gather + vq_topk_merge"} if world > 1 else {})),
             "clocks": clocks.summary(),
             "e2e": {"value": B * args.steps / (main["e2e_ms"] * 1e-3), "unit": "queries/s",
                     "h2d_bytes_per_step": B * DIM * 4, "d2h_bytes_per_step": B * K_TOP * (12 if world > 1 else 8) + (B * 4 if two_stage else 0)},
@@ -405,6 +408,8 @@ def main():
                     help="query batch of the headline line (BASELINE config 2 names 1, 32 and 1024; the others are swept)")
     ap.add_argument("--path", default="auto")
     ap.add_argument("--impl", default="ours")
+    ap.add_argument("--exchange", default="auto", choices=["auto", "peer", "collective"],
+                    help="N > 1: fused NVLink peer-memory push+merge kernel (auto/peer) or NCCL all-gather + merge")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-sweep", action="store_true", help="skip the batch 1/32/1024 sweep")
     ap.add_argument("--no-hnsw", action="store_true", help="skip the HNSW (BASELINE config 3) leg")

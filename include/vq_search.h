@@ -103,6 +103,38 @@ int vq_topk_merge(const float* scores, const int32_t* rows, int g, int64_t g_str
                   const int64_t* shard_offsets, int k_out,
                   float* out_scores, int64_t* out_rows, void* stream);
 
+/* Shard/merge over NVLink peer memory: ONE kernel per rank replaces ncclAllGather of the per-GPU
+ * top-k + vq_topk_merge (the reference is single-process and has no counterpart).
+ * [kernel: peer_exchange_merge]
+ * Every rank owns an exchange window (header + arrival flags + double-buffered candidate slots for
+ * `world` ranks x b_max queries x k_max entries) that all peers map through CUDA IPC:
+ *   vq_peer_window_create   cudaMalloc + zero + IPC handle (VQ_PEER_HANDLE_BYTES bytes, host memory) —
+ *                           the handles are exchanged by the host (e.g. torch.distributed.all_gather_object)
+ *   vq_peer_window_open     maps a PEER's window into this process (enables peer access lazily)
+ *   vq_peer_window_close / vq_peer_window_destroy / vq_peer_window_status (host copy of epoch + error word)
+ * vq_peer_exchange_merge is a collective over the ranks sharing the windows: all ranks call it with the
+ * same b, k, k_out, in the same order, one stream per window set.  It pushes this rank's local candidates
+ *   scores / rows [b, k] (best first per query; row < 0 = empty slot, local row numbers)
+ * into every peer's window with plain stores over NVLink, waits (per CTA, acquire flags, no barrier) for
+ * the peers' entries of the same queries and merges world*k -> k_out (score desc, global row asc):
+ *   windows_dev   device array of `world` window base pointers, index = rank (own window included)
+ *   shard_offsets [world] int64 added to local rows (may be NULL)
+ *   out_scores [b, k_out] fp32, out_rows [b, k_out] int64 — identical on every rank
+ *   out_status    optional device int32, set to 1 if a peer did not arrive within VQ_PEER_TIMEOUT_MS
+ *                 (default 10 s; the error is also sticky in the window header)
+ * The epoch counter lives in the window, so the launch can be captured in a CUDA graph and replayed. */
+#define VQ_PEER_HANDLE_BYTES 64
+size_t vq_peer_window_bytes(int world, int b_max, int k_max);
+int vq_peer_window_create(size_t bytes, void** local_ptr, unsigned char* handle_out_host);
+int vq_peer_window_open(const unsigned char* handle_host, void** peer_ptr);
+int vq_peer_window_close(void* peer_ptr);
+int vq_peer_window_destroy(void* local_ptr);
+int vq_peer_window_status(const void* local_ptr, uint32_t* epoch_host, uint32_t* error_host);
+int vq_peer_exchange_merge(const void* windows_dev, int world, int rank, int b_max, int k_max,
+                           const float* scores, const int32_t* rows, int b, int k,
+                           const int64_t* shard_offsets, int k_out,
+                           float* out_scores, int64_t* out_rows, int32_t* out_status, void* stream);
+
 /* Exact fp32 re-score of candidate rows (two-stage mode: bf16 scan selects k_cand, this
  * re-scores them from the fp32 shadow store and keeps the best k).     [kernel: rescore_rows]
  *   cand_rows [b, k_cand] int32 (row < 0 ignored); queries [b, ld] fp32 *already normalised*

@@ -29,6 +29,13 @@ SIGNATURES = {
     "vq_scan_workspace_bytes": (_sz, [_i64, _i32, _i32, _i32, _i32, _i32, _i32]),
     "vq_scan_topk": (_i32, [_vp, _i64, _i32, _i32, _i32, _vp, _i32, _i32, _i32, _vp, _vp, _vp, _sz, _i32, _vp]),
     "vq_topk_merge": (_i32, [_vp, _vp, _i32, _i64, _i32, _i32, _vp, _i32, _vp, _vp, _vp]),
+    "vq_peer_window_bytes": (_sz, [_i32, _i32, _i32]),
+    "vq_peer_window_create": (_i32, [_sz, C.POINTER(C.c_void_p), C.c_char_p]),
+    "vq_peer_window_open": (_i32, [C.c_char_p, C.POINTER(C.c_void_p)]),
+    "vq_peer_window_close": (_i32, [_vp]),
+    "vq_peer_window_destroy": (_i32, [_vp]),
+    "vq_peer_window_status": (_i32, [_vp, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
+    "vq_peer_exchange_merge": (_i32, [_vp, _i32, _i32, _i32, _i32, _vp, _vp, _i32, _i32, _vp, _i32, _vp, _vp, _vp, _vp]),
     "vq_profile_enable": (_i32, [_i32]),
     "vq_profile_last_kernel_ms": (C.c_float, []),
     "vq_rescore_topk": (_i32, [_vp, _i64, _i32, _i32, _vp, _i32, _vp, _i32, _i32, _vp, _vp, _vp, _sz, _vp]),

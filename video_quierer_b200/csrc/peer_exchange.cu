@@ -1,0 +1,258 @@
+// Shard/merge layer over NVLink peer memory: ONE kernel per rank replaces
+// `ncclAllGather` of the per-GPU top-k + `topk_merge_kernel`.  The reference has no counterpart
+// (single process).
+//
+// Every rank owns an exchange *window* in its HBM that all peers have mapped (CUDA IPC, NVSwitch):
+//
+//   [ header 256 B | flags u32 [world][ctas_max] | entries int2 [2 parities][world][b_max][k_max] ]
+//
+// One launch = one epoch e (kept in the window header, so a CUDA-graph replay needs no new arguments).
+// CTA c serves queries [8c, 8c+8):
+//   push   its k local (score,row) pairs per query are stored straight into EVERY peer's window
+//          (slot [e&1][my rank], 8-byte stores in 8*k*8-byte runs), then one release store at system
+//          scope of e into flags[my rank][c] of that peer;
+//   wait   `world` threads poll the CTA's own flags (acquire, system scope) until every rank's
+//          entries for these 8 queries have landed — no grid-wide or cross-rank barrier, a CTA only
+//          depends on the same CTA of its peers;
+//   merge  one warp per query: the world sorted lists are staged in shared memory and merged by
+//          repeated head selection (score desc, global row asc — the engine's order), shard offsets
+//          added, global rows written as int64.
+// Two parities suffice: a peer can start epoch e+2 only after all my CTAs pushed e+1, i.e. after all
+// my CTAs finished reading epoch e.  A wait that exceeds the timeout (a peer that never launched) sets
+// the error word of the header and *out_status instead of hanging the GPU.
+#include <stdlib.h>
+#include <string.h>
+
+#include "vq_common.cuh"
+
+namespace {
+
+constexpr int kQpc = 8;              // queries per CTA = warps per CTA
+constexpr int kThreads = kQpc * 32;
+constexpr size_t kHeaderBytes = 256;
+constexpr int kMaxWorld = 32;
+
+struct PeerHeader {
+    unsigned epoch;      // last completed epoch of THIS rank
+    unsigned done;       // CTAs of the running epoch that have finished
+    unsigned error;      // sticky: a wait timed out
+    unsigned pad;
+};
+
+__host__ __device__ inline size_t align256(size_t v) { return (v + 255) / 256 * 256; }
+__host__ __device__ inline int ctas_for(int b) { return (b + kQpc - 1) / kQpc; }
+__host__ __device__ inline size_t flags_bytes(int world, int b_max) { return align256((size_t)world * ctas_for(b_max) * 4); }
+
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+
+__global__ void __launch_bounds__(kThreads)
+peer_exchange_merge_kernel(void* const* __restrict__ windows, int world, int rank, int b_max, int k_max,
+                           const float* __restrict__ scores, const int* __restrict__ rows, int b, int k,
+                           const long long* __restrict__ offsets, int k_out,
+                           float* __restrict__ out_scores, long long* __restrict__ out_rows,
+                           int* __restrict__ out_status, unsigned long long timeout_ns) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    int2* staged = reinterpret_cast<int2*>(smem_raw);                     // [kQpc][world][k]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, cta = blockIdx.x;
+    unsigned char* mine = static_cast<unsigned char*>(windows[rank]);
+    PeerHeader* hdr = reinterpret_cast<PeerHeader*>(mine);
+    const unsigned e = *reinterpret_cast<volatile unsigned*>(&hdr->epoch) + 1u;
+    const int par = (int)(e & 1u);
+    const int ctas_max = ctas_for(b_max);
+    const size_t data_off = kHeaderBytes + flags_bytes(world, b_max);
+    const int q0 = cta * kQpc;
+    const int nq = min(kQpc, b - q0);
+
+    // ---- push: this CTA's entries into every window (own rank included), peers visited in a
+    // rank-rotated order so that the NVLink traffic of a step is spread over all ports at once
+    const int per_peer = nq * k;
+    for (int i = tid; i < world * per_peer; i += kThreads) {
+        const int p = i / per_peer, x = i - p * per_peer;
+        const int ql = x / k, j = x - ql * k;
+        int pp = p + rank;
+        if (pp >= world) pp -= world;
+        const size_t src = (size_t)(q0 + ql) * k + j;
+        const int2 v = make_int2(__float_as_int(scores[src]), rows[src]);
+        int2* dst = reinterpret_cast<int2*>(static_cast<unsigned char*>(windows[pp]) + data_off) +
+                    (((size_t)par * world + rank) * b_max + (q0 + ql)) * k_max + j;
+        *dst = v;
+    }
+    __syncthreads();
+    if (tid < world) {
+        int pp = tid + rank;
+        if (pp >= world) pp -= world;
+        unsigned* flag = reinterpret_cast<unsigned*>(static_cast<unsigned char*>(windows[pp]) + kHeaderBytes) +
+                         (size_t)rank * ctas_max + cta;
+        __threadfence_system();
+        st_release_sys(flag, e);
+    }
+
+    // ---- wait for the same CTA of every rank
+    if (tid < world) {
+        const unsigned* flag = reinterpret_cast<const unsigned*>(mine + kHeaderBytes) + (size_t)tid * ctas_max + cta;
+        const unsigned long long t0 = globaltimer_ns();
+        unsigned spins = 0;
+        while ((int)(ld_acquire_sys(flag) - e) < 0) {
+            if ((++spins & 63u) == 0 && globaltimer_ns() - t0 > timeout_ns) {
+                atomicExch(&hdr->error, 1u);
+                if (out_status) *out_status = 1;
+                break;
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- merge: warp `warp` owns query q0 + warp
+    if (warp < nq) {
+        const int q = q0 + warp;
+        int2* mys = staged + (size_t)warp * world * k;
+        const int2* data = reinterpret_cast<const int2*>(mine + data_off);
+        for (int i = lane; i < world * k; i += 32) {
+            const int g = i / k, j = i - g * k;
+            mys[i] = __ldcg(data + (((size_t)par * world + g) * b_max + q) * k_max + j);
+        }
+        __syncwarp();
+        int head = 0;
+        float s = VQ_NEG_INF;
+        long long r = LLONG_MAX;
+        const long long off = (lane < world && offsets) ? offsets[lane] : 0;
+        auto load_head = [&]() {
+            s = VQ_NEG_INF;
+            r = LLONG_MAX;
+            if (lane < world && head < k) {
+                const int2 v = mys[lane * k + head];
+                if (v.y >= 0) { s = __int_as_float(v.x); r = (long long)v.y + off; }
+            }
+        };
+        load_head();
+        for (int o = 0; o < k_out; ++o) {
+            float bs = s;
+            long long br = r;
+            int bl = lane;
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) {
+                const float os = __shfl_xor_sync(0xffffffffu, bs, d);
+                const long long orr = __shfl_xor_sync(0xffffffffu, br, d);
+                const int ol = __shfl_xor_sync(0xffffffffu, bl, d);
+                const bool take = (os > bs) || (os == bs && (orr < br || (orr == br && ol < bl)));
+                if (take) { bs = os; br = orr; bl = ol; }
+            }
+            if (lane == bl) {
+                const bool valid = (r != LLONG_MAX);
+                out_scores[(size_t)q * k_out + o] = valid ? s : VQ_NEG_INF;
+                out_rows[(size_t)q * k_out + o] = valid ? r : -1ll;
+                if (valid) { ++head; load_head(); }
+            }
+        }
+    }
+
+    // ---- the last CTA closes the epoch (read by the next launch on this stream)
+    __syncthreads();
+    if (tid == 0) {
+        const unsigned prev = atomicAdd(&hdr->done, 1u);
+        if (prev == gridDim.x - 1) {
+            hdr->done = 0;
+            __threadfence();
+            hdr->epoch = e;
+        }
+    }
+}
+
+unsigned long long exchange_timeout_ns() {
+    static const unsigned long long t =
+        getenv("VQ_PEER_TIMEOUT_MS") ? strtoull(getenv("VQ_PEER_TIMEOUT_MS"), nullptr, 10) * 1000000ull : 10000000000ull;
+    return t;
+}
+
+}  // namespace
+
+extern "C" {
+
+size_t vq_peer_window_bytes(int world, int b_max, int k_max) {
+    if (world <= 0 || b_max <= 0 || k_max <= 0) return 0;
+    return kHeaderBytes + flags_bytes(world, b_max) + align256((size_t)2 * world * b_max * k_max * sizeof(int2));
+}
+
+int vq_peer_window_create(size_t bytes, void** local_ptr, unsigned char* handle_out) {
+    VQ_CHECK_ARG(bytes >= kHeaderBytes && local_ptr && handle_out, "vq_peer_window_create: bad arguments");
+    void* p = nullptr;
+    VQ_CUDA(cudaMalloc(&p, bytes));
+    VQ_CUDA(cudaMemset(p, 0, bytes));
+    VQ_CUDA(cudaDeviceSynchronize());
+    cudaIpcMemHandle_t h;
+    cudaError_t e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) {
+        cudaFree(p);
+        vq_set_error("cudaIpcGetMemHandle failed: %s", cudaGetErrorString(e));
+        return VQ_ECUDA;
+    }
+    static_assert(sizeof(cudaIpcMemHandle_t) == VQ_PEER_HANDLE_BYTES, "handle size");
+    memcpy(handle_out, &h, sizeof(h));
+    *local_ptr = p;
+    return VQ_OK;
+}
+
+int vq_peer_window_open(const unsigned char* handle, void** peer_ptr) {
+    VQ_CHECK_ARG(handle && peer_ptr, "vq_peer_window_open: bad arguments");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, sizeof(h));
+    VQ_CUDA(cudaIpcOpenMemHandle(peer_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return VQ_OK;
+}
+
+int vq_peer_window_close(void* peer_ptr) {
+    if (peer_ptr) VQ_CUDA(cudaIpcCloseMemHandle(peer_ptr));
+    return VQ_OK;
+}
+
+int vq_peer_window_destroy(void* local_ptr) {
+    if (local_ptr) VQ_CUDA(cudaFree(local_ptr));
+    return VQ_OK;
+}
+
+int vq_peer_window_status(const void* local_ptr, uint32_t* epoch_host, uint32_t* error_host) {
+    VQ_CHECK_ARG(local_ptr, "vq_peer_window_status: null window");
+    PeerHeader h;
+    VQ_CUDA(cudaMemcpy(&h, local_ptr, sizeof(h), cudaMemcpyDeviceToHost));
+    if (epoch_host) *epoch_host = h.epoch;
+    if (error_host) *error_host = h.error;
+    return VQ_OK;
+}
+
+int vq_peer_exchange_merge(const void* windows_dev, int world, int rank, int b_max, int k_max,
+                           const float* scores, const int32_t* rows, int b, int k,
+                           const int64_t* shard_offsets, int k_out,
+                           float* out_scores, int64_t* out_rows, int32_t* out_status, void* stream) {
+    VQ_CHECK_ARG(windows_dev && scores && rows && out_scores && out_rows, "vq_peer_exchange_merge: null pointer");
+    VQ_CHECK_ARG(world >= 1 && world <= kMaxWorld && rank >= 0 && rank < world, "world=%d rank=%d out of range (world <= %d)",
+                 world, rank, kMaxWorld);
+    VQ_CHECK_ARG(b >= 0 && b <= b_max && k >= 1 && k <= k_max, "b=%d k=%d exceed the window (b_max=%d k_max=%d)", b, k, b_max, k_max);
+    VQ_CHECK_ARG(k_out >= 1, "k_out=%d must be >= 1", k_out);
+    if (b == 0) return VQ_OK;
+    const size_t smem = (size_t)kQpc * world * k * sizeof(int2);
+    VQ_CHECK_ARG(smem <= 200 * 1024, "world*k=%d too large for the merge stage", world * k);
+    static bool attr_done = false;
+    if (!attr_done) {
+        VQ_CUDA(cudaFuncSetAttribute(peer_exchange_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attr_done = true;
+    }
+    peer_exchange_merge_kernel<<<ctas_for(b), kThreads, smem, (cudaStream_t)stream>>>(
+        (void* const*)windows_dev, world, rank, b_max, k_max, scores, rows, b, k,
+        (const long long*)shard_offsets, k_out, out_scores, (long long*)out_rows, out_status, exchange_timeout_ns());
+    VQ_LAUNCH_CHECK("peer_exchange_merge_kernel");
+    return VQ_OK;
+}
+
+}  // extern "C"

@@ -3,6 +3,11 @@
 The frame-embedding store is row-sharded: rank r owns the contiguous rows
 ``[r*ceil(N/G), min(N, (r+1)*ceil(N/G)))``.  A search is
   1. every rank scans its shard for a local top-k   (vq_scan_topk / vq_hnsw_search),
+  2+3. on CUDA ranks of one node (`exchange="peer"`, the default there): ONE fused kernel per rank
+     (`peer.PeerExchange`, vq_peer_exchange_merge) stores the local candidates straight into every
+     peer's HBM over NVLink, waits per CTA for the same queries of the other ranks and merges
+     ``g*k -> k`` with the shard offsets added — no NCCL call on the data path;
+     otherwise (`exchange="collective"`: gloo, several nodes, or peer mapping unavailable):
   2. ONE all-gather of the packed ``[scores | rows]`` candidate block (8*b*k bytes per rank,
      latency-bound on NVSwitch),
   3. an on-device merge ``g*k -> k`` that adds the shard offsets (vq_topk_merge reads the
@@ -41,9 +46,18 @@ class ShardedSearcher:
     """Row-sharded exact/ANN search across the ranks of a process group."""
 
     def __init__(self, local_search: Callable, n_total: int, group=None,
-                 merge: Optional[Callable] = None, device=None):
+                 merge: Optional[Callable] = None, device=None, exchange: str = "auto"):
         """local_search(queries[b,dim], k) -> (scores [b,k] fp32, rows [b,k] int32) on this
-        rank's shard (local row numbers, -1 = empty slot)."""
+        rank's shard (local row numbers, -1 = empty slot).
+        exchange: "peer" (fused NVLink push + merge kernel; raises if the windows cannot be mapped),
+        "collective" (all-gather + merge) or "auto" (peer on CUDA ranks with the NCCL backend and no
+        injected merge, falling back to the collective — with a message on stderr — if the IPC
+        mapping is refused)."""
+        if exchange not in ("auto", "peer", "collective"):
+            raise ValueError(f"exchange must be auto|peer|collective, got {exchange!r}")
+        self.exchange = exchange
+        self._peer = None
+        self._peer_failed = False
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
@@ -67,11 +81,54 @@ class ShardedSearcher:
         rows = gathered[:, 1]
         return self._scanner.merge(scores, rows, self._offsets, k_out, g_stride=2 * b * k)
 
+    def _peer_exchange(self, s: torch.Tensor, r: torch.Tensor):
+        """The PeerExchange serving [b,k] candidates, (re)built collectively when the shape outgrows it;
+        None = use the collective route."""
+        if self.exchange == "collective" or self._merge is not None or self.world == 1 or not s.is_cuda:
+            return None
+        if self.exchange == "auto" and (self._peer_failed or dist.get_backend(self.group) != "nccl"):
+            return None
+        b, k = s.shape
+        if self._peer is not None and self._peer.fits(b, k):
+            return self._peer
+        if torch.cuda.is_current_stream_capturing():
+            raise RuntimeError("peer exchange windows must be sized before CUDA-graph capture (run one eager search)")
+        from .peer import PeerExchange
+        try:
+            if self._peer is not None:
+                old, self._peer = self._peer, None
+                b, k = max(b, old.b_max), max(k, old.k_max)
+                old.close()
+            self._peer = PeerExchange(s.device, self.group, b_max=b, k_max=k)
+            if self._offsets is None:
+                self._offsets = torch.tensor(shard_offsets(self.n_total, self.world), dtype=torch.int64, device=s.device)
+        except Exception as e:  # noqa: BLE001 — IPC refused (container policy, no P2P): all ranks see the same
+            if self.exchange == "peer":
+                raise
+            import sys
+            print(f"[sharded] peer windows unavailable ({type(e).__name__}: {e}); using all-gather + merge", file=sys.stderr)
+            self._peer_failed = True
+            self._peer = None
+        return self._peer
+
+    def check(self):
+        """Raises if the peer exchange recorded a timeout (synchronises); no-op on the collective route."""
+        if self._peer is not None:
+            self._peer.check()
+
+    def close(self):
+        if self._peer is not None:
+            self._peer.close()
+            self._peer = None
+
     def search(self, queries: torch.Tensor, k: int):
         """Returns (scores [b,k] fp32, global rows [b,k] int64), identical on every rank."""
         s, r = self.local_search(queries, k)
         if self.world == 1 and self._merge is None:
             return s, r.to(torch.int64)                       # one shard: nothing to exchange or merge
+        px = self._peer_exchange(s, r)
+        if px is not None:
+            return px.exchange_merge(s.contiguous(), r.contiguous().to(torch.int32), self._offsets, k)
         packed = pack_candidates(s, r)                        # [2, b, k] int32
         if self.world == 1:
             gathered = packed[None]
