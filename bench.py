@@ -23,6 +23,7 @@ video_search_overhaul.py:40-64; the Python reference itself cannot travel to the
 from __future__ import annotations
 
 import argparse
+import contextlib
 import json
 import os
 import subprocess
@@ -190,19 +191,31 @@ def run_ours(args):
             st_c.append(x[s - b0: e - b0], _lib.NORM_PLAIN)  # kernel (a): L2-normalise on ingest
         stores.append(st_c)
     store = stores[0]
-    scanner = engine.Scanner(dev)
-    last = {"bad": None}            # certificate of the most recent local search ([b] int32 on the device)
-    cur = {"i": 0}                  # which copy of the shard the next search scans
 
-    def local_search(q, k):
-        st_i = stores[cur["i"]]
-        if two_stage:
-            s, r, bad = two_stage_search(scanner, st_i, q, k, args.path)
-            last["bad"] = bad
-            return s, r
-        return scanner.scan(st_i.f32, st_i.n, DIM, q, k, _lib.NORM_EPS, args.path)
+    # ---- search lanes: `depth` steps in flight, each lane with its own stream, workspace and (N > 1)
+    # exchange windows; the store copies are shared.  Depth 1 = strictly one step after the other.
+    class Lane:
+        def __init__(self, idx):
+            self.idx = idx
+            self.stream = torch.cuda.Stream(dev) if args.pipeline > 1 else None
+            self.scanner = engine.Scanner(dev)
+            self.bad = None            # certificate of the lane's most recent local search ([b] int32, device)
+            self.copy = 0              # which copy of the shard the next search scans
+            self.searcher = ShardedSearcher(self.local_search, N_ROWS, device=dev, exchange=args.exchange)
 
-    searcher = ShardedSearcher(local_search, N_ROWS, device=dev, exchange=args.exchange)
+        def local_search(self, q, k):
+            st_i = stores[self.copy]
+            if two_stage:
+                s, r, self.bad = two_stage_search(self.scanner, st_i, q, k, args.path)
+                return s, r
+            return self.scanner.scan(st_i.f32, st_i.n, DIM, q, k, _lib.NORM_EPS, args.path)
+
+        def search(self, q, k):
+            # one shard: the local search IS the answer (int32 rows); several: exchange + merge (int64 rows)
+            return self.local_search(q, k) if world == 1 else self.searcher.search(q, k)
+
+    lanes = [Lane(0)]
+    scanner = lanes[0].scanner
     gq = torch.Generator(device="cpu").manual_seed(7)
 
     def barrier():
@@ -211,117 +224,180 @@ def run_ours(args):
             dist.barrier()
             torch.cuda.synchronize()
 
+    def on(stream):
+        return torch.cuda.stream(stream) if stream is not None else contextlib.nullcontext()
+
     def measure(B, steps, warmup, with_e2e):
         host_q = torch.randn((B, DIM), generator=gq).pin_memory()
         dev_q = host_q.to(dev)
-        # one shard: the local search IS the answer (int32 rows); several: all-gather + merge (int64 rows)
-        search = (lambda qq, kk: local_search(qq, kk)) if world == 1 else searcher.search
         for _ in range(max(warmup, 3)):
-            search(dev_q, K_TOP)
-        launches = scanner.last_launches + (1 if world > 1 else 0)   # + merge of the shard/merge layer
+            lanes[0].search(dev_q, K_TOP)
+        launches = scanner.last_launches + (1 if world > 1 else 0)   # + exchange/merge of the shard layer
         path = scanner.last_path
         barrier()
+        # pipelining needs lane-private exchange windows; the NCCL route serialises on one communicator
+        depth = args.pipeline if (world == 1 or lanes[0].searcher._peer is not None) else 1
+        while len(lanes) < depth:
+            lanes.append(Lane(len(lanes)))
+            lanes[-1].search(dev_q, K_TOP)
+        barrier()
+        # slot j = (lane j % depth, store copy j % n_copies); consecutive steps take consecutive slots
+        n_slots = -(-max(n_copies, depth) // depth) * depth
+        slots = [(lanes[j % depth], j % n_copies) for j in range(n_slots)]
         # the serving path for a fixed batch shape: the whole step captured once as a CUDA graph
         graphs = None
         if not args.no_graph:
             try:
                 from video_quierer_b200.graphs import GraphedSearch
                 graphs = []
-                for c in range(n_copies):                  # one captured step per copy of the shard
-                    cur["i"] = c
-                    gs = GraphedSearch(lambda qq: search(qq, K_TOP) + (last["bad"],), B, DIM, dev)
+                for ln, c in slots:
+                    ln.copy = c
+                    gs = GraphedSearch(lambda qq, ln=ln: ln.search(qq, K_TOP) + (ln.bad,), B, DIM, dev, stream=ln.stream)
                     gs.q.copy_(dev_q)
                     graphs.append(gs)
             except Exception as e:  # noqa: BLE001 — e.g. a collective that refuses capture: run eagerly
                 print(f"[bench] CUDA graph capture unavailable ({type(e).__name__}: {e}); eager launches", file=sys.stderr)
                 graphs = None
             barrier()
-        graphed = graphs[0] if graphs else None
         step_no = [0]
+        cur_stream = torch.cuda.current_stream(dev)
+
+        def fork():
+            for ln in lanes[:depth]:
+                if ln.stream is not None:
+                    ln.stream.wait_stream(cur_stream)
+
+        def join():
+            for ln in lanes[:depth]:
+                if ln.stream is not None:
+                    cur_stream.wait_stream(ln.stream)
 
         def step_device():
-            c = step_no[0] % n_copies
+            j = step_no[0] % n_slots
             step_no[0] += 1
             if graphs is not None:
-                graphs[c].graph.replay()
-                return graphs[c].out
-            cur["i"] = c
-            return search(dev_q, K_TOP)
+                return graphs[j].replay()
+            ln, c = slots[j]
+            ln.copy = c
+            with on(ln.stream):
+                return ln.search(dev_q, K_TOP)
 
-        # -- timed region 1: device-resident queries, CUDA events on the launch stream
+        # -- dominant kernel alone: the library's own events around the scan kernel, sampled right before
+        # AND right after the timed region (clocks under a long tensor-bound run sag with the power cap)
+        kern = []
+
+        def sample_kernel(times):
+            lib.vq_profile_enable(1)
+            for it_k in range(times):
+                st_k = stores[it_k % n_copies]
+                scanner.scan(st_k.bf16 if two_stage else st_k.f32, st_k.n, DIM, dev_q,
+                             (int(os.environ.get("VQ_KCAND", 0)) or 32) if two_stage else K_TOP, _lib.NORM_EPS, args.path)
+                kern.append(lib.vq_profile_last_kernel_ms())
+            lib.vq_profile_enable(0)
+
+        sample_kernel(min(steps, 10))
+        barrier()
+        # -- timed region 1: device-resident queries, CUDA events on the launch stream (the lanes fork from
+        # it after the first event and join it before the second)
         # steps are queued back to back; with a collective inside the step the queue is drained every
         # `sync_every` steps (measured on 8 GPUs: an unbounded queue of graph replays that contain an NCCL
         # all-gather runs 3x slower per step than the same replays with a shallow queue)
-        sync_every = int(os.environ.get("VQ_BENCH_SYNC_EVERY", "0")) or (steps if world == 1 else 4)
+        nccl_inside = world > 1 and lanes[0].searcher._peer is None
+        sync_every = int(os.environ.get("VQ_BENCH_SYNC_EVERY", "0")) or (4 if nccl_inside else steps)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
+        fork()
         for i in range(steps):
             step_device()
             if (i + 1) % sync_every == 0 and i + 1 < steps:
                 torch.cuda.synchronize()
+        join()
         e1.record()
         barrier()
         dev_ms = e0.elapsed_time(e1)
-        # -- dominant kernel alone: the library's own events around the scan kernel
-        lib.vq_profile_enable(1)
-        kern = []
-        for it_k in range(min(steps, 20)):
-            st_k = stores[it_k % n_copies]
-            scanner.scan(st_k.bf16 if two_stage else st_k.f32, st_k.n, DIM, dev_q,
-                         (int(os.environ.get("VQ_KCAND", 0)) or 32) if two_stage else K_TOP, _lib.NORM_EPS, args.path)
-            kern.append(lib.vq_profile_last_kernel_ms())
-        lib.vq_profile_enable(0)
+        sample_kernel(min(steps, 10))
         kern = sorted(v for v in kern if v > 0)
         kmed = kern[len(kern) // 2] if kern else None
-        e2e_ms = None
-        if with_e2e:
-            # -- timed region 2: end to end with HOST (pinned) buffers: H2D + search + D2H (+ fallback)
-            out_rows = torch.empty((B, K_TOP), dtype=torch.int64 if world > 1 else torch.int32).pin_memory()
-            out_scores = torch.empty((B, K_TOP), dtype=torch.float32).pin_memory()
-            out_bad = torch.zeros((B,), dtype=torch.int32).pin_memory()
-            n_fallback = [0]
+        torch.cuda.synchronize()
 
-            def step_e2e():
-                c = step_no[0] % n_copies
-                step_no[0] += 1
-                cur["i"] = c
-                if graphs is not None:
-                    res = graphs[c](host_q)                    # H2D of this step's inputs + one graph launch
-                    q = graphs[c].q
-                else:
-                    q = host_q.to(dev, non_blocking=True)      # H2D of this step's inputs
-                    res = search(q, K_TOP) + (last["bad"],)
-                s, r, bad = res
-                out_scores.copy_(s, non_blocking=True)         # D2H of the step's result
-                out_rows.copy_(r, non_blocking=True)
-                if bad is not None:
-                    out_bad.copy_(bad, non_blocking=True)      # + its per-query certificate
-                torch.cuda.synchronize()
-                if bad is not None and world == 1 and bool(out_bad.any()):
+        e2e_ms = None
+        n_fallback = [0]
+        if with_e2e:
+            # -- timed region 2: end to end with HOST (pinned) buffers: H2D + search + D2H (+ fallback), every
+            # step.  `depth` steps are in flight: a lane's result is harvested (event wait, certificate check,
+            # exact fallback) right before the lane is reused.
+            class Out:
+                def __init__(self):
+                    self.rows = torch.empty((B, K_TOP), dtype=torch.int64 if world > 1 else torch.int32).pin_memory()
+                    self.scores = torch.empty((B, K_TOP), dtype=torch.float32).pin_memory()
+                    self.bad = torch.zeros((B,), dtype=torch.int32).pin_memory()
+                    self.ev = torch.cuda.Event()
+                    self.pending = None          # (lane, copy, device queries, device scores) of the step in flight
+            outs = [Out() for _ in range(depth)]
+
+            def harvest(o):
+                if o.pending is None:
+                    return
+                ln, c, q, s = o.pending
+                o.pending = None
+                o.ev.synchronize()
+                if ln.bad is not None and world == 1 and bool(o.bad.any()):
                     # queries whose two-stage result could not be certified: collect pass (+ fp32 scan on
                     # overflow), inside the timing
-                    idx = torch.nonzero(out_bad).flatten()
-                    sf, rf = resolve_uncertified(scanner, stores[c], q, K_TOP, idx.to(dev), s)
-                    out_scores[idx] = sf.cpu()
-                    out_rows[idx] = rf.cpu().to(out_rows.dtype)
+                    idx = torch.nonzero(o.bad).flatten()
+                    with on(ln.stream):
+                        sf, rf = resolve_uncertified(ln.scanner, stores[c], q, K_TOP, idx.to(dev), s)
+                        o.scores[idx] = sf.cpu()
+                        o.rows[idx] = rf.cpu().to(o.rows.dtype)
                     n_fallback[0] += len(idx)
+
+            def step_e2e():
+                j = step_no[0] % n_slots
+                step_no[0] += 1
+                ln, c = slots[j]
+                o = outs[ln.idx]
+                harvest(o)                                     # the lane's previous step
+                ln.copy = c
+                with on(ln.stream):
+                    if graphs is not None:
+                        res = graphs[j](host_q)                # H2D of this step's inputs + one graph launch
+                        q = graphs[j].q
+                    else:
+                        q = host_q.to(dev, non_blocking=True)  # H2D of this step's inputs
+                        res = ln.search(q, K_TOP) + (ln.bad,)
+                    s, r, bad = res
+                    o.scores.copy_(s, non_blocking=True)       # D2H of the step's result
+                    o.rows.copy_(r, non_blocking=True)
+                    if bad is not None:
+                        o.bad.copy_(bad, non_blocking=True)    # + its per-query certificate
+                    o.ev.record()
+                o.pending = (ln, c, q, s)
+
+            def drain():
+                for o in outs:
+                    harvest(o)
+                torch.cuda.synchronize()
 
             for _ in range(3):
                 step_e2e()
+            drain()
             barrier()
             t0 = time.perf_counter()
+            fork()
             for _ in range(steps):
                 step_e2e()
+            drain()
             barrier()
             e2e_ms = (time.perf_counter() - t0) * 1e3
         t = torch.tensor([dev_ms, e2e_ms or 0.0], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dev_ms, e2e_ms = (float(v) for v in t.cpu())
-        unc = int(last["bad"].sum().item()) if last["bad"] is not None else 0
-        searcher.check()                                # a peer-exchange wait that timed out voids the run
+        unc = max((int(ln.bad.sum().item()) if ln.bad is not None else 0) for ln in lanes[:depth])
+        for ln in lanes:
+            ln.searcher.check()                         # a peer-exchange wait that timed out voids the run
         return {"B": B, "dev_ms": dev_ms, "e2e_ms": e2e_ms, "kernel_ms": kmed, "launches": launches, "path": path,
-                "graph": graphed is not None, "uncertified": unc}
+                "graph": graphs is not None, "uncertified": unc, "depth": depth, "fallbacks": n_fallback[0]}
 
     with ClockSampler(local) as clocks:
         main = measure(args.batch, args.steps, args.warmup, True)
@@ -367,7 +443,8 @@ def run_ours(args):
             "dtype": "bf16 scan + f32 rescore" if two_stage else "f32", "data": "synthetic",
             "config": dict(_config(B, world, main["path"], two_stage), launch="cuda-graph" if main["graph"] else "eager",
                            **({"exchange": "peer-memory push + merge kernel over NVLink (vq_peer_exchange_merge)"
-                               if searcher._peer is not None else "nccl all-gather + vq_topk_merge"} if world > 1 else {})),
+                               if lanes[0].searcher._peer is not None else "nccl all-gather + vq_topk_merge"} if world > 1 else {}),
+                           steps_in_flight=main["depth"]),
             "clocks": clocks.summary(),
             "e2e": {"value": B * args.steps / (main["e2e_ms"] * 1e-3), "unit": "queries/s",
                     "h2d_bytes_per_step": B * DIM * 4, "d2h_bytes_per_step": B * K_TOP * (12 if world > 1 else 8) + (B * 4 if two_stage else 0)},
@@ -410,6 +487,8 @@ def main():
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--exchange", default="auto", choices=["auto", "peer", "collective"],
                     help="N > 1: fused NVLink peer-memory push+merge kernel (auto/peer) or NCCL all-gather + merge")
+    ap.add_argument("--pipeline", type=int, default=2,
+                    help="search steps in flight (each on its own stream with its own workspace / exchange windows)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-sweep", action="store_true", help="skip the batch 1/32/1024 sweep")
     ap.add_argument("--no-hnsw", action="store_true", help="skip the HNSW (BASELINE config 3) leg")

@@ -16,9 +16,11 @@ import torch
 
 
 class GraphedSearch:
-    def __init__(self, fn: Callable, batch: int, dim: int, device, warmup: int = 3):
-        """fn(queries [batch, dim] fp32 device tensor) -> tensor or tuple of tensors."""
+    def __init__(self, fn: Callable, batch: int, dim: int, device, warmup: int = 3, stream=None):
+        """fn(queries [batch, dim] fp32 device tensor) -> tensor or tuple of tensors.
+        stream: the stream the graph is replayed on (None = whatever stream is current at the call)."""
         self.device = torch.device(device)
+        self.stream = stream
         self.q = torch.zeros((batch, dim), dtype=torch.float32, device=self.device)
         side = torch.cuda.Stream(self.device)
         side.wait_stream(torch.cuda.current_stream(self.device))
@@ -31,9 +33,61 @@ class GraphedSearch:
         with torch.cuda.graph(self.graph):
             self.out = fn(self.q)
 
+    def replay(self):
+        if self.stream is None:
+            self.graph.replay()
+        else:
+            with torch.cuda.stream(self.stream):
+                self.graph.replay()
+        return self.out
+
     def __call__(self, queries: torch.Tensor):
         """queries: [batch, dim] fp32, host (pinned for async copy) or device.  The returned tensors
-        are the graph's static outputs: consume or copy them before the next call."""
-        self.q.copy_(queries, non_blocking=True)
-        self.graph.replay()
-        return self.out
+        are the graph's static outputs: consume or copy them before the next call (on `stream`)."""
+        if self.stream is None:
+            self.q.copy_(queries, non_blocking=True)
+        else:
+            with torch.cuda.stream(self.stream):
+                self.q.copy_(queries, non_blocking=True)
+        return self.replay()
+
+
+class PipelinedSearch:
+    """`depth` search lanes, each with its own stream, workspace and captured step; consecutive batches
+    go to consecutive lanes.  A step is one bandwidth/tensor-bound scan between latency-bound kernels
+    (query prep, threshold bootstrap, final selection + re-score, shard exchange): with two batches in
+    flight the head and tail of one overlap the scan of the other.  Every lane needs its OWN scanner
+    (workspace) and, when sharded, its own exchange windows: `make_fn(lane)` must return a step function
+    that shares nothing mutable with the other lanes (the store is read-only and shared)."""
+
+    def __init__(self, make_fn: Callable, batch: int, dim: int, device, depth: int = 2, graph: bool = True):
+        self.device = torch.device(device)
+        self.depth = depth
+        self.streams = [torch.cuda.Stream(self.device) for _ in range(depth)]
+        self.fns = [make_fn(i) for i in range(depth)]
+        self.lanes = [GraphedSearch(self.fns[i], batch, dim, device, stream=self.streams[i]) if graph else None
+                      for i in range(depth)]
+        self.q = [None if graph else torch.zeros((batch, dim), dtype=torch.float32, device=self.device) for _ in range(depth)]
+        self.done = [torch.cuda.Event() for _ in range(depth)]
+        self.n = 0
+
+    def submit(self, queries: torch.Tensor):
+        """Enqueue one batch on the next lane; returns (lane, outputs).  The outputs are valid once
+        `self.done[lane]` has completed and until the lane is used again (depth submissions later)."""
+        lane = self.n % self.depth
+        self.n += 1
+        st = self.streams[lane]
+        st.wait_stream(torch.cuda.current_stream(self.device))
+        if self.lanes[lane] is not None:
+            out = self.lanes[lane](queries)
+        else:
+            with torch.cuda.stream(st):
+                self.q[lane].copy_(queries, non_blocking=True)
+                out = self.fns[lane](self.q[lane])
+        self.done[lane].record(st)
+        return lane, out
+
+    def drain(self):
+        cur = torch.cuda.current_stream(self.device)
+        for st in self.streams:
+            cur.wait_stream(st)
