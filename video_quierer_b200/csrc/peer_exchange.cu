@@ -105,6 +105,7 @@ peer_exchange_merge_kernel(void* const* __restrict__ windows, int world, int ran
         const unsigned long long t0 = globaltimer_ns();
         unsigned spins = 0;
         while ((int)(ld_acquire_sys(flag) - e) < 0) {
+            __nanosleep(spins < 64u ? 40u : 400u);      // a late peer: stop competing with the co-resident scan
             if ((++spins & 63u) == 0 && globaltimer_ns() - t0 > timeout_ns) {
                 atomicExch(&hdr->error, 1u);
                 if (out_status) *out_status = 1;

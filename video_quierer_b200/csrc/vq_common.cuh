@@ -43,6 +43,7 @@ void vq_note_launch(const char* path_or_null, int launches);
 
 int vq_num_sms();
 int vq_pdl_mask();           // bit i set: kernels of PDL class i are launched with the attribute
+int vq_launch_priority(int launch_class);   // CUDA priority of a launch class (0 = default), see api.cu
 
 // Launch with programmatic dependent launch (PDL): the kernel may start while the previous kernel of
 // the stream is still running; it must execute vq_pdl_wait() before touching anything an earlier
@@ -57,8 +58,13 @@ cudaError_t vq_launch_cluster(int pdl_class, int cluster, void (*kernel)(KArgs..
     cfg.blockDim = block;
     cfg.dynamicSmemBytes = smem;
     cfg.stream = stream;
-    cudaLaunchAttribute at[2];
+    cudaLaunchAttribute at[3];
     int na = 0;
+    if (const int prio = vq_launch_priority(pdl_class)) {
+        at[na].id = cudaLaunchAttributePriority;
+        at[na].val.priority = prio;
+        ++na;
+    }
     if ((vq_pdl_mask() >> pdl_class) & 1) {
         at[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         at[na].val.programmaticStreamSerializationAllowed = 1;
