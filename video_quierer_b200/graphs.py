@@ -16,22 +16,38 @@ import torch
 
 
 class GraphedSearch:
-    def __init__(self, fn: Callable, batch: int, dim: int, device, warmup: int = 3, stream=None):
-        """fn(queries [batch, dim] fp32 device tensor) -> tensor or tuple of tensors.
-        stream: the stream the graph is replayed on (None = whatever stream is current at the call)."""
+    def __init__(self, fn: Callable, batch: int, dim: int, device, warmup: int = 3, stream=None, host_io: bool = False):
+        """fn(queries [batch, dim] fp32 device tensor) -> tensor or tuple of tensors (None entries allowed).
+        stream: the stream the graph is replayed on (None = whatever stream is current at the call).
+        host_io: the host<->device copies are part of the captured step — `host_q` (pinned, [batch, dim]) is
+        the request slot the batcher fills, `host_out` the pinned twins of the outputs; one replay = H2D of
+        the queries + search + D2H of the results, with no per-step Python work beyond the launch."""
         self.device = torch.device(device)
         self.stream = stream
         self.q = torch.zeros((batch, dim), dtype=torch.float32, device=self.device)
+        self.host_q = torch.zeros((batch, dim), dtype=torch.float32).pin_memory() if host_io else None
+        self.host_out = None
         side = torch.cuda.Stream(self.device)
         side.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(side):
             for _ in range(max(1, warmup)):               # sizes workspaces, caches tensor maps / attributes
-                fn(self.q)
+                probe = fn(self.q)
         torch.cuda.current_stream(self.device).wait_stream(side)
         torch.cuda.synchronize(self.device)
+        if host_io:                                       # pinned memory cannot be allocated while capturing
+            outs = probe if isinstance(probe, (tuple, list)) else (probe,)
+            self.host_out = tuple(None if o is None else torch.empty(tuple(o.shape), dtype=o.dtype).pin_memory() for o in outs)
+        del probe
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
+            if host_io:
+                self.q.copy_(self.host_q, non_blocking=True)
             self.out = fn(self.q)
+            if host_io:
+                outs = self.out if isinstance(self.out, (tuple, list)) else (self.out,)
+                for h, o in zip(self.host_out, outs):
+                    if h is not None:
+                        h.copy_(o, non_blocking=True)
 
     def replay(self):
         if self.stream is None:
