@@ -106,8 +106,9 @@ int vq_topk_merge(const float* scores, const int32_t* rows, int g, int64_t g_str
 /* Shard/merge over NVLink peer memory: ONE kernel per rank replaces ncclAllGather of the per-GPU
  * top-k + vq_topk_merge (the reference is single-process and has no counterpart).
  * [kernel: peer_exchange_merge]
- * Every rank owns an exchange window (header + arrival flags + double-buffered candidate slots for
- * `world` ranks x b_max queries x k_max entries) that all peers map through CUDA IPC:
+ * Every rank owns an exchange window (header + double-buffered 16-byte candidate lines for `world`
+ * ranks x b_max queries x k_max entries; a line = {score, epoch, row, epoch}, each 8-byte half validates
+ * itself, so neither side needs a fence) that all peers map through CUDA IPC:
  *   vq_peer_window_create   cudaMalloc + zero + IPC handle (VQ_PEER_HANDLE_BYTES bytes, host memory) —
  *                           the handles are exchanged by the host (e.g. torch.distributed.all_gather_object)
  *   vq_peer_window_open     maps a PEER's window into this process (enables peer access lazily)
@@ -115,8 +116,9 @@ int vq_topk_merge(const float* scores, const int32_t* rows, int g, int64_t g_str
  * vq_peer_exchange_merge is a collective over the ranks sharing the windows: all ranks call it with the
  * same b, k, k_out, in the same order, one stream per window set.  It pushes this rank's local candidates
  *   scores / rows [b, k] (best first per query; row < 0 = empty slot, local row numbers)
- * into every peer's window with plain stores over NVLink, waits (per CTA, acquire flags, no barrier) for
- * the peers' entries of the same queries and merges world*k -> k_out (score desc, global row asc):
+ * into every peer's window with 16-byte stores over NVLink, polls (one warp per query, no barrier) its own
+ * window until the peers' lines of the same query carry this epoch and merges world*k -> k_out (score desc,
+ * global row asc):
  *   windows_dev   device array of `world` window base pointers, index = rank (own window included)
  *   shard_offsets [world] int64 added to local rows (may be NULL)
  *   out_scores [b, k_out] fp32, out_rows [b, k_out] int64 — identical on every rank

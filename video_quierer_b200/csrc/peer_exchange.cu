@@ -4,22 +4,25 @@
 //
 // Every rank owns an exchange *window* in its HBM that all peers have mapped (CUDA IPC, NVSwitch):
 //
-//   [ header 256 B | flags u32 [world][ctas_max] | entries int2 [2 parities][world][b_max][k_max] ]
+//   [ header 256 B | lines uint4 [2 parities][world][b_max][k_max] ]     line = {score, epoch, row, epoch}
 //
 // One launch = one epoch e (kept in the window header, so a CUDA-graph replay needs no new arguments).
 // CTA c serves queries [8c, 8c+8):
-//   push   its k local (score,row) pairs per query are stored straight into EVERY peer's window
-//          (slot [e&1][my rank], 8-byte stores in 8*k*8-byte runs), then one release store at system
-//          scope of e into flags[my rank][c] of that peer;
-//   wait   `world` threads poll the CTA's own flags (acquire, system scope) until every rank's
-//          entries for these 8 queries have landed — no grid-wide or cross-rank barrier, a CTA only
-//          depends on the same CTA of its peers;
-//   merge  one warp per query: the world sorted lists are staged in shared memory and merged by
-//          repeated head selection (score desc, global row asc — the engine's order), shard offsets
-//          added, global rows written as int64.
-// Two parities suffice: a peer can start epoch e+2 only after all my CTAs pushed e+1, i.e. after all
-// my CTAs finished reading epoch e.  A wait that exceeds the timeout (a peer that never launched) sets
-// the error word of the header and *out_status instead of hanging the GPU.
+//   push   its k local (score,row) pairs per query are stored straight into EVERY peer's window (slot
+//          [e&1][my rank]) as 16-byte lines whose two 8-byte halves each carry the epoch next to the
+//          payload.  An aligned 8-byte store lands atomically, so a half whose flag word reads e holds this
+//          epoch's payload: the data validates itself — no separate flag, no system-scope fence on the
+//          sender, no acquire on the receiver (the low-latency line protocol of NCCL's LL transport);
+//   merge  one warp per query: every lane polls its lines of the world lists (volatile 16-byte loads from
+//          the rank's OWN memory) until both halves carry e, stages the payload in shared memory, and the
+//          world sorted lists are merged by repeated head selection (score desc, global row asc — the
+//          engine's order), shard offsets added, global rows written as int64.  A warp depends only on the
+//          same query of its peers: no grid-wide or cross-rank barrier.
+// Two parities suffice: a peer can start epoch e+2 only after all my CTAs pushed e+1, i.e. after all my
+// CTAs finished reading epoch e.  A poll that exceeds the timeout (a peer that never launched) sets the
+// error word of the header and *out_status instead of hanging the GPU.
+// (First version: plain stores + one release flag per (rank, CTA) + acquire polling: the two system-scope
+// membars of the sender were ~half of the kernel's 23 us, profiles/r01c_peer_exchange_b1024.*.)
 #include <stdlib.h>
 #include <string.h>
 
@@ -41,15 +44,14 @@ struct PeerHeader {
 
 __host__ __device__ inline size_t align256(size_t v) { return (v + 255) / 256 * 256; }
 __host__ __device__ inline int ctas_for(int b) { return (b + kQpc - 1) / kQpc; }
-__host__ __device__ inline size_t flags_bytes(int world, int b_max) { return align256((size_t)world * ctas_for(b_max) * 4); }
 
-__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
-    unsigned v;
-    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
+__device__ __forceinline__ void st_line(uint4* p, uint4 v) {
+    asm volatile("st.volatile.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
-__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
-    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+__device__ __forceinline__ uint4 ld_line(const uint4* p) {
+    uint4 v;
+    asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+    return v;
 }
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
     unsigned long long t;
@@ -70,12 +72,10 @@ peer_exchange_merge_kernel(void* const* __restrict__ windows, int world, int ran
     PeerHeader* hdr = reinterpret_cast<PeerHeader*>(mine);
     const unsigned e = *reinterpret_cast<volatile unsigned*>(&hdr->epoch) + 1u;
     const int par = (int)(e & 1u);
-    const int ctas_max = ctas_for(b_max);
-    const size_t data_off = kHeaderBytes + flags_bytes(world, b_max);
     const int q0 = cta * kQpc;
     const int nq = min(kQpc, b - q0);
 
-    // ---- push: this CTA's entries into every window (own rank included), peers visited in a
+    // ---- push: this CTA's lines into every window (own rank included), peers visited in a
     // rank-rotated order so that the NVLink traffic of a step is spread over all ports at once
     const int per_peer = nq * k;
     for (int i = tid; i < world * per_peer; i += kThreads) {
@@ -84,45 +84,35 @@ peer_exchange_merge_kernel(void* const* __restrict__ windows, int world, int ran
         int pp = p + rank;
         if (pp >= world) pp -= world;
         const size_t src = (size_t)(q0 + ql) * k + j;
-        const int2 v = make_int2(__float_as_int(scores[src]), rows[src]);
-        int2* dst = reinterpret_cast<int2*>(static_cast<unsigned char*>(windows[pp]) + data_off) +
-                    (((size_t)par * world + rank) * b_max + (q0 + ql)) * k_max + j;
-        *dst = v;
+        const uint4 v = make_uint4(__float_as_uint(scores[src]), e, (unsigned)rows[src], e);
+        uint4* dst = reinterpret_cast<uint4*>(static_cast<unsigned char*>(windows[pp]) + kHeaderBytes) +
+                     (((size_t)par * world + rank) * b_max + (q0 + ql)) * k_max + j;
+        st_line(dst, v);
     }
-    __syncthreads();
-    if (tid < world) {
-        int pp = tid + rank;
-        if (pp >= world) pp -= world;
-        unsigned* flag = reinterpret_cast<unsigned*>(static_cast<unsigned char*>(windows[pp]) + kHeaderBytes) +
-                         (size_t)rank * ctas_max + cta;
-        __threadfence_system();
-        st_release_sys(flag, e);
-    }
-
-    // ---- wait for the same CTA of every rank
-    if (tid < world) {
-        const unsigned* flag = reinterpret_cast<const unsigned*>(mine + kHeaderBytes) + (size_t)tid * ctas_max + cta;
-        const unsigned long long t0 = globaltimer_ns();
-        unsigned spins = 0;
-        while ((int)(ld_acquire_sys(flag) - e) < 0) {
-            __nanosleep(spins < 64u ? 40u : 400u);      // a late peer: stop competing with the co-resident scan
-            if ((++spins & 63u) == 0 && globaltimer_ns() - t0 > timeout_ns) {
-                atomicExch(&hdr->error, 1u);
-                if (out_status) *out_status = 1;
-                break;
-            }
-        }
-    }
-    __syncthreads();
 
     // ---- merge: warp `warp` owns query q0 + warp
     if (warp < nq) {
         const int q = q0 + warp;
         int2* mys = staged + (size_t)warp * world * k;
-        const int2* data = reinterpret_cast<const int2*>(mine + data_off);
+        const uint4* data = reinterpret_cast<const uint4*>(mine + kHeaderBytes);
+        unsigned long long t0 = 0;
         for (int i = lane; i < world * k; i += 32) {
             const int g = i / k, j = i - g * k;
-            mys[i] = __ldcg(data + (((size_t)par * world + g) * b_max + q) * k_max + j);
+            const uint4* src = data + (((size_t)par * world + g) * b_max + q) * k_max + j;
+            uint4 v = ld_line(src);
+            unsigned spins = 0;
+            while (v.y != e || v.w != e) {                  // the line of rank g has not landed yet
+                if (spins == 0) t0 = globaltimer_ns();
+                __nanosleep(spins < 64u ? 20u : 200u);      // a late peer: stop competing with the co-resident scan
+                if ((++spins & 255u) == 0 && globaltimer_ns() - t0 > timeout_ns) {
+                    atomicExch(&hdr->error, 1u);
+                    if (out_status) *out_status = 1;
+                    v = make_uint4(__float_as_uint(VQ_NEG_INF), e, 0xffffffffu, e);     // empty slot
+                    break;
+                }
+                v = ld_line(src);
+            }
+            mys[i] = make_int2((int)v.x, (int)v.z);
         }
         __syncwarp();
         int head = 0;
@@ -183,7 +173,7 @@ extern "C" {
 
 size_t vq_peer_window_bytes(int world, int b_max, int k_max) {
     if (world <= 0 || b_max <= 0 || k_max <= 0) return 0;
-    return kHeaderBytes + flags_bytes(world, b_max) + align256((size_t)2 * world * b_max * k_max * sizeof(int2));
+    return kHeaderBytes + align256((size_t)2 * world * b_max * k_max * sizeof(uint4));
 }
 
 int vq_peer_window_create(size_t bytes, void** local_ptr, unsigned char* handle_out) {
