@@ -64,3 +64,46 @@ def test_no_product_import_of_oracle():
             if f.endswith((".py", ".cu", ".cuh")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
+
+
+def test_peer_exchange_argument_validation_without_gpu(built_lib):
+    """The shard-exchange entry points check their arguments before any CUDA call."""
+    lib = _lib.load()
+    # window size: header + 2 parities x world x b_max x k_max lines of 16 bytes
+    assert lib.vq_peer_window_bytes(8, 1024, 16) >= 256 + 2 * 8 * 1024 * 16 * 16
+    assert lib.vq_peer_window_bytes(0, 1024, 16) == 0
+    one = ctypes.c_void_p(1)                     # non-NULL placeholders: validation must fail before any dereference
+    args = dict(world=2, rank=0, b_max=64, k_max=16, b=8, k=10, k_out=10)
+
+    def call(**kw):
+        a = dict(args, **kw)
+        return lib.vq_peer_exchange_merge(one, a["world"], a["rank"], a["b_max"], a["k_max"], one, one, a["b"], a["k"],
+                                          None, a["k_out"], one, one, None, None)
+    assert call(rank=2) == -1 and b"rank" in lib.vq_last_error()
+    assert call(world=33) == -1
+    assert call(b=65) == -1 and b"window" in lib.vq_last_error()
+    assert call(k=17) == -1
+    assert call(k_out=0) == -1
+    assert lib.vq_peer_exchange_merge(None, 2, 0, 64, 16, one, one, 8, 10, None, 10, one, one, None, None) == -1
+    assert call(b=0) == 0                        # empty batch: nothing to do
+    assert lib.vq_peer_window_open(None, None) == -1
+
+
+def test_peer_classes_need_cuda():
+    import pytest
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    from video_quierer_b200.peer import LocalWindows
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        LocalWindows(2, "cpu", 8, 16)
+
+
+def test_sharded_searcher_exchange_argument():
+    import pytest
+    from video_quierer_b200.sharded import ShardedSearcher
+    with pytest.raises(ValueError, match="exchange"):
+        ShardedSearcher(lambda q, k: None, 10, exchange="smoke-signals")
+    s = ShardedSearcher(lambda q, k: None, 10, exchange="collective")
+    s.check()                                    # no peer windows: a no-op
+    s.close()
