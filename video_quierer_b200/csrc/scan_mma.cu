@@ -705,7 +705,10 @@ MmaPlan plan(int64_t n, int ld, int b, int k) {
     p.stages = (st > 12 ? 12 : st) >> p.grp_log2 << p.grp_log2;
     // an even number of query tiles: two CTAs with neighbouring query tiles form a cluster and share every
     // store tile (each loads half a box and multicasts it), halving the L2 -> SM traffic per FLOP
-    static const int cl_env = getenv("VQ_MMA_CLUSTER") ? atoi(getenv("VQ_MMA_CLUSTER")) : 0;
+    // Short runs gain 1-5 %; in a long tensor-bound run the board sits at its 1000 W cap and the halved
+    // L2 -> SM stream buys clock: 400 steps at batch 1024, 0.896 -> 0.930 M QPS (SM clock under load 1.60 ->
+    // 1.67 GHz), measured twice back to back.  VQ_MMA_CLUSTER=0 switches it off.
+    static const int cl_env = getenv("VQ_MMA_CLUSTER") ? atoi(getenv("VQ_MMA_CLUSTER")) : 2;
     p.cl = (cl_env == 2 && p.n_qt % 2 == 0) ? 2 : 1;
     // Bootstrap the per-query threshold from a sample of tiles when the scan is long enough to pay for two
     // extra (tiny) launches; the sample holds >= 4k tiles so that the k-th largest tile maximum is a strong
