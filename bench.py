@@ -151,8 +151,10 @@ def run_reference(args):
 
 def _config(batch, gpus, path, two_stage=False):
     elem = 2 if two_stage else 4
+    which = "BASELINE config 2" if N_ROWS == 1_000_000 else \
+        ("BASELINE config 5" if N_ROWS == 100_000_000 and batch == 4096 else "experiment: --rows")
     return {"workload": f"exact cosine top-{K_TOP}: {N_ROWS}x{DIM} frame store, query batch {batch} "
-                        f"(BASELINE config 2), row-sharded over {gpus} GPU(s)",
+                        f"({which}), row-sharded over {gpus} GPU(s)",
             "n_rows": N_ROWS, "dim": DIM, "k": K_TOP, "batch": batch,
             "store_dtype": "fp32 master + bf16 scan copy (tensor-core scan selects 32 candidates, exact fp32 "
                            "re-score, certified)" if two_stage else "fp32",
