@@ -25,6 +25,7 @@ from __future__ import annotations
 import argparse
 import contextlib
 import json
+import math
 import os
 import subprocess
 import sys
@@ -252,7 +253,7 @@ def run_ours(args):
             lanes[-1].search(dev_q, K_TOP)
         barrier()
         # slot j = (lane j % depth, store copy j % n_copies); consecutive steps take consecutive slots
-        n_slots = -(-max(n_copies, depth) // depth) * depth
+        n_slots = math.lcm(n_copies, depth)            # every lane meets every copy: the rotation never shortens
         slots = [(lanes[j % depth], j % n_copies) for j in range(n_slots)]
         # the serving path for a fixed batch shape: the whole step captured once as a CUDA graph
         graphs = None
