@@ -273,15 +273,36 @@ def run_ours(args):
         # e2e: the same step with its host<->device copies captured too (one replay = H2D of the pinned
         # request slot + search + D2H of ids, scores and certificates into pinned result slots)
         hgraphs = None
+        ingest_mode = ["full"]
         if graphs is not None and with_e2e and not args.no_host_graph:
             try:
                 hgraphs = []
+                # N > 1 on the peer route: every rank ingests only ITS slice of the batch over PCIe and the
+                # slices are all-gathered over NVLink (vq_peer_allgather_rows) — 8 ranks pulling the whole batch
+                # from host memory at once capped the step near 0.25 ms
+                sliced = world > 1 and lanes[0].searcher._peer is not None and args.ingest == "slice"
+                if sliced:
+                    from video_quierer_b200.peer import PeerRowGather, slice_range
+                    q_lo, q_hi = slice_range(B, world, rank)
+                    for ln in lanes[:depth]:
+                        if getattr(ln, "rowgather", None) is None or ln.rowgather.b_max < B:
+                            ln.rowgather = PeerRowGather(dev, None, b_max=B, ld_max=DIM)
                 for ln, c in slots:
                     ln.copy = c
+                    ingest = None
+                    if sliced:
+                        h_slice = host_q[q_lo:q_hi].clone().pin_memory()     # the request slot of this rank's slice
+                        d_slice = torch.empty((q_hi - q_lo, DIM), dtype=torch.float32, device=dev)
+
+                        def ingest(ln=ln, h_slice=h_slice, d_slice=d_slice):
+                            d_slice.copy_(h_slice, non_blocking=True)
+                            return ln.rowgather.allgather_rows(d_slice, B)
                     hg = GraphedSearch(lambda qq, ln=ln: ln.search(qq, K_TOP) + (ln.bad,), B, DIM, dev, stream=ln.stream,
-                                       host_io=True)
-                    hg.host_q.copy_(host_q)            # the request slot of this step's batch
+                                       host_io=True, ingest=ingest)
+                    if hg.host_q is not None:
+                        hg.host_q.copy_(host_q)        # the request slot of this step's batch
                     hgraphs.append(hg)
+                ingest_mode[0] = "slice" if sliced else "full"
             except Exception as e:  # noqa: BLE001
                 print(f"[bench] host-io graph capture unavailable ({type(e).__name__}: {e}); explicit copies", file=sys.stderr)
                 hgraphs = None
@@ -355,6 +376,7 @@ def run_ours(args):
         torch.cuda.synchronize()
 
         e2e_ms = None
+        e2e_host = None
         n_fallback = [0]
         if with_e2e:
             # -- timed region 2: end to end with HOST (pinned) buffers: H2D + search + D2H (+ fallback), every
@@ -368,6 +390,7 @@ def run_ours(args):
                     self.ev = torch.cuda.Event()
                     self.pending = None          # (lane, copy, device queries, device scores) of the step in flight
             outs = [Out() for _ in range(depth)]
+            host_t = [0.0]
 
             def harvest(o):
                 if o.pending is None:
@@ -390,7 +413,9 @@ def run_ours(args):
                 step_no[0] += 1
                 ln, c = slots[j]
                 o = outs[ln.idx]
+                t_a = time.perf_counter()
                 harvest(o)                                     # the lane's previous step
+                host_t[0] += time.perf_counter() - t_a         # host blocked on the GPU (plus the certificate check)
                 ln.copy = c
                 with on(ln.stream):
                     if hgraphs is not None:
@@ -425,13 +450,17 @@ def run_ours(args):
                 step_e2e()
             drain()
             barrier()
+            host_t[0] = 0.0
             t0 = time.perf_counter()
             fork()
             for _ in range(steps):
                 step_e2e()
+            t1 = time.perf_counter()
             drain()
             barrier()
             e2e_ms = (time.perf_counter() - t0) * 1e3
+            # where the host thread of this rank spent the loop: blocked on results vs issuing work
+            e2e_host = {"wait_ms_per_step": host_t[0] / steps * 1e3, "issue_ms_per_step": ((t1 - t0) - host_t[0]) / steps * 1e3}
         t = torch.tensor([dev_ms, e2e_ms or 0.0], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -439,8 +468,10 @@ def run_ours(args):
         unc = max((int(ln.bad.sum().item()) if ln.bad is not None else 0) for ln in lanes[:depth])
         for ln in lanes:
             ln.searcher.check()                         # a peer-exchange wait that timed out voids the run
+            if getattr(ln, "rowgather", None) is not None:
+                ln.rowgather.check()
         return {"B": B, "steps": steps, "dev_ms": dev_ms, "e2e_ms": e2e_ms, "kernel_ms": kmed, "kernel_hot_ms": khot, "launches": launches, "path": path,
-                "graph": graphs is not None, "host_graph": hgraphs is not None, "uncertified": unc, "depth": depth, "fallbacks": n_fallback[0]}
+                "graph": graphs is not None, "host_graph": hgraphs is not None, "ingest": ingest_mode[0], "uncertified": unc, "depth": depth, "fallbacks": n_fallback[0], "e2e_host": e2e_host}
 
     with ClockSampler(local) as clocks:
         main = measure(args.batch, args.steps, args.warmup, True)
@@ -507,10 +538,14 @@ def run_ours(args):
                                if lanes[0].searcher._peer is not None else "nccl all-gather + vq_topk_merge"} if world > 1 else {}),
                            steps_in_flight=main["depth"],
                            e2e_launch="H2D + search + D2H captured in one CUDA graph per step" if main["host_graph"]
-                           else "explicit pinned copies around the step"),
+                           else "explicit pinned copies around the step",
+                           **({"e2e_ingest": "each rank copies 1/N of the batch from pinned host memory, slices all-gathered "
+                                             "over NVLink peer memory (vq_peer_allgather_rows)" if main["ingest"] == "slice"
+                               else "each rank copies the whole batch from pinned host memory"} if world > 1 else {})),
             "clocks": clocks.summary(),
             "e2e": {"value": B * args.steps / (main["e2e_ms"] * 1e-3), "unit": "queries/s",
-                    "h2d_bytes_per_step": B * DIM * 4, "d2h_bytes_per_step": B * K_TOP * (12 if world > 1 else 8) + (B * 4 if two_stage else 0)},
+                    "h2d_bytes_per_step": B * DIM * 4 * (1 if main["ingest"] == "slice" or world == 1 else world), "d2h_bytes_per_step": B * K_TOP * (12 if world > 1 else 8) + (B * 4 if two_stage else 0),
+                    "host_thread_rank0": main["e2e_host"]},
             "gpu_launches": main["launches"] * args.steps,
             "roofline": roof(main),
             "uncertified_queries_per_batch": main["uncertified"],
@@ -555,6 +590,9 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-sweep", action="store_true", help="skip the batch 1/32/1024 sweep")
     ap.add_argument("--no-hnsw", action="store_true", help="skip the HNSW (BASELINE config 3) leg")
+    ap.add_argument("--ingest", default="slice", choices=["slice", "full"],
+                    help="e2e at N > 1: every rank copies its slice of the host batch + NVLink all-gather (slice), "
+                         "or every rank copies the whole batch (full)")
     ap.add_argument("--no-host-graph", action="store_true",
                     help="e2e: explicit H2D/D2H copies around the captured step instead of capturing them with it")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying a CUDA graph")

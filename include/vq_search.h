@@ -137,6 +137,17 @@ int vq_peer_exchange_merge(const void* windows_dev, int world, int rank, int b_m
                            const int64_t* shard_offsets, int k_out,
                            float* out_scores, int64_t* out_rows, int32_t* out_status, void* stream);
 
+/* Ingest side of a sharded step: all-gather of the query batch over NVLink peer memory, so that every
+ * rank copies only ITS slice of the host batch over PCIe (rows [rank*per, min(b, (rank+1)*per)), per =
+ * ceil(b / world)).  Same windows (vq_peer_window_create/open with vq_peer_rows_window_bytes), same
+ * self-validating line protocol and collective rules as vq_peer_exchange_merge, its own window set.
+ *   slice  [rows of this rank, dim] fp32 dense (dim even)     out  [b, dim] fp32 dense, identical on all ranks
+ * Replaces: nothing in the reference (single process); SURVEY.md 8(e) "queries are replicated to all
+ * ranks".                                                                 [kernel: peer_allgather_rows] */
+size_t vq_peer_rows_window_bytes(int world, int b_max, int ld_max);
+int vq_peer_allgather_rows(const void* windows_dev, int world, int rank, int b_max, int ld_max,
+                           const float* slice, int b, int dim, float* out, int32_t* out_status, void* stream);
+
 /* Exact fp32 re-score of candidate rows (two-stage mode: bf16 scan selects k_cand, this
  * re-scores them from the fp32 shadow store and keeps the best k).     [kernel: rescore_rows]
  *   cand_rows [b, k_cand] int32 (row < 0 ignored); queries [b, ld] fp32 *already normalised*

@@ -74,6 +74,28 @@ def test_simulated_ranks_protocol(built_lib, world, b, k, k_out):
             assert np.array_equal(os_.cpu().numpy(), ref_s), f"rank {i} epoch {epoch}: scores differ"
 
 
+@pytest.mark.parametrize("world,b,dim", [(2, 37, 512), (8, 1024, 512), (8, 5, 64), (4, 130, 768), (3, 64, 32)])
+def test_simulated_ranks_rows_allgather(built_lib, world, b, dim):
+    """vq_peer_allgather_rows: every simulated rank contributes its slice of the query batch and ends up
+    with the whole batch, bit for bit, over several epochs (both parities) and a smaller batch in between."""
+    from video_quierer_b200.peer import LocalWindows, slice_range
+    dev = torch.device("cuda", 0)
+    g = torch.Generator(device="cpu").manual_seed(world * 100 + b)
+    lw = LocalWindows(world, dev, b_max=max(b, 64), k_max=0, rows_ld=max(dim, 512))
+    for epoch in range(5):
+        bb = b if epoch != 2 else max(1, b // 3)
+        q = torch.randn((bb, dim), generator=g)
+        slices = []
+        for r in range(world):
+            lo, hi = slice_range(bb, world, r)
+            slices.append(q[lo:hi].contiguous().to(dev))
+        outs = lw.allgather_rows_all(slices, bb)
+        torch.cuda.synchronize()
+        assert int(lw.status.sum()) == 0, "a simulated rank timed out"
+        for r, o in enumerate(outs):
+            assert torch.equal(o.cpu(), q), f"rank {r} epoch {epoch}"
+
+
 def test_missing_peer_times_out_instead_of_hanging(built_lib):
     """Only rank 0 of 2 launches: its wait must give up (VQ_PEER_TIMEOUT_MS) and flag the error."""
     import subprocess
@@ -145,6 +167,21 @@ def _ipc_worker(rank, world, port, ret):
             torch.cuda.synchronize()
             assert torch.equal(gs_r, cr) and torch.equal(gs_s, cs), f"rank {rank} replay {it}"
         peer.check()
+        # ingest side: every rank contributes its slice of the batch, all end up with the whole batch
+        from video_quierer_b200.peer import PeerRowGather, slice_range
+        rg = PeerRowGather(dev, None, b_max=128, ld_max=dim)
+        for bb in (b, 7, b):
+            lo_q, hi_q = slice_range(bb, world, rank)
+            got = rg.allgather_rows(queries[lo_q:hi_q].contiguous(), bb)
+            assert torch.equal(got, queries[:bb]), f"rank {rank}: gathered queries differ (b={bb})"
+        gsl = GraphedSearch(lambda qq: peer.search(qq, k), b, dim, dev,
+                            ingest=lambda: rg.allgather_rows(queries[slice_range(b, world, rank)[0]:slice_range(b, world, rank)[1]].contiguous(), b))
+        for it in range(3):
+            gsl.replay()
+            torch.cuda.synchronize()
+            assert torch.equal(gsl.host_out[1], cr.cpu()) and torch.equal(gsl.host_out[0], cs.cpu()), f"rank {rank} sliced replay {it}"
+        rg.check()
+        rg.close()
         # against the whole store on one GPU
         whole = (queries / (queries.norm(dim=1, keepdim=True) + 1e-10)) @ full.to(dev).T
         top = torch.topk(whole, k, dim=1).indices

@@ -36,6 +36,8 @@ SIGNATURES = {
     "vq_peer_window_destroy": (_i32, [_vp]),
     "vq_peer_window_status": (_i32, [_vp, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
     "vq_peer_exchange_merge": (_i32, [_vp, _i32, _i32, _i32, _i32, _vp, _vp, _i32, _i32, _vp, _i32, _vp, _vp, _vp, _vp]),
+    "vq_peer_rows_window_bytes": (_sz, [_i32, _i32, _i32]),
+    "vq_peer_allgather_rows": (_i32, [_vp, _i32, _i32, _i32, _i32, _vp, _i32, _i32, _vp, _vp, _vp]),
     "vq_profile_enable": (_i32, [_i32]),
     "vq_profile_last_kernel_ms": (C.c_float, []),
     "vq_rescore_topk": (_i32, [_vp, _i64, _i32, _i32, _vp, _i32, _vp, _i32, _i32, _vp, _vp, _vp, _sz, _vp]),

@@ -161,6 +161,84 @@ peer_exchange_merge_kernel(void* const* __restrict__ windows, int world, int ran
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// All-gather of the query batch over peer memory (the ingest side of a sharded search step): every
+// rank copies only ITS slice of the host batch over PCIe (rows [rank*per, ...), per = ceil(b/world))
+// and the slices are exchanged over NVLink with the same self-validating lines, 2 floats per line.
+// (Measured on 8 GPUs: with every rank pulling the whole 2 MB batch from host memory the end-to-end
+// step is capped near 0.25 ms whatever the pipeline depth, while the host thread only waits.)
+//   window: [ header 256 B | lines uint4 [2 parities][world][per_max][ld_max / 2] ]
+// CTA c serves rows [kRowsPerCta*c, ...) of EVERY slice: it pushes those rows of its own slice into all
+// windows, then unpacks the same rows of each rank's slice from its own window into the dense matrix.
+constexpr int kRowsPerCta = 1;
+
+__global__ void __launch_bounds__(256)
+peer_allgather_rows_kernel(void* const* __restrict__ windows, int world, int rank, int per_max, int ld_max,
+                           const float* __restrict__ slice,      // [rows of this rank, dim] dense
+                           int b, int dim, float* __restrict__ out,   // [b, dim] dense, identical on every rank
+                           int* __restrict__ out_status, unsigned long long timeout_ns) {
+    const int tid = threadIdx.x;
+    unsigned char* mine = static_cast<unsigned char*>(windows[rank]);
+    PeerHeader* hdr = reinterpret_cast<PeerHeader*>(mine);
+    const unsigned e = *reinterpret_cast<volatile unsigned*>(&hdr->epoch) + 1u;
+    const int par = (int)(e & 1u);
+    const int per = (b + world - 1) / world;                    // rows per slice (the last may be short)
+    const int lpr = dim >> 1, lpr_max = ld_max >> 1;            // lines per row
+    const int r0 = blockIdx.x * kRowsPerCta;
+    const int my_rows = max(0, min(per, b - rank * per));
+
+    // ---- push rows [r0, r0 + kRowsPerCta) of my slice into every window
+    const int nr = max(0, min(kRowsPerCta, my_rows - r0));
+    const int per_peer = nr * lpr;
+    for (int i = tid; i < world * per_peer; i += blockDim.x) {
+        const int p = i / per_peer, x = i - p * per_peer;
+        const int rl = x / lpr, j = x - rl * lpr;
+        int pp = p + rank;
+        if (pp >= world) pp -= world;
+        const float2 f = *reinterpret_cast<const float2*>(slice + (size_t)(r0 + rl) * dim + 2 * j);
+        uint4* dst = reinterpret_cast<uint4*>(static_cast<unsigned char*>(windows[pp]) + kHeaderBytes) +
+                     (((size_t)par * world + rank) * per_max + (r0 + rl)) * lpr_max + j;
+        st_line(dst, make_uint4(__float_as_uint(f.x), e, __float_as_uint(f.y), e));
+    }
+
+    // ---- unpack the same rows of every rank's slice from my own window
+    const uint4* data = reinterpret_cast<const uint4*>(mine + kHeaderBytes);
+    unsigned long long t0 = 0;
+    for (int g = 0; g < world; ++g) {
+        const int g_rows = max(0, min(per, b - g * per));
+        const int gnr = max(0, min(kRowsPerCta, g_rows - r0));
+        for (int i = tid; i < gnr * lpr; i += blockDim.x) {
+            const int rl = i / lpr, j = i - rl * lpr;
+            const uint4* src = data + (((size_t)par * world + g) * per_max + (r0 + rl)) * lpr_max + j;
+            uint4 v = ld_line(src);
+            unsigned spins = 0;
+            while (v.y != e || v.w != e) {
+                if (spins == 0) t0 = globaltimer_ns();
+                __nanosleep(spins < 64u ? 20u : 200u);
+                if ((++spins & 255u) == 0 && globaltimer_ns() - t0 > timeout_ns) {
+                    atomicExch(&hdr->error, 1u);
+                    if (out_status) *out_status = 1;
+                    v = make_uint4(0u, e, 0u, e);
+                    break;
+                }
+                v = ld_line(src);
+            }
+            *reinterpret_cast<float2*>(out + ((size_t)g * per + r0 + rl) * dim + 2 * j) =
+                make_float2(__uint_as_float(v.x), __uint_as_float(v.z));
+        }
+    }
+
+    __syncthreads();
+    if (tid == 0) {
+        const unsigned prev = atomicAdd(&hdr->done, 1u);
+        if (prev == gridDim.x - 1) {
+            hdr->done = 0;
+            __threadfence();
+            hdr->epoch = e;
+        }
+    }
+}
+
 unsigned long long exchange_timeout_ns() {
     static const unsigned long long t =
         getenv("VQ_PEER_TIMEOUT_MS") ? strtoull(getenv("VQ_PEER_TIMEOUT_MS"), nullptr, 10) * 1000000ull : 10000000000ull;
@@ -243,6 +321,30 @@ int vq_peer_exchange_merge(const void* windows_dev, int world, int rank, int b_m
         (void* const*)windows_dev, world, rank, b_max, k_max, scores, rows, b, k,
         (const long long*)shard_offsets, k_out, out_scores, (long long*)out_rows, out_status, exchange_timeout_ns());
     VQ_LAUNCH_CHECK("peer_exchange_merge_kernel");
+    return VQ_OK;
+}
+
+size_t vq_peer_rows_window_bytes(int world, int b_max, int ld_max) {
+    if (world <= 0 || b_max <= 0 || ld_max <= 0 || (ld_max & 1)) return 0;
+    const size_t per_max = ((size_t)b_max + world - 1) / world;
+    return kHeaderBytes + align256((size_t)2 * world * per_max * (ld_max / 2) * sizeof(uint4));
+}
+
+int vq_peer_allgather_rows(const void* windows_dev, int world, int rank, int b_max, int ld_max,
+                           const float* slice, int b, int dim, float* out, int32_t* out_status, void* stream) {
+    VQ_CHECK_ARG(windows_dev && out, "vq_peer_allgather_rows: null pointer");
+    VQ_CHECK_ARG(world >= 1 && world <= kMaxWorld && rank >= 0 && rank < world, "world=%d rank=%d out of range (world <= %d)",
+                 world, rank, kMaxWorld);
+    VQ_CHECK_ARG(b >= 0 && b <= b_max && dim >= 2 && dim <= ld_max && (dim & 1) == 0 && (ld_max & 1) == 0,
+                 "b=%d dim=%d exceed the window (b_max=%d ld_max=%d) or dim is odd", b, dim, b_max, ld_max);
+    if (b == 0) return VQ_OK;
+    const int per = (b + world - 1) / world, per_max = (b_max + world - 1) / world;
+    VQ_CHECK_ARG(per <= per_max, "slice of %d rows exceeds the window (%d)", per, per_max);
+    VQ_CHECK_ARG(slice || rank * per >= b, "vq_peer_allgather_rows: null slice");
+    const int grid = (per + kRowsPerCta - 1) / kRowsPerCta;
+    peer_allgather_rows_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((void* const*)windows_dev, world, rank, per_max, ld_max, slice,
+                                                                       b, dim, out, out_status, exchange_timeout_ns());
+    VQ_LAUNCH_CHECK("peer_allgather_rows_kernel");
     return VQ_OK;
 }
 

@@ -16,22 +16,27 @@ import torch
 
 
 class GraphedSearch:
-    def __init__(self, fn: Callable, batch: int, dim: int, device, warmup: int = 3, stream=None, host_io: bool = False):
+    def __init__(self, fn: Callable, batch: int, dim: int, device, warmup: int = 3, stream=None, host_io: bool = False,
+                 ingest: Callable | None = None):
         """fn(queries [batch, dim] fp32 device tensor) -> tensor or tuple of tensors (None entries allowed).
         stream: the stream the graph is replayed on (None = whatever stream is current at the call).
         host_io: the host<->device copies are part of the captured step — `host_q` (pinned, [batch, dim]) is
         the request slot the batcher fills, `host_out` the pinned twins of the outputs; one replay = H2D of
-        the queries + search + D2H of the results, with no per-step Python work beyond the launch."""
+        the queries + search + D2H of the results, with no per-step Python work beyond the launch.
+        ingest: replaces the H2D copy of `host_q`: a callable that enqueues whatever brings the step's queries
+        onto the device (e.g. H2D of this rank's slice + `peer.PeerRowGather.allgather_rows`) and returns the
+        [batch, dim] device tensor; it is captured with the step (implies pinned result slots like host_io)."""
         self.device = torch.device(device)
         self.stream = stream
         self.q = torch.zeros((batch, dim), dtype=torch.float32, device=self.device)
-        self.host_q = torch.zeros((batch, dim), dtype=torch.float32).pin_memory() if host_io else None
+        host_io = host_io or ingest is not None
+        self.host_q = torch.zeros((batch, dim), dtype=torch.float32).pin_memory() if (host_io and ingest is None) else None
         self.host_out = None
         side = torch.cuda.Stream(self.device)
         side.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(side):
             for _ in range(max(1, warmup)):               # sizes workspaces, caches tensor maps / attributes
-                probe = fn(self.q)
+                probe = fn(ingest() if ingest is not None else self.q)
         torch.cuda.current_stream(self.device).wait_stream(side)
         torch.cuda.synchronize(self.device)
         if host_io:                                       # pinned memory cannot be allocated while capturing
@@ -40,7 +45,9 @@ class GraphedSearch:
         del probe
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
-            if host_io:
+            if ingest is not None:
+                self.q = ingest()
+            elif host_io:
                 self.q.copy_(self.host_q, non_blocking=True)
             self.out = fn(self.q)
             if host_io:
