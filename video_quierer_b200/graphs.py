@@ -28,6 +28,7 @@ class GraphedSearch:
         [batch, dim] device tensor; it is captured with the step (implies pinned result slots like host_io)."""
         self.device = torch.device(device)
         self.stream = stream
+        self._fn, self._ingest = fn, ingest          # the captured nodes point into whatever these closures own
         self.q = torch.zeros((batch, dim), dtype=torch.float32, device=self.device)
         host_io = host_io or ingest is not None
         self.host_q = torch.zeros((batch, dim), dtype=torch.float32).pin_memory() if (host_io and ingest is None) else None
