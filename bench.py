@@ -357,11 +357,25 @@ def run_ours(args):
         # all-gather runs 3x slower per step than the same replays with a shallow queue)
         nccl_inside = world > 1 and lanes[0].searcher._peer is None
         sync_every = int(os.environ.get("VQ_BENCH_SYNC_EVERY", "0")) or (4 if nccl_inside else steps)
+        # Peer route, N > 1: the host keeps at most `cap` steps (two per lane) enqueued ahead of the GPU.
+        # With the whole run enqueued at once the lanes of different ranks drift apart — rank A ahead on
+        # lane 0, rank B ahead on lane 1 — and every exchange then waits for a different straggler (seen on
+        # 8 GPUs: 3.8 M QPS free-running in a run whose host-gated e2e loop reached 4.4 M).  A serving
+        # process bounds its queue the same way.
+        cap = int(os.environ.get("VQ_BENCH_INFLIGHT", "0")) or (2 * depth if (world > 1 and not nccl_inside) else 0)
+        done_evs = []
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         fork()
         for i in range(steps):
+            if cap and i >= cap:
+                done_evs[i - cap].synchronize()
+            ln_i = slots[step_no[0] % n_slots][0]
             step_device()
+            if cap:
+                ev = torch.cuda.Event()
+                ev.record(ln_i.stream if ln_i.stream is not None else cur_stream)
+                done_evs.append(ev)
             if (i + 1) % sync_every == 0 and i + 1 < steps:
                 torch.cuda.synchronize()
         join()
@@ -471,7 +485,7 @@ def run_ours(args):
             if getattr(ln, "rowgather", None) is not None:
                 ln.rowgather.check()
         return {"B": B, "steps": steps, "dev_ms": dev_ms, "e2e_ms": e2e_ms, "kernel_ms": kmed, "kernel_hot_ms": khot, "launches": launches, "path": path,
-                "graph": graphs is not None, "host_graph": hgraphs is not None, "ingest": ingest_mode[0], "uncertified": unc, "depth": depth, "fallbacks": n_fallback[0], "e2e_host": e2e_host}
+                "graph": graphs is not None, "host_graph": hgraphs is not None, "ingest": ingest_mode[0], "uncertified": unc, "depth": depth, "cap": cap, "fallbacks": n_fallback[0], "e2e_host": e2e_host}
 
     with ClockSampler(local) as clocks:
         main = measure(args.batch, args.steps, args.warmup, True)
@@ -537,6 +551,7 @@ def run_ours(args):
                            **({"exchange": "peer-memory push + merge kernel over NVLink (vq_peer_exchange_merge)"
                                if lanes[0].searcher._peer is not None else "nccl all-gather + vq_topk_merge"} if world > 1 else {}),
                            steps_in_flight=main["depth"],
+                           **({"max_steps_enqueued": main["cap"]} if main["cap"] else {}),
                            e2e_launch="H2D + search + D2H captured in one CUDA graph per step" if main["host_graph"]
                            else "explicit pinned copies around the step",
                            **({"e2e_ingest": "each rank copies 1/N of the batch from pinned host memory, slices all-gathered "
