@@ -107,3 +107,31 @@ def test_sharded_searcher_exchange_argument():
     s = ShardedSearcher(lambda q, k: None, 10, exchange="collective")
     s.check()                                    # no peer windows: a no-op
     s.close()
+
+
+def test_peer_rows_allgather_argument_validation_without_gpu(built_lib):
+    lib = _lib.load()
+    # header + 2 parities x world x ceil(b/world) rows x dim/2 lines of 16 bytes
+    assert lib.vq_peer_rows_window_bytes(8, 1024, 512) >= 256 + 2 * 8 * 128 * 256 * 16
+    assert lib.vq_peer_rows_window_bytes(8, 1024, 511) == 0            # odd row length: two floats per line
+    one = ctypes.c_void_p(1)
+
+    def call(world=2, rank=0, b_max=64, ld_max=512, b=8, dim=512, slice_=one):
+        return lib.vq_peer_allgather_rows(one, world, rank, b_max, ld_max, slice_, b, dim, one, None, None)
+    assert call(rank=5) == -1 and b"rank" in lib.vq_last_error()
+    assert call(b=65) == -1 and b"window" in lib.vq_last_error()
+    assert call(dim=514) == -1
+    assert call(dim=511) == -1
+    assert call(slice_=None) == -1 and b"slice" in lib.vq_last_error()
+    assert call(b=0) == 0
+
+
+def test_query_slices_cover_the_batch():
+    from video_quierer_b200.peer import slice_range
+    for b in (0, 1, 5, 37, 1024, 4096):
+        for world in (1, 2, 3, 8):
+            r = [slice_range(b, world, k) for k in range(world)]
+            assert r[0][0] == 0 and r[-1][1] == b
+            assert all(r[i][1] == r[i + 1][0] for i in range(world - 1))
+            per = -(-b // world) if b else 0
+            assert all(hi - lo <= per for lo, hi in r)
