@@ -50,7 +50,10 @@ extern "C" {
 /* scan path selection */
 #define VQ_SCAN_AUTO   0     /* pick by batch size and store dtype */
 #define VQ_SCAN_FMA    1     /* fp32-FMA HBM-streaming path ("GEMV" path), any store dtype */
-#define VQ_SCAN_MMA    2     /* tcgen05/TMEM tile-GEMM path (bf16 store: kind::f16; fp32 store: kind::tf32) */
+#define VQ_SCAN_MMA    2     /* tcgen05/TMEM tile-GEMM path (kind::f16 over a bf16 store; an fp32 store is refused
+                                with VQ_EUNSUPPORTED: exact fp32 results at tensor-core speed come from
+                                vq_search_exact over the bf16 + fp32 twins) */
+#define VQ_SCAN_FMA32  3     /* the FMA path with its widest query tile (32 per pass; experiments) */
 
 int         vq_abi_version(void);
 const char* vq_last_error(void);
@@ -158,13 +161,41 @@ int vq_rescore_topk(const float* store_f32, int64_t n, int dim, int ld,
                     float* out_scores, int32_t* out_rows,
                     void* workspace, size_t workspace_bytes, void* stream);
 
-/* Two-stage exact search in ONE call (throughput mode of (b)+(c)): the tensor-core scan of the bf16
+/* Exact search at tensor-core speed, ONE call, ONE pass over the store — the default search path of
+ * B200FlatIndex and what bench.py measures.                  [kernels: scan_mma_bf16<exact>, exact_finish]
+ * Replaces: SimpleVideoIndex.search, video_search_overhaul.py:40-64, with identical results: the ids
+ * are those of the fp32 scan and the scores are fp32 FMA dot products of the fp32 rows.
+ *   store_bf16 / store_f32  [n, ld] twins of the SAME rows (same ld, ld % 64 == 0, ld <= 768)
+ *   store_bounds  device float[2] = {max |x^|, max |x^ - x|} over the rows (x^ = the bf16 row, x = the fp32
+ *                 row), maintained with vq_store_bounds; any upper bounds are valid
+ *   out_overflow  [b] int32: 1 = more rows than the gather buffer holds came within the error bound of the
+ *                 k-th best (mass ties / duplicates) — re-run that query with vq_scan_topk on the fp32 store
+ *   out_stats     optional [b, 2] int32: rows the scan gathered, rows re-scored in fp32 (roofline accounting)
+ * How: the tensor-core scan of the bf16 copy keeps a running k-th best S and gathers every row whose
+ * bf16-operand score reaches S - 2*eps_q, eps_q = |q^ - q| max|x^| + |q| max|x^ - x| + fp32 accumulation
+ * slack (a Cauchy-Schwarz bound of |q^.x^ - q.x|, computed per query).  The exact k-th best s_k is
+ * >= S_final - eps_q, so every row of the exact top-k has bf16 score >= s_k - eps_q >= S - 2*eps_q and is
+ * gathered.  exact_finish re-scores the best candidates in fp32, which yields a lower bound s_lb <= s_k
+ * reached by k real rows, then every other candidate with bf16 score >= s_lb - eps_q, and returns the best k
+ * by (exact score desc, row asc).  k <= 64. */
+size_t vq_search_exact_workspace_bytes(int64_t n, int dim, int ld, int b, int k);
+int vq_search_exact(const void* store_bf16, const float* store_f32, int64_t n, int dim, int ld,
+                    const float* queries, int b, int k, int query_norm, const float* store_bounds,
+                    float* out_scores, int32_t* out_rows, int32_t* out_overflow, int32_t* out_stats,
+                    void* workspace, size_t workspace_bytes, void* stream);
+/* Fold rows [0, rows) of the twins into store_bounds (atomic max; zero the two floats once, then call after
+ * every append with the appended rows).                                        [kernel: store_bounds] */
+int vq_store_bounds(const float* store_f32, const void* store_bf16, int64_t rows, int ld,
+                    float* store_bounds, void* stream);
+
+/* Two-stage exact search in ONE call (superseded by vq_search_exact; kept for k_cand experiments): the tensor-core scan of the bf16
  * copy selects k_cand candidates per query, they are re-scored exactly (fp32 FMA, same arithmetic as
  * vq_rescore_topk) from the fp32 copy of the SAME rows, and the best k by exact score are returned.
  * Replaces the same reference code as vq_scan_topk (video_search_overhaul.py:40-64).
  *   store_bf16 / store_f32  [n, ld] twins (same ld, ld % 64 == 0)
  *   queries    [b, dim] raw fp32; query_norm as in vq_scan_topk
- *   score_eps  bound on |bf16-operand score - fp32 score| (2^-8 * max row norm + slack)
+ *   score_eps  bound on |bf16-operand score - fp32 score|: both operands are rounded to 8 significant bits
+ *              (unit roundoff 2^-8 each), so (2^-7 + 2^-16) * |q| * max row norm + accumulation slack
  *   out_uncertified [b] int32: 0 = the result is provably the exact top-k (every row outside the
  *              candidate set has exact score <= k_cand-th candidate score + score_eps < k-th exact
  *              score); 1 = could not be certified (near-duplicate heavy data): re-run that query with

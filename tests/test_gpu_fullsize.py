@@ -77,21 +77,21 @@ def _sharded(eng, scan_fn, n, g, b, k):
     return sc.merge(scores, rows, offsets, k)
 
 
-def test_config2_1m_x_512_batch_1024_two_stage(eng):
+def test_config2_1m_x_512_batch_1024_exact(eng):
     """BASELINE config 2 at full size: 1M x 512, query batch 1024, k = 10, the path bench.py times."""
     engine, _lib, torch = eng
-    from video_quierer_b200.flat_index import two_stage_search
+    from video_quierer_b200.flat_index import exact_search
     n, dim, b, k = 1_000_000, 512, 1024, 10
     q = _queries(eng, b, dim, seed=5)
     plant_rows = [0, 127, 128, 6756, 500_000, 999_935, 999_999]
     planted = {r: q[i] for i, r in enumerate(plant_rows)}
     st = _fill_store(eng, n, dim, True, True, planted)
     sc = engine.Scanner()
-    s, r, bad = two_stage_search(sc, st, q, k)
+    s, r, bad = exact_search(sc, st, q, k)
     torch.cuda.synchronize()
-    assert sc.last_path == "scan_mma_bf16+rescore"
+    assert sc.last_path == "scan_mma_bf16<exact>+finish"
     s_h, r_h = s.cpu().numpy(), r.cpu().numpy()
-    assert int(bad.sum()) == 0                                   # every query certified on this data
+    assert int(bad.sum()) == 0                                   # no gather overflowed
     for i, row in enumerate(plant_rows):
         assert r_h[i, 0] == row and abs(s_h[i, 0] - 1.0) < 1e-5
     _check_order(s_h, r_h)
@@ -104,7 +104,8 @@ def test_config2_1m_x_512_batch_1024_two_stage(eng):
         sub = engine.DeviceStore.__new__(engine.DeviceStore)
         sub.__dict__.update(st.__dict__)
         sub.f32, sub.bf16, sub.n = st.f32[lo:hi], st.bf16[lo:hi], hi - lo
-        ss, rr, _ = two_stage_search(sc, sub, q, k)
+        ss, rr, ov = exact_search(sc, sub, q, k)
+        assert int(ov.sum()) == 0
         return ss, rr
     ms, mr = _sharded(eng, shard_scan, n, 8, b, k)
     assert np.array_equal(mr.cpu().numpy(), r_h.astype(np.int64))
@@ -113,7 +114,7 @@ def test_config2_1m_x_512_batch_1024_two_stage(eng):
     s2, r2 = sc.scan(st.f32, st.n, dim, q[:8].contiguous(), k, _lib.NORM_EPS, "fma")
     assert np.array_equal(r2.cpu().numpy(), r_h[:8])
     assert np.allclose(s2.cpu().numpy(), s_h[:8], rtol=1e-5, atol=1e-6)
-    s1, r1, _ = two_stage_search(sc, st, q[5:6].contiguous(), k)
+    s1, r1, _ = exact_search(sc, st, q[5:6].contiguous(), k)
     assert np.array_equal(r1.cpu().numpy()[0], r_h[5]) and np.array_equal(s1.cpu().numpy()[0], s_h[5])
 
 

@@ -10,7 +10,7 @@ pytestmark = pytest.mark.gpu
 @pytest.mark.parametrize("graph", [True, False])
 def test_two_lanes_match_sequential(built_lib, graph):
     from video_quierer_b200 import engine
-    from video_quierer_b200.flat_index import two_stage_search
+    from video_quierer_b200.flat_index import exact_search
     from video_quierer_b200.graphs import PipelinedSearch
     from video_quierer_b200.utils import synth
     dev = torch.device("cuda", 0)
@@ -23,13 +23,13 @@ def test_two_lanes_match_sequential(built_lib, graph):
     ref_scanner = engine.Scanner(dev)
     ref = []
     for q in batches:
-        s, r, bad = two_stage_search(ref_scanner, store, q.to(dev), k)
+        s, r, bad = exact_search(ref_scanner, store, q.to(dev), k)
         assert int(bad.sum()) == 0
         ref.append((s.cpu(), r.cpu()))
 
     def make_fn(lane):
         sc = engine.Scanner(dev)                       # lane-private workspace
-        return lambda qq: two_stage_search(sc, store, qq, k)
+        return lambda qq: exact_search(sc, store, qq, k)
 
     pipe = PipelinedSearch(make_fn, b, dim, dev, depth=2, graph=graph)
     got = [None] * len(batches)

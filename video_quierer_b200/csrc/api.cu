@@ -33,6 +33,13 @@ int vq_scan_mma_collect(const void* store_bf16, const float* store_f32, int64_t 
                         int query_norm, int b, const float* thresholds, int cap, int k, float* out_scores, int32_t* out_rows,
                         int32_t* out_overflow, void* ws, size_t ws_bytes, cudaStream_t stream, int* launches);
 
+size_t vq_scan_mma_exact_workspace(int64_t n, int ld, int b, int k);
+int vq_scan_mma_exact(const void* store_bf16, const float* store_f32, int64_t n, int dim, int ld, const float* queries,
+                      int query_norm, int b, int k, const float* bounds, float* out_scores, int32_t* out_rows,
+                      int32_t* out_overflow, int32_t* out_stats, void* ws, size_t ws_bytes, cudaStream_t stream, int* launches);
+int vq_store_bounds_launch(const float* f32, const void* bf16, long long rows, int ld, float* bounds, cudaStream_t stream);
+int vq_fill_empty_launch(float* scores, int* rows, long long count, cudaStream_t stream);
+
 // ----------------------------------------------------------------------------- error state
 static thread_local char g_err[512] = "";
 static thread_local char g_path[64] = "";
@@ -202,10 +209,9 @@ int vq_scan_topk(const void* store, int64_t n, int dim, int ld, int store_dtype,
     }
     int launches = 0;
     if (n == 0) {   // empty store: all slots empty (the reference returns [] — video_search_overhaul.py:42-43)
-        VQ_CUDA(cudaMemsetAsync(out_rows, 0xff, (size_t)b * k * 4, stream));
-        VQ_CUDA(cudaMemsetAsync(out_scores, 0xff, (size_t)b * k * 4, stream));   // NaN pattern; rows=-1 is the marker
-        vq_note_launch("empty", 0);
-        return VQ_OK;
+        rc = vq_fill_empty_launch(out_scores, out_rows, (long long)b * k, stream);   // score -inf, row -1 (header contract)
+        vq_note_launch("empty", 1);
+        return rc;
     }
 
     bool use_mma = false;
@@ -331,6 +337,45 @@ int vq_search_two_stage(const void* store_bf16, const float* store_f32, int64_t 
                          out_scores, out_rows, out_uncertified, workspace, workspace_bytes, stream, &launches);
     if (rc) return rc;
     vq_note_launch("scan_mma_bf16+rescore", launches);
+    return VQ_OK;
+}
+
+int vq_store_bounds(const float* store_f32, const void* store_bf16, int64_t rows, int ld, float* bounds, void* stream) {
+    VQ_CHECK_ARG(rows >= 0 && ld > 0 && ld % 64 == 0, "bad shape rows=%lld ld=%d", (long long)rows, ld);
+    VQ_CHECK_ARG(bounds != nullptr, "bounds is NULL");
+    if (rows == 0) return VQ_OK;
+    VQ_CHECK_ARG(store_f32 && store_bf16, "NULL store pointer");
+    const int rc = vq_store_bounds_launch(store_f32, store_bf16, rows, ld, bounds, (cudaStream_t)stream);
+    vq_note_launch("store_bounds", 1);
+    return rc;
+}
+
+size_t vq_search_exact_workspace_bytes(int64_t n, int dim, int ld, int b, int k) {
+    (void)dim;
+    if (n <= 0 || b <= 0 || k <= 0) return 256;
+    return vq_scan_mma_exact_workspace(n, ld, b, k) + 256;
+}
+
+int vq_search_exact(const void* store_bf16, const float* store_f32, int64_t n, int dim, int ld,
+                    const float* queries, int b, int k, int query_norm, const float* store_bounds,
+                    float* out_scores, int32_t* out_rows, int32_t* out_overflow, int32_t* out_stats,
+                    void* workspace, size_t workspace_bytes, void* stream_v) {
+    cudaStream_t stream = (cudaStream_t)stream_v;
+    int rc = check_store(n, dim, ld, VQ_BF16);
+    if (rc) return rc;
+    VQ_CHECK_ARG(b >= 0 && k > 0 && k <= 64, "need b >= 0 and 0 < k <= 64 (b=%d k=%d)", b, k);
+    VQ_CHECK_ARG(query_norm >= VQ_NORM_NONE && query_norm <= VQ_NORM_PLAIN, "bad query_norm %d", query_norm);
+    if (b == 0) { vq_note_launch("none", 0); return VQ_OK; }
+    VQ_CHECK_ARG(n > 0, "exact search needs a non-empty store");
+    VQ_CHECK_ARG(store_bf16 && store_f32 && queries && store_bounds && out_scores && out_rows && out_overflow && workspace,
+                 "NULL pointer argument");
+    VQ_CHECK_ARG(((uintptr_t)workspace & 255) == 0, "workspace must be 256-byte aligned");
+    VQ_CHECK_ARG(((uintptr_t)store_bf16 & 15) == 0 && ((uintptr_t)store_f32 & 15) == 0, "stores must be 16-byte aligned");
+    int launches = 0;
+    rc = vq_scan_mma_exact(store_bf16, store_f32, n, dim, ld, queries, query_norm, b, k, store_bounds, out_scores, out_rows,
+                           out_overflow, out_stats, workspace, workspace_bytes, stream, &launches);
+    if (rc) return rc;
+    vq_note_launch("scan_mma_bf16<exact>+finish", launches);
     return VQ_OK;
 }
 

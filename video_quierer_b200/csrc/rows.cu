@@ -65,7 +65,58 @@ rescore_rows_kernel(const float* __restrict__ store, int ld, const float* __rest
     if (lane == 0) out_scores[w] = acc;
 }
 
+// Per-store operand-rounding bounds of the exact search (vq_search_exact): bounds[0] = max over rows of the
+// bf16 row's norm |x^|, bounds[1] = max |x^ - x| (x = the fp32 row).  One warp per row reads both copies;
+// the maxima are merged with integer atomics on the (non-negative) float bit patterns.  Rows with a
+// non-finite norm are skipped: their scores are NaN and never beat anything.
+__global__ void __launch_bounds__(256)
+store_bounds_kernel(const float* __restrict__ f32, const __nv_bfloat16* __restrict__ bf16, long long rows, int ld,
+                    float* __restrict__ bounds) {
+    const int lane = threadIdx.x & 31;
+    const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const float4* x = reinterpret_cast<const float4*>(f32 + row * ld);
+    const uint2* h = reinterpret_cast<const uint2*>(bf16 + row * ld);
+    float n2 = 0.f, e2 = 0.f;
+    for (int c = lane; c < ld / 4; c += 32) {
+        const float4 a = x[c];
+        const uint2 w = h[c];
+        const float h0 = vq_bf16lo(w.x), h1 = vq_bf16hi(w.x), h2 = vq_bf16lo(w.y), h3 = vq_bf16hi(w.y);
+        n2 = fmaf(h0, h0, n2); n2 = fmaf(h1, h1, n2); n2 = fmaf(h2, h2, n2); n2 = fmaf(h3, h3, n2);
+        const float d0 = h0 - a.x, d1 = h1 - a.y, d2 = h2 - a.z, d3 = h3 - a.w;
+        e2 = fmaf(d0, d0, e2); e2 = fmaf(d1, d1, e2); e2 = fmaf(d2, d2, e2); e2 = fmaf(d3, d3, e2);
+    }
+    n2 = vq_warp_sum(n2);
+    e2 = vq_warp_sum(e2);
+    if (lane == 0) {
+        const float nrm = sqrtf(n2), err = sqrtf(e2);
+        if (nrm < INFINITY && err < INFINITY) {          // false for NaN as well
+            atomicMax(reinterpret_cast<int*>(bounds), __float_as_int(nrm));
+            atomicMax(reinterpret_cast<int*>(bounds) + 1, __float_as_int(err));
+        }
+    }
+}
+
+__global__ void fill_empty_kernel(float* scores, int* rows, long long count) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < count) { scores[i] = VQ_NEG_INF; rows[i] = -1; }
+}
+
 }  // namespace
+
+int vq_store_bounds_launch(const float* f32, const void* bf16, long long rows, int ld, float* bounds, cudaStream_t stream) {
+    if (rows == 0) return VQ_OK;
+    store_bounds_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, stream>>>(f32, reinterpret_cast<const __nv_bfloat16*>(bf16), rows, ld, bounds);
+    VQ_LAUNCH_CHECK("store_bounds_kernel");
+    return VQ_OK;
+}
+
+int vq_fill_empty_launch(float* scores, int* rows, long long count, cudaStream_t stream) {
+    if (count == 0) return VQ_OK;
+    fill_empty_kernel<<<(unsigned)((count + 255) / 256), 256, 0, stream>>>(scores, rows, count);
+    VQ_LAUNCH_CHECK("fill_empty_kernel");
+    return VQ_OK;
+}
 
 int vq_ingest_launch(const float* src, long long rows, int dim, int src_ld, void* dst, int dst_dtype,
                      int dst_ld, int mode, cudaStream_t stream) {

@@ -59,7 +59,7 @@ constexpr int KB_ELEMS = 64;            // bf16 per k-block = one 128-byte swizz
 constexpr int TMEM_COLS = 512;          // whole tensor memory: 2 accumulators + resident query tile
 constexpr int kThreads = 256;
 constexpr int kMaxK = 64;
-constexpr int kModeList = 0, kModeBoot = 1, kModeCollect = 2;   // epilogue of scan_mma_bf16_kernel
+constexpr int kModeList = 0, kModeBoot = 1, kModeCollect = 2, kModeExact = 3;   // epilogue of scan_mma_bf16_kernel
 constexpr int kStage = 8;               // collect mode: candidates a thread stages in shared memory per global atomic
 constexpr int kIssuers = 2;            // MMA-issuing warps (warps 1 and 2), alternating k-blocks
 constexpr int kMaxBootTiles = 256;     // sample tiles of the threshold bootstrap (8 per lane in boot_select)
@@ -243,6 +243,53 @@ __device__ __forceinline__ void filter_insert(const uint32_t (&v)[32], int row_b
     }
 }
 
+// Exact mode: the register list only tracks the running k-th best bf16-operand score (thr); EVERY row whose
+// score reaches thr_c = thr - 2*eps is appended to the query's candidate buffer (staged in shared memory,
+// `flush` publishes kStage of them with one atomicAdd).  Why 2*eps: let S_k be the final k-th best bf16
+// score.  The k rows that reach it have exact score >= S_k - eps, so the exact k-th best s_k >= S_k - eps;
+// a row of the exact top-k has exact score >= s_k, i.e. bf16 score >= s_k - eps >= S_k - 2*eps >= thr_c at
+// any time (thr only grows towards S_k).  The collected set therefore contains the exact top-k.
+template <int KL, typename Flush>
+__device__ __forceinline__ void filter_collect(const uint32_t (&v)[32], int row_base, int left, float g_keep, const float& eps2,
+                                               float& thr, float& thr_c, float (&ls)[KL], int (&lr)[KL],
+                                               float* stage_s, int* stage_r, int& staged, Flush&& flush) {
+    float m = __uint_as_float(v[0]);
+#pragma unroll
+    for (int j = 1; j + 1 < 32; j += 2) m = fmaxf(fmaxf(m, __uint_as_float(v[j])), __uint_as_float(v[j + 1]));
+    m = fmaxf(m, __uint_as_float(v[31]));
+    if (!(m >= thr_c)) return;
+    unsigned mask = 0;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) mask |= (__uint_as_float(v[j]) >= thr_c) ? (1u << j) : 0u;
+    if (left < 32) mask &= left > 0 ? ((1u << left) - 1u) : 0u;
+    while (mask) {
+        const int j = __ffs(mask) - 1;
+        mask &= mask - 1;
+        float s = __uint_as_float(v[0]);
+#pragma unroll
+        for (int jj = 1; jj < 32; ++jj) s = (j == jj) ? __uint_as_float(v[jj]) : s;
+        stage_s[staged * QT] = s;
+        stage_r[staged * QT] = row_base + j;
+        if (++staged == kStage) flush();
+        if (s > thr) {
+            ls[0] = s;
+            lr[0] = row_base + j;
+#pragma unroll
+            for (int i = 0; i + 1 < KL; ++i) {
+                const bool sw = ls[i] > ls[i + 1];
+                const float a0 = ls[i], a1 = ls[i + 1];
+                const int r0 = lr[i], r1 = lr[i + 1];
+                ls[i] = sw ? a1 : a0;
+                ls[i + 1] = sw ? a0 : a1;
+                lr[i] = sw ? r1 : r0;
+                lr[i + 1] = sw ? r0 : r1;
+            }
+            thr = fmaxf(ls[0], g_keep);
+            thr_c = thr - eps2;
+        }
+    }
+}
+
 template <int KL, int NT, int MODE>
 __global__ void __launch_bounds__(kThreads, 1)
 scan_mma_bf16_kernel(const __grid_constant__ CUtensorMap tmS,
@@ -250,7 +297,8 @@ scan_mma_bf16_kernel(const __grid_constant__ CUtensorMap tmS,
                      float* __restrict__ gtau,                // [b_pad] shared k-th best per query (-inf initialised)
                      int n, int ld, int nkb, int n_qt, int k, int stages, int grp_log2, int cl, int tile_mul, int b_pad,
                      float* __restrict__ cand_s,              // [b_pad, cap] surviving candidates (BOOT: [tiles, b_pad] maxima)
-                     int* __restrict__ cand_r, int* __restrict__ cand_cnt, int cap, int dbg) {
+                     int* __restrict__ cand_r, int* __restrict__ cand_cnt, int cap, int dbg,
+                     const float* __restrict__ qeps) {            // [b_pad] per-query score-error bound (exact mode)
     constexpr int B_KB_BYTES = NT * 128;
     constexpr uint32_t A_COL0 = 2 * NT;                         // first TMEM column of the query tile
     extern __shared__ unsigned char smem_raw[];
@@ -459,6 +507,61 @@ scan_mma_bf16_kernel(const __grid_constant__ CUtensorMap tmS,
                 if (lane == 0) mbar_arrive(&tmem_empty[acc]);
             }
             if (staged) flush();
+        } else if (MODE == kModeExact) {
+            // single-pass exact search: register list for the running k-th best + collection of every row
+            // within 2*eps of it (see filter_collect)
+            float ls[KL];
+            int lr[KL];
+#pragma unroll
+            for (int i = 0; i < KL; ++i) { ls[i] = i < k ? VQ_NEG_INF : INFINITY; lr[i] = VQ_EMPTY_ROW; }
+            float eps2 = 2.f * qeps[q];              // -inf once the buffer has overflowed: thr_c = +inf, nothing passes
+            const size_t dst = (size_t)q * cap;
+            float* stage_s = reinterpret_cast<float*>(smem + (size_t)stages * B_KB_BYTES + 512) + (ew * 32 + lane);
+            int* stage_r = reinterpret_cast<int*>(smem + (size_t)stages * B_KB_BYTES + 512 + (size_t)QT * kStage * 4) + (ew * 32 + lane);
+            int staged = 0;
+            auto flush = [&]() {
+                const int at = atomicAdd(cand_cnt + q, staged);
+                for (int i = 0; i < staged; ++i)
+                    if (at + i < cap) { cand_s[dst + at + i] = stage_s[i * QT]; cand_r[dst + at + i] = stage_r[i * QT]; }
+                staged = 0;
+                if (at + kStage > cap) eps2 = VQ_NEG_INF;    // overflow (mass ties): the finish kernel flags the query
+            };
+            float published = VQ_NEG_INF;
+            int it = 0;
+            float g_next = *reinterpret_cast<volatile float*>(gtau + q);
+            for (int tile = group; tile < n_tiles; tile += n_groups, ++it) {
+                const int acc = it & 1;
+                const uint32_t acc_phase = (it >> 1) & 1;
+                const float g = g_next;
+                g_next = *reinterpret_cast<volatile float*>(gtau + q);
+                const float g_keep = (g == VQ_NEG_INF) ? g : nextafterf(g, VQ_NEG_INF);
+                float thr = fmaxf(ls[0], g_keep);
+                float thr_c = thr - eps2;
+                mbar_wait(&tmem_full[acc], acc_phase);
+                tc_fence_after();
+                const int row0 = tile * NT;
+                const int valid = (n - row0) < NT ? (n - row0) : NT;
+                constexpr int n_chunks = NT / 32;
+                uint32_t va[32], vb[32];
+                tmem_ld32_issue(lane_base + (uint32_t)(acc * NT), va);
+#pragma unroll 1
+                for (int c = 0; c < n_chunks; c += 2) {
+                    tmem_ld_wait(va);
+                    tmem_ld32_issue(lane_base + (uint32_t)(acc * NT + (c + 1) * 32), vb);
+                    filter_collect<KL>(va, row0 + c * 32, valid - c * 32, g_keep, eps2, thr, thr_c, ls, lr, stage_s, stage_r, staged, flush);
+                    tmem_ld_wait(vb);
+                    if (c + 2 < n_chunks) tmem_ld32_issue(lane_base + (uint32_t)(acc * NT + (c + 2) * 32), va);
+                    filter_collect<KL>(vb, row0 + (c + 1) * 32, valid - (c + 1) * 32, g_keep, eps2, thr, thr_c, ls, lr, stage_s, stage_r, staged, flush);
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+                if (ls[0] > published) {
+                    published = ls[0];
+                    atomic_max_float(gtau + q, published);
+                }
+            }
+            if (staged) flush();
         } else if (MODE == kModeBoot) {
             // threshold bootstrap: only the per-query maximum of every sample tile is kept
             int it = 0;
@@ -565,16 +668,20 @@ scan_mma_bf16_kernel(const __grid_constant__ CUtensorMap tmS,
 __global__ void __launch_bounds__(256)
 prep_queries_bf16_kernel(const float* __restrict__ src, int b, int dim, int src_ld, __nv_bfloat16* __restrict__ dst, int ld,
                          int b_pad, int mode, float* __restrict__ gtau, int* __restrict__ cand_cnt,
-                         const float* __restrict__ thr_in) {   // collect pass: per-query thresholds (NULL otherwise)
+                         const float* __restrict__ thr_in,     // collect pass: per-query thresholds (NULL otherwise)
+                         const float* __restrict__ bounds,     // exact mode: {max |x^|, max |x^ - x|} over the store's rows
+                         float* __restrict__ qeps) {           // exact mode: per-query bound on |bf16 score - fp32 score|
     const int lane = threadIdx.x & 31;
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     vq_pdl_wait();                     // the previous search's kernels still read gtau / cand_cnt / dst
     vq_pdl_trigger();
     if (row >= b_pad) return;
     __nv_bfloat16* o = dst + (size_t)row * ld;
-    if (lane == 0) { gtau[row] = thr_in ? (row < b ? thr_in[row] : INFINITY) : VQ_NEG_INF; cand_cnt[row] = 0; }
+    // padding queries (zero rows of the last query tile) must neither keep nor gather anything: bound +inf
+    if (lane == 0) { gtau[row] = row < b ? (thr_in ? thr_in[row] : VQ_NEG_INF) : INFINITY; cand_cnt[row] = 0; }
     if (row >= b) {
         for (int c = lane; c < ld; c += 32) o[c] = __float2bfloat16_rn(0.f);
+        if (qeps && lane == 0) qeps[row] = 0.f;
         return;
     }
     const float* s = src + (size_t)row * src_ld;
@@ -586,8 +693,28 @@ prep_queries_bf16_kernel(const float* __restrict__ src, int b, int dim, int src_
         d = sqrtf(sum);
         if (mode == VQ_NORM_EPS) d += 1e-10f;
     }
-    for (int c = lane; c < ld; c += 32)
-        o[c] = __float2bfloat16_rn(c < dim ? (mode == VQ_NORM_NONE ? s[c] : s[c] / d) : 0.f);
+    float e2 = 0.f, n2 = 0.f;          // |q^ - q|^2 and |q|^2 of the normalised fp32 query q (what the re-score uses)
+    for (int c = lane; c < ld; c += 32) {
+        const float x = c < dim ? (mode == VQ_NORM_NONE ? s[c] : s[c] / d) : 0.f;
+        const __nv_bfloat16 h = __float2bfloat16_rn(x);
+        o[c] = h;
+        const float df = __bfloat162float(h) - x;
+        e2 = fmaf(df, df, e2);
+        n2 = fmaf(x, x, n2);
+    }
+    if (qeps) {
+        // score error of the tensor-core scan against the fp32 re-score, per query (Cauchy-Schwarz on
+        //   q^.x^ - q.x = (q^ - q).x^ + q.(x^ - x)):  |q^ - q| * max|x^| + |q| * max|x^ - x|,
+        // plus the fp32 accumulation error of both sums (<= 3 * ld * 2^-24 * |q| |x^|), inflated by 1e-3 for
+        // the rounding of this very computation.  Non-finite input: eps = +inf would gather everything, the
+        // scores are NaN anyway and nothing is gathered.
+        e2 = vq_warp_sum(e2);
+        n2 = vq_warp_sum(n2);
+        if (lane == 0) {
+            const float qn = sqrtf(n2), b0 = bounds[0], b1 = bounds[1];
+            qeps[row] = 1.001f * (sqrtf(e2) * b0 + qn * b1 + 3.f * (float)ld * 5.9604645e-8f * qn * b0);
+        }
+    }
 }
 
 // Threshold bootstrap, step 2: the k-th largest of the n_t per-tile maxima of a query is reached by k
@@ -743,17 +870,19 @@ MmaPlan plan(int64_t n, int ld, int b, int k) {
 }
 
 struct MmaWs {
-    float* gtau; int* cnt; float* cand_s; int* cand_r; float* boot_max; __nv_bfloat16* qbf;
+    float* gtau; int* cnt; float* cand_s; int* cand_r; float* boot_max; __nv_bfloat16* qbf; float* qeps;
 };
 MmaWs carve(const MmaPlan& p, void* ws_v) {
     unsigned char* ws = (unsigned char*)ws_v;
     MmaWs w;
+    w.qeps = nullptr;
     w.gtau = (float*)(ws + p.off_tau);
     w.cnt = (int*)(ws + p.off_cnt);
     w.cand_s = (float*)(ws + p.off_cand_s);
     w.cand_r = (int*)(ws + p.off_cand_r);
     w.boot_max = (float*)(ws + p.off_boot);
     w.qbf = (__nv_bfloat16*)(ws + p.off_qbf);
+    w.qeps = nullptr;
     return w;
 }
 
@@ -769,14 +898,15 @@ cudaError_t launch_mma(const MmaPlan& p, const CUtensorMap& tmS, const __nv_bflo
         attr_done = true;
     }
     const int grid = BOOT ? p.boot_groups * p.n_qt : p.grid;
-    const int cl = MODE == kModeList ? p.cl : 1;
+    const int cl = (MODE == kModeList || MODE == kModeExact) ? p.cl : 1;
     return vq_launch_cluster(BOOT ? 1 : 3, cl, kern, dim3(grid), dim3(kThreads), p.smem, stream, tmS, qbf, w.gtau, n, ld, p.nkb, p.n_qt,
-                             k, p.stages, p.grp_log2, cl, BOOT ? p.boot_mul : 1, p.b_pad, BOOT ? w.boot_max : w.cand_s, w.cand_r, w.cnt, p.cap, dbg);
+                             k, p.stages, p.grp_log2, cl, BOOT ? p.boot_mul : 1, p.b_pad, BOOT ? w.boot_max : w.cand_s, w.cand_r, w.cnt, p.cap, dbg,
+                             (const float*)w.qeps);
 }
 
 // [boot pass ->] main pass; gtau / cnt must have been reset by the caller's prologue kernel.
 int run_scan(const MmaPlan& p, const void* store, int64_t n, int ld, const __nv_bfloat16* qbf, const MmaWs& w, int b, int k,
-             cudaStream_t stream, int* launches) {
+             cudaStream_t stream, int* launches, bool exact = false) {
     static const int dbg = getenv("VQ_MMA_DEBUG") ? atoi(getenv("VQ_MMA_DEBUG")) : 0;
     CUtensorMap tmS;
     if (!get_map_bf16(&tmS, store, (uint64_t)n, (uint64_t)ld, (uint32_t)p.nt)) {
@@ -808,7 +938,16 @@ int run_scan(const MmaPlan& p, const void* store, int64_t n, int ld, const __nv_
         return VQ_ECUDA;
     }
     vq_prof_begin(stream);
-    if (p.nt == 128)
+    if (exact) {
+        if (p.nt == 128)
+            e = k <= 16 ? launch_mma<16, 128, kModeExact>(p, tmM, qbf, w, (int)n, ld, k, dbg, stream)
+              : k <= 32 ? launch_mma<32, 128, kModeExact>(p, tmM, qbf, w, (int)n, ld, k, dbg, stream)
+                        : launch_mma<64, 128, kModeExact>(p, tmM, qbf, w, (int)n, ld, k, dbg, stream);
+        else
+            e = k <= 16 ? launch_mma<16, 64, kModeExact>(p, tmM, qbf, w, (int)n, ld, k, dbg, stream)
+              : k <= 32 ? launch_mma<32, 64, kModeExact>(p, tmM, qbf, w, (int)n, ld, k, dbg, stream)
+                        : launch_mma<64, 64, kModeExact>(p, tmM, qbf, w, (int)n, ld, k, dbg, stream);
+    } else if (p.nt == 128)
         e = k <= 16 ? launch_mma<16, 128, kModeList>(p, tmM, qbf, w, (int)n, ld, k, dbg, stream)
           : k <= 32 ? launch_mma<32, 128, kModeList>(p, tmM, qbf, w, (int)n, ld, k, dbg, stream)
                     : launch_mma<64, 128, kModeList>(p, tmM, qbf, w, (int)n, ld, k, dbg, stream);
@@ -897,7 +1036,7 @@ int vq_scan_mma_run(const void* store, int64_t n, int dim, int ld, int store_dty
     }
     const MmaWs w = carve(p, ws_v);
     if (vq_launch(0, prep_queries_bf16_kernel, dim3((p.b_pad + 7) / 8), dim3(256), 0, stream, queries, b, dim, dim, w.qbf, ld,
-                  p.b_pad, query_norm, w.gtau, w.cnt, (const float*)nullptr) != cudaSuccess) {
+                  p.b_pad, query_norm, w.gtau, w.cnt, (const float*)nullptr, (const float*)nullptr, (float*)nullptr) != cudaSuccess) {
         vq_set_error("launch of prep_queries_bf16_kernel failed: %s", cudaGetErrorString(cudaGetLastError()));
         return VQ_ECUDA;
     }
@@ -939,6 +1078,7 @@ int vq_scan_mma_collect(const void* store_bf16, const float* store_f32, int64_t 
     }
     unsigned char* ws = (unsigned char*)ws_v;
     MmaWs w;
+    w.qeps = nullptr;
     w.gtau = (float*)(ws + p.off_tau);
     w.cnt = (int*)(ws + p.off_cnt);
     const size_t cand_bytes = align256((size_t)p.b_pad * cap * 4);
@@ -948,7 +1088,7 @@ int vq_scan_mma_collect(const void* store_bf16, const float* store_f32, int64_t 
     w.boot_max = (float*)(ws + p.off_cand_s + 2 * cand_bytes + align256((size_t)p.b_pad * ld * 2));
     p.cap = cap;
     if (vq_launch(0, prep_queries_bf16_kernel, dim3((p.b_pad + 7) / 8), dim3(256), 0, stream, queries, b, dim, dim, w.qbf, ld,
-                  p.b_pad, query_norm, w.gtau, w.cnt, thresholds) != cudaSuccess) {
+                  p.b_pad, query_norm, w.gtau, w.cnt, thresholds, (const float*)nullptr, (float*)nullptr) != cudaSuccess) {
         vq_set_error("launch of prep_queries_bf16_kernel failed");
         return VQ_ECUDA;
     }
@@ -990,5 +1130,99 @@ int vq_scan_mma_collect(const void* store_bf16, const float* store_f32, int64_t 
     const int rc = vq_scan_finish_launch(2, w.cand_s, w.cand_r, w.cnt, cap, b, k, store_f32, ld, dim, queries, query_norm, 0.f, k,
                                          out_scores, out_rows, out_overflow, stream);
     if (rc) return rc;
+    return VQ_OK;
+}
+
+// ---------------------------------------------------------------------------------------- exact search
+// exact_finish.cu: selection + fp32 re-score of the candidates the exact-mode scan gathered
+int vq_exact_finish_launch(const float* cand_s, const int* cand_r, const int* cand_cnt, int cap, int b, int k_sel,
+                           const float* qeps, const float* store_f32, int ld, int dim, const float* queries, int query_norm,
+                           int k_out, float* out_scores, int* out_rows, int* out_overflow, int* out_stats, cudaStream_t stream);
+
+namespace {
+// Exact-mode plan: the scan plan for lists of k entries with a candidate buffer of `cap` slots per query
+// (appends of the whole scan, not just list survivors) and the per-query eps array.
+struct ExactPlan { MmaPlan p; int k_sel; size_t off_eps; };
+ExactPlan plan_exact(int64_t n, int ld, int b, int k) {
+    ExactPlan x;
+    MmaPlan& p = x.p;
+    p = plan(n, ld, b, k);
+    const int sms = vq_num_sms();
+    const long long n_tiles = (n + p.nt - 1) / p.nt;
+    // rows a query may gather: the rows within 2 eps of its k-th best plus the transient while the shared
+    // bound warms up (measured: a few hundred on iid data, 1-3 thousand on tightly clustered data at <= 8
+    // query tiles; with more query tiles every CTA sees a larger part of the store and its own bound is better)
+    int cap = p.n_qt <= 8 ? 4096 : (p.n_qt <= 16 ? 2048 : 1024);
+    static const int cap_env = getenv("VQ_EXACT_CAP") ? atoi(getenv("VQ_EXACT_CAP")) : 0;
+    if (cap_env > 0) cap = cap_env;
+    const long long n8 = (n + 7) / 8 * 8;
+    if (cap > n8) cap = (int)n8;                  // a row is gathered at most once per query: cannot overflow
+    // the bound must be valid from the first tile on (a CTA whose bound is still -inf gathers its first k
+    // rows unconditionally): bootstrap whenever the store holds two sample sets
+    int bt = sms > 4 * k ? sms : 4 * k;
+    if (bt > kMaxBootTiles) bt = kMaxBootTiles;
+    static const bool boot_on = getenv("VQ_MMA_BOOT") ? atoi(getenv("VQ_MMA_BOOT")) != 0 : true;
+    if (boot_on && n_tiles >= 2LL * bt && bt >= k) {
+        p.boot_tiles = bt;
+        p.boot_groups = bt < p.groups ? bt : p.groups;
+        p.boot_mul = (int)((n / p.nt) / bt);
+        if (p.boot_mul < 1) p.boot_mul = 1;
+    } else {
+        p.boot_tiles = p.boot_groups = 0;
+        p.boot_mul = 1;
+        if (cap < n8 && (long long)p.groups * k > cap / 2) {     // no bootstrap: groups * k unconditional appends
+            p.groups = cap / (2 * k) > 0 ? cap / (2 * k) : 1;
+            p.grid = p.groups * p.n_qt;
+        }
+    }
+    p.cap = cap;
+    x.k_sel = k <= 16 ? 32 : (k + (k / 2 > 22 ? k / 2 : 22));
+    const size_t cand_bytes = align256((size_t)p.b_pad * cap * 4);
+    size_t o = p.off_cand_s;
+    p.off_cand_r = o + cand_bytes;
+    o += 2 * cand_bytes;
+    p.off_boot = o;   o += align256((size_t)kMaxBootTiles * p.b_pad * 4);
+    p.off_qbf = o;    o += align256((size_t)p.b_pad * ld * 2);
+    x.off_eps = o;    o += align256((size_t)p.b_pad * 4);
+    p.total = o;
+    return x;
+}
+}  // namespace
+
+size_t vq_scan_mma_exact_workspace(int64_t n, int ld, int b, int k) {
+    if (b < 1 || k < 1 || k > kMaxK || n < 1 || ld > 768 || ld % KB_ELEMS != 0) return 0;
+    return plan_exact(n, ld, b, k).p.total + 256;
+}
+
+// Single-pass exact top-k: prep (normalise + bf16 + per-query eps) -> [boot -> boot_select] -> exact-mode
+// scan (list + gather) -> exact_finish (select, fp32 re-score, final top-k).  Exact by construction; the only
+// failure mode is a gather that overflows (mass ties), reported per query in out_overflow.
+int vq_scan_mma_exact(const void* store_bf16, const float* store_f32, int64_t n, int dim, int ld, const float* queries,
+                      int query_norm, int b, int k, const float* bounds, float* out_scores, int32_t* out_rows,
+                      int32_t* out_overflow, int32_t* out_stats, void* ws_v, size_t ws_bytes, cudaStream_t stream, int* launches) {
+    if (!vq_scan_mma_supported(n, dim, ld, VQ_BF16, b, k)) {
+        vq_set_error("exact search: unsupported shape n=%lld dim=%d ld=%d b=%d k=%d", (long long)n, dim, ld, b, k);
+        return VQ_EUNSUPPORTED;
+    }
+    const ExactPlan x = plan_exact(n, ld, b, k);
+    const MmaPlan& p = x.p;
+    if (ws_bytes < p.total) {
+        vq_set_error("exact search: workspace too small (%zu < %zu)", ws_bytes, p.total);
+        return VQ_EWORKSPACE;
+    }
+    MmaWs w = carve(p, ws_v);
+    w.qeps = (float*)((unsigned char*)ws_v + x.off_eps);
+    if (vq_launch(0, prep_queries_bf16_kernel, dim3((p.b_pad + 7) / 8), dim3(256), 0, stream, queries, b, dim, dim, w.qbf, ld,
+                  p.b_pad, query_norm, w.gtau, w.cnt, (const float*)nullptr, bounds, w.qeps) != cudaSuccess) {
+        vq_set_error("launch of prep_queries_bf16_kernel failed: %s", cudaGetErrorString(cudaGetLastError()));
+        return VQ_ECUDA;
+    }
+    int nl = 0;
+    int rc = run_scan(p, store_bf16, n, ld, w.qbf, w, b, k, stream, &nl, true);
+    if (rc) return rc;
+    rc = vq_exact_finish_launch(w.cand_s, w.cand_r, w.cnt, p.cap, b, x.k_sel, w.qeps, store_f32, ld, dim, queries, query_norm,
+                                k, out_scores, out_rows, out_overflow, out_stats, stream);
+    if (rc) return rc;
+    *launches = 2 + nl;
     return VQ_OK;
 }

@@ -107,6 +107,19 @@ __device__ __forceinline__ uint4 vq_ldg_stream(const void* p) {
     return v;
 }
 
+// monotone map: larger score -> smaller 32-bit key (ascending key order = best first); -0 is folded into +0
+__device__ __forceinline__ uint32_t vq_score_key(float s) {
+    if (s == 0.f) s = 0.f;
+    uint32_t u = __float_as_uint(s);
+    u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+    return ~u;
+}
+__device__ __forceinline__ float vq_key_score(uint32_t k) {
+    uint32_t u = ~k;
+    u = (u & 0x80000000u) ? (u & 0x7fffffffu) : ~u;
+    return __uint_as_float(u);
+}
+
 __device__ __forceinline__ float vq_bf16lo(uint32_t w) { return __uint_as_float(w << 16); }
 __device__ __forceinline__ float vq_bf16hi(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
 

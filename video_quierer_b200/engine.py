@@ -69,6 +69,9 @@ class DeviceStore:
         self.f32 = None
         self.bf16 = None
         self.lib = _lib.load()
+        # operand-rounding bounds of the exact search, on the device: [max |bf16 row|, max |bf16 row - fp32 row|]
+        # (folded in by `append`; monotone — rows that are removed later only leave the bound looser)
+        self.bounds = None
         if capacity:
             self._reserve(capacity)
 
@@ -120,8 +123,19 @@ class DeviceStore:
                 dst = self.bf16[self.n: self.n + m]
                 _lib.check(self.lib.vq_ingest_rows(_ptr(src), m, self.dim, self.dim, _ptr(dst), _lib.BF16, self.ld,
                                                    norm, st), "vq_ingest_rows")
+            self._fold_bounds(self.n, self.n + m)
         self.n += m
         self._sample = None
+
+    def _fold_bounds(self, lo: int, hi: int):
+        """`vq_store_bounds` over rows [lo, hi) of the twins (no-op unless both copies are kept)."""
+        if self.f32 is None or self.bf16 is None or hi <= lo:
+            return
+        with torch.cuda.device(self.device):
+            if self.bounds is None:
+                self.bounds = torch.zeros(2, dtype=torch.float32, device=self.device)
+            _lib.check(self.lib.vq_store_bounds(_ptr(self.f32[lo:hi]), _ptr(self.bf16[lo:hi]), hi - lo, self.ld,
+                                                _ptr(self.bounds), _stream(self.device)), "vq_store_bounds")
 
     # ------------------------------------------------------------------ raw persistence (rawstore.py)
     def save_raw_arrays(self, writer):
@@ -161,11 +175,14 @@ class DeviceStore:
                 else:
                     dst[lo:hi].copy_(torch.from_numpy(host))
         st.n = n
+        st._fold_bounds(0, n)
         return st
 
     def truncate(self, n: int):
         self.n = min(self.n, max(0, int(n)))
         self._sample = None
+        if self.n == 0 and self.bounds is not None:
+            self.bounds.zero_()
 
     def sample_f32(self, stride: int) -> torch.Tensor:
         """Compact (fp32, bf16) copies of every `stride`-th row (rows 0, stride, 2*stride, ...), cached
@@ -178,6 +195,13 @@ class DeviceStore:
                 b = self.bf16[: self.n: stride].contiguous() if self.bf16 is not None else None
                 self._sample = (key, f, b)
         return self._sample[1], self._sample[2]
+
+    def max_row_norm(self) -> float:
+        """Largest row norm of the store (host float; synchronises).  1.0 if no bounds are tracked."""
+        if self.bounds is None:
+            return 1.0
+        b = self.bounds.cpu()
+        return max(float(b[0] + b[1]), 1e-30)           # |x| <= |x^| + |x^ - x|
 
     def view(self, dtype: str = "fp32") -> torch.Tensor:
         t = self.f32 if _DT[dtype] == _lib.F32 else self.bf16
@@ -224,7 +248,7 @@ class Scanner:
         return out_s, out_r
 
     def two_stage(self, bf16: torch.Tensor, f32: torch.Tensor, n: int, dim: int, queries: torch.Tensor, k: int,
-                  k_cand: int, norm: int = _lib.NORM_EPS, score_eps: float = 2.0 ** -8 + 1e-5):
+                  k_cand: int, norm: int = _lib.NORM_EPS, score_eps: float = 2.0 ** -7 + 1e-4):
         """`vq_search_two_stage`: tensor-core scan of the bf16 copy for k_cand candidates, exact fp32
         re-score, best k, per-query certificate.  Returns (scores [b,k] f32, rows [b,k] i32,
         uncertified [b] i32) device tensors."""
@@ -248,6 +272,31 @@ class Scanner:
                 self.last_path = _lib.last_scan_path()
                 self.last_launches = _lib.last_launch_count()
         return out_s, out_r, bad
+
+    def exact(self, st: "DeviceStore", queries: torch.Tensor, k: int, norm: int = _lib.NORM_EPS, stats: torch.Tensor | None = None):
+        """`vq_search_exact`: the exact fp32 top-k in ONE tensor-core pass over the bf16 copy (+ fp32 re-score
+        of the gathered candidates).  Returns (scores [b,k] f32, rows [b,k] i32, overflow [b] i32) device
+        tensors; a query whose overflow flag is set (mass ties) must be re-run on the fp32 FMA scan.
+        stats: optional [b, 2] int32 device tensor (rows gathered by the scan, rows re-scored)."""
+        if st.bf16 is None or st.f32 is None or st.bounds is None:
+            raise RuntimeError("exact search needs a store that keeps both the fp32 and the bf16 copy")
+        b = queries.shape[0]
+        with torch.cuda.device(self.device):
+            out_s = torch.empty((b, k), dtype=torch.float32, device=self.device)
+            out_r = torch.empty((b, k), dtype=torch.int32, device=self.device)
+            over = torch.zeros((b,), dtype=torch.int32, device=self.device)
+            if b == 0:
+                return out_s, out_r, over
+            need = self.lib.vq_search_exact_workspace_bytes(st.n, st.dim, st.ld, b, k)
+            with self.lock:
+                ws = self.ws.get(need)
+                rc = self.lib.vq_search_exact(_ptr(st.bf16), _ptr(st.f32), st.n, st.dim, st.ld, _ptr(queries), b, k, norm,
+                                              _ptr(st.bounds), _ptr(out_s), _ptr(out_r), _ptr(over), _ptr(stats), _ptr(ws), ws.numel(),
+                                              _stream(self.device))
+                _lib.check(rc, "vq_search_exact")
+                self.last_path = _lib.last_scan_path()
+                self.last_launches = _lib.last_launch_count()
+        return out_s, out_r, over
 
     def collect(self, bf16: torch.Tensor, f32: torch.Tensor, n: int, dim: int, queries: torch.Tensor, k: int,
                 thresholds: torch.Tensor, cap: int = 4096, norm: int = _lib.NORM_EPS):

@@ -128,17 +128,33 @@ class LazyRows:
     pop = __delitem__ = __setitem__ = insert = remove = clear = sort = reverse = _frozen
 
 
-# Worst-case |bf16-operand score - fp32 score| for unit-norm rows and queries: each operand is
-# rounded to 8 significant bits (relative 2^-9), products are exact, so
-# |delta| <= (2*2^-9 + 2^-18) * sum|q_i x_i| <= 2^-8 * |q| |x|  (Cauchy-Schwarz) plus fp32 accumulation noise.
-BF16_SCORE_EPS = 2.0 ** -8 + 1e-5
+# Worst-case |bf16-operand score - fp32 score| per unit of |q| |x|: each operand is rounded to 8 significant
+# bits (unit roundoff 2^-8), products are exact, so
+# |delta| <= (2*2^-8 + 2^-16) * sum|q_i x_i| <= (2^-7 + 2^-16) * |q| |x|  (Cauchy-Schwarz) plus the fp32
+# accumulation error of both sums (<= 3 * 768 * 2^-24).  Used by the two-stage / large-k routes, multiplied by
+# the store's largest row norm; `vq_search_exact` computes a tighter, per-query bound on the device from the
+# actual rounding errors (|q^ - q|, max |x^ - x|).
+BF16_SCORE_EPS = 2.0 ** -7 + 2.0 ** -16 + 1.4e-4
 MAX_TENSOR_K, MAX_TENSOR_LD = 64, 768        # limits of scan_mma_bf16_kernel (csrc/scan_mma.cu)
 MAX_BATCH = 8192                             # queries per launch chain of the facade (64 query tiles)
 
 
+def exact_search(scanner: Scanner, st: DeviceStore, q_dev: torch.Tensor, k: int):
+    """The exact fp32 top-k of the store at tensor-core speed.  k <= 64 and ld <= 768: ONE pass
+    (`vq_search_exact`: scan of the bf16 copy that gathers everything within the operand-rounding bound of
+    the running k-th best, fp32 re-score, exact by construction); larger k / wider rows: `large_k_search`.
+    Returns ([b,k] f32, [b,k] i32, overflow [b] i32 device tensor or None).  The caller re-runs queries
+    whose overflow flag is set (mass ties) with `exact_fallback` after its device->host read, so no sync
+    is added here."""
+    if k > MAX_TENSOR_K or st.ld > MAX_TENSOR_LD:
+        return large_k_search(scanner, st, q_dev, k) + (None,)
+    return scanner.exact(st, q_dev, k, _lib.NORM_EPS)
+
+
 def two_stage_search(scanner: Scanner, st: DeviceStore, q_dev: torch.Tensor, k: int, path: str = "auto",
-                     max_row_norm: float = 1.0):
-    """Exact top-k from a bf16 scan, ONE C-ABI call (`vq_search_two_stage`): (1) the tensor-core
+                     max_row_norm: float | None = None):
+    """(Superseded by `exact_search`; kept as the k_cand experiment route.)
+    Exact top-k from a bf16 scan, ONE C-ABI call (`vq_search_two_stage`): (1) the tensor-core
     scan of the bf16 copy selects k' candidates, (2) they are re-scored exactly from the fp32 copy,
     (3) the result is *certified*: every row outside the candidate set has exact score <=
     (k'-th bf16 score) + eps, so if the exact k-th score is above that bound nothing was missed.
@@ -151,6 +167,8 @@ def two_stage_search(scanner: Scanner, st: DeviceStore, q_dev: torch.Tensor, k: 
     # fp32 FMA scan.
     kc = int(os.environ.get("VQ_KCAND", 0)) or (32 if k <= 16 else max(2 * k, k + 22))
     kc = max(min(st.n, kc, MAX_TENSOR_K), min(k, st.n))
+    if max_row_norm is None:
+        max_row_norm = st.max_row_norm()
     if k > MAX_TENSOR_K or st.ld > MAX_TENSOR_LD:
         return large_k_search(scanner, st, q_dev, k, max_row_norm) + (None,)
     s_hi, rows, bad = scanner.two_stage(st.bf16, st.f32, st.n, st.dim, q_dev, k, kc, _lib.NORM_EPS,
@@ -167,7 +185,7 @@ COLLECT_CAP = 4096
 LARGE_K_CAP = 16384
 
 
-def large_k_search(scanner: Scanner, st: DeviceStore, q_dev: torch.Tensor, k: int, max_row_norm: float = 1.0):
+def large_k_search(scanner: Scanner, st: DeviceStore, q_dev: torch.Tensor, k: int, max_row_norm: float | None = None):
     """Exact top-k beyond the register lists of the tensor kernel (64 < k <= 256; BASELINE config 4:
     k = 100), in two tensor-core collect passes:
       1. over a STRIDED SAMPLE of the store (a compact copy of every `stride`-th row, cached with the
@@ -178,6 +196,8 @@ def large_k_search(scanner: Scanner, st: DeviceStore, q_dev: torch.Tensor, k: in
          (about k * stride rows per query), all are re-scored in fp32, the best k are returned.
     Exact by construction.  Queries whose gather overflows, and stores that are too small or too
     wide for the tensor kernel, are answered by the fp32 FMA scan."""
+    if max_row_norm is None:
+        max_row_norm = st.max_row_norm()
     tile = 128 if st.ld <= 512 else 64
     # the sample must hold k + 1 full tiles (the derived threshold is the k-th largest tile maximum); the
     # second pass gathers ~k * stride rows per query, which has to stay well inside LARGE_K_CAP
@@ -197,13 +217,15 @@ def large_k_search(scanner: Scanner, st: DeviceStore, q_dev: torch.Tensor, k: in
 
 
 def resolve_uncertified(scanner: Scanner, st: DeviceStore, q_dev: torch.Tensor, k: int, idx: torch.Tensor,
-                        s_two_stage: torch.Tensor, max_row_norm: float = 1.0):
+                        s_two_stage: torch.Tensor, max_row_norm: float | None = None):
     """Exact top-k for the queries `idx` whose two-stage result was not certified (near-duplicate
     heavy data).  The k-th exact score the two-stage pass returned is a lower bound s_k of the true
     k-th best, so every row of the true top-k has bf16-operand score >= s_k - eps: a second
     tensor-core pass gathers exactly those rows (`vq_search_collect`), re-scores ALL of them from
     the fp32 copy and keeps the best k.  Only queries with more than COLLECT_CAP such rows (mass
     duplicates) go to the fp32 FMA scan.  Returns (scores [m,k] f32, rows [m,k] i32) device tensors."""
+    if max_row_norm is None:
+        max_row_norm = st.max_row_norm()
     qs = q_dev[idx].contiguous()
     thr = s_two_stage[idx, k - 1] - BF16_SCORE_EPS * max_row_norm
     s, r, over = scanner.collect(st.bf16, st.f32, st.n, st.dim, qs, k, thr, COLLECT_CAP)
@@ -217,10 +239,15 @@ def resolve_uncertified(scanner: Scanner, st: DeviceStore, q_dev: torch.Tensor, 
 class B200FlatIndex:
     """Exact cosine search over a device-resident frame-embedding matrix."""
 
-    def __init__(self, device=None, store_dtype: str = "fp32", rescore: bool = True, path: str = "auto"):
-        """store_dtype 'fp32' = parity mode (scores within 1e-5 of the reference);
-        'bf16' = throughput mode: bf16 scan picks candidates, and with `rescore` they are
-        re-scored exactly from an fp32 shadow copy before the final top-k."""
+    def __init__(self, device=None, store_dtype: str = "bf16", rescore: bool = True, path: str = "auto"):
+        """store_dtype 'bf16' + rescore (the default) = exact mode: an fp32 master copy plus a bf16 scan copy;
+        the tensor-core scan of the bf16 copy gathers every row that can belong to the exact top-k and the
+        answer is re-scored from the fp32 copy (`vq_search_exact`) — the ids of the fp32 scan and fp32 scores
+        within 1e-5 of the reference, at 6 bytes per element.
+        store_dtype 'fp32' = the fp32 copy only, scanned by the fp32 FMA kernel (4 bytes per element, same
+        results, HBM-bound up to batch 8 and FMA-bound beyond).
+        store_dtype 'bf16' without rescore = the bf16 copy only: approximate scores (operands rounded to
+        bf16), 2 bytes per element."""
         self._embeddings = EmbeddingList()
         self.metadata: List[Dict] = []
         self.video_hashes: Dict = {}
@@ -232,7 +259,7 @@ class B200FlatIndex:
         self._scanner = Scanner(self.device)
         self._lock = threading.RLock()
         self.search_times: List[float] = []
-        self.stats = {"two_stage_queries": 0, "uncertified_queries": 0}   # uncertified ones are resolved by the collect pass
+        self.stats = {"exact_queries": 0, "overflow_queries": 0}   # overflowing ones (mass ties) re-run on the fp32 FMA scan
 
     # ------------------------------------------------------------------ attribute surface
     @property
@@ -327,16 +354,16 @@ class B200FlatIndex:
         if not self.rescore:
             s, r = self._scanner.scan(st.bf16, st.n, st.dim, q, kk, _lib.NORM_EPS, self.path)
             return s.cpu().numpy(), r.cpu().numpy()
-        s, r, bad = two_stage_search(self._scanner, st, q, kk, self.path)
+        s, r, over = exact_search(self._scanner, st, q, kk)
         s_h, r_h = s.cpu().numpy(), r.cpu().numpy()
-        self.stats["two_stage_queries"] += int(q.shape[0])
-        if bad is not None:
-            bad_h = np.nonzero(bad.cpu().numpy())[0]
-            if len(bad_h):
-                self.stats["uncertified_queries"] += len(bad_h)
-                idx = torch.from_numpy(bad_h).to(self.device)
-                s2, r2 = resolve_uncertified(self._scanner, st, q, kk, idx, s)
-                s_h[bad_h], r_h[bad_h] = s2.cpu().numpy(), r2.cpu().numpy()
+        self.stats["exact_queries"] += int(q.shape[0])
+        if over is not None:
+            over_h = np.nonzero(over.cpu().numpy())[0]
+            if len(over_h):                      # mass ties: more rows within the error bound than the gather holds
+                self.stats["overflow_queries"] += len(over_h)
+                idx = torch.from_numpy(over_h).to(self.device)
+                s2, r2 = exact_fallback(self._scanner, st, q, kk, idx)
+                s_h[over_h], r_h[over_h] = s2.cpu().numpy(), r2.cpu().numpy()
         return s_h, r_h
 
     def search(self, query_embedding: np.ndarray, k: int = 5) -> List[Dict]:
