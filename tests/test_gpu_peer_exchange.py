@@ -129,6 +129,7 @@ def _ipc_worker(rank, world, port, ret):
     import torch.distributed as dist
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
+    os.environ["VQ_PEER_TIMEOUT_MS"] = "1000"
     torch.cuda.set_device(rank)
     dev = torch.device("cuda", rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
@@ -186,6 +187,32 @@ def _ipc_worker(rank, world, port, ret):
         whole = (queries / (queries.norm(dim=1, keepdim=True) + 1e-10)) @ full.to(dev).T
         top = torch.topk(whole, k, dim=1).indices
         assert (top == cr).float().mean().item() > 0.999          # (near-ties may swap neighbours)
+        # the exact single-pass search as the local search (what bench.py shards), checked read-out
+        st2 = engine.DeviceStore(dim, dev, keep_fp32=True, keep_bf16=True)
+        st2.append(full[lo:hi].to(dev))
+        ex = ShardedSearcher(lambda q, kk: scanner.exact(st2, q, kk)[:2], n, device=dev, exchange="peer")
+        es, er = ex.search_checked(queries, k)
+        assert np.array_equal(er, cr.cpu().numpy()) and np.allclose(es, cs.cpu().numpy(), rtol=1e-6, atol=1e-7)
+        ex.close()
+        # a late peer: rank 1 skips one exchange -> rank 0 must RAISE instead of returning a partial top-k, refuse
+        # further searches, and work again after reset() on both ranks (failure surfaced on the data path)
+        if rank == 0:
+            try:
+                peer.search_checked(queries, k)
+                raise AssertionError("a missing peer went unnoticed")
+            except _lib.VQError as e:
+                assert "did not deliver" in str(e)
+            try:
+                peer.search(queries, k)
+                raise AssertionError("search after a failed exchange must be refused")
+            except RuntimeError:
+                pass
+        else:
+            import time
+            time.sleep(3.0)
+        peer.reset()
+        ps, pr = peer.search_checked(queries, k)
+        assert np.array_equal(pr, cr.cpu().numpy()) and np.array_equal(ps, cs.cpu().numpy())
         peer.close()
         ret[rank] = "ok"
     except Exception as e:  # noqa: BLE001
@@ -193,6 +220,63 @@ def _ipc_worker(rank, world, port, ret):
         ret[rank] = "".join(traceback.format_exception(e))
     finally:
         dist.destroy_process_group()
+
+
+def _hnsw_shard_worker(rank, world, port, ret):
+    """North-star: 'HNSW is partitioned as per-shard sub-graphs searched in parallel and merged the same way' —
+    one sub-graph per GPU, the same fused exchange + merge kernel, no host round trip on the search path."""
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        from video_quierer_b200.hnsw_index import B200HNSWIndex
+        from video_quierer_b200.sharded import ShardedSearcher, shard_range
+        from video_quierer_b200.utils import synth
+        n, dim, k, b = 24_000, 128, 10, 200
+        full = synth.clip_like(n, dim, seed=5)
+        queries = torch.from_numpy(synth.clip_like(b, dim, seed=6, n_store=n)).to(dev)
+        lo, hi = shard_range(n, world, rank)
+        h = B200HNSWIndex(dimension=dim, M=16, ef_construction=200, ef_search=128, max_M=16, device=dev)
+        h.add_batch(list(full[lo:hi]), list(range(lo, hi)))
+        h.build()
+        sh = ShardedSearcher(h.as_local_search(), n, device=dev, exchange="peer")
+        s, r = sh.search_checked(queries, k)
+        assert int(h.last_overflow.sum()) == 0
+        qn = queries.cpu().numpy()
+        qn = qn / np.linalg.norm(qn, axis=1, keepdims=True)
+        truth = np.argsort(-(qn @ full.T), axis=1)[:, :k]
+        recall = np.mean([len(set(r[i]) & set(truth[i])) / k for i in range(b)])
+        # the unsharded index at the same M / ef on this rank's GPU as the bar (union of sub-graph results >= it)
+        whole = B200HNSWIndex(dimension=dim, M=16, ef_construction=200, ef_search=128, max_M=16, device=dev)
+        whole.add_batch(list(full), list(range(n)))
+        _, wr = whole.search_arrays(qn, k)
+        recall_whole = np.mean([len(set(wr[i]) & set(truth[i])) / k for i in range(b)])
+        assert recall >= recall_whole - 0.01 and recall > 0.9, (recall, recall_whole)
+        assert np.all(np.diff(s, axis=1) <= 1e-7)                          # merged best first
+        gathered = [None] * world
+        dist.all_gather_object(gathered, r.tolist())
+        assert gathered[0] == gathered[rank]                               # identical on every rank
+        sh.close()
+        ret[rank] = "ok"
+    except Exception as e:  # noqa: BLE001
+        import traceback
+        ret[rank] = "".join(traceback.format_exception(e))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_gpu_hnsw_subgraphs(built_lib):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs on one node")
+    import torch.multiprocessing as mp
+    world = 2
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_hnsw_shard_worker, args=(world, _free_port(), ret), nprocs=world, join=True)
+    assert all(ret.get(r) == "ok" for r in range(world)), dict(ret)
 
 
 def test_two_gpu_ipc_exchange(built_lib):

@@ -209,12 +209,10 @@ int vq_exact_finish_launch(const float* cand_s, const int* cand_r, const int* ca
         vq_set_error("exact_finish: %d candidate slots per query do not fit shared memory", cap);
         return VQ_EUNSUPPORTED;
     }
-    int dev = 0;
-    static bool attr_done[64] = {false};
-    VQ_CUDA(cudaGetDevice(&dev));
-    if (dev < 0 || dev >= 64 || !attr_done[dev]) {
+    static std::atomic<unsigned long long> attr_done{0};
+    if (vq_first_use_on_device(&attr_done)) {
         VQ_CUDA(cudaFuncSetAttribute(exact_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        if (dev >= 0 && dev < 64) attr_done[dev] = true;
+        vq_mark_used(&attr_done);
     }
     const cudaError_t e = vq_launch(4, exact_finish_kernel, dim3(b), dim3(kThreads), smem, stream, cand_s, cand_r, cand_cnt, cap, k_sel,
                                     qeps, store_f32, ld, dim, queries, query_norm, k_out, out_scores, out_rows, out_overflow, out_stats, sort_cap);

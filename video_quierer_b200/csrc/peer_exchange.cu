@@ -312,10 +312,10 @@ int vq_peer_exchange_merge(const void* windows_dev, int world, int rank, int b_m
     if (b == 0) return VQ_OK;
     const size_t smem = (size_t)kQpc * world * k * sizeof(int2);
     VQ_CHECK_ARG(smem <= 200 * 1024, "world*k=%d too large for the merge stage", world * k);
-    static bool attr_done = false;
-    if (!attr_done) {
+    static std::atomic<unsigned long long> attr_done{0};
+    if (vq_first_use_on_device(&attr_done)) {
         VQ_CUDA(cudaFuncSetAttribute(peer_exchange_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        attr_done = true;
+        vq_mark_used(&attr_done);
     }
     peer_exchange_merge_kernel<<<ctas_for(b), kThreads, smem, (cudaStream_t)stream>>>(
         (void* const*)windows_dev, world, rank, b_max, k_max, scores, rows, b, k,

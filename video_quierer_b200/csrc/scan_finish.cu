@@ -311,12 +311,12 @@ static int finish_launch(int mode, const float* cand_s, const int* cand_r, const
         vq_set_error("scan_finish: %d candidate slots per query do not fit shared memory", cap);
         return VQ_EUNSUPPORTED;
     }
-    static bool attr_done = false;
-    if (!attr_done) {
+    static std::atomic<unsigned long long> attr_done{0};
+    if (vq_first_use_on_device(&attr_done)) {
         const int on = getenv("VQ_FINISH_DEBUG") ? 1 : 0;
         cudaMemcpyToSymbol(g_finish_dbg, &on, sizeof(int));
         VQ_CUDA(cudaFuncSetAttribute(scan_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-        attr_done = true;
+        vq_mark_used(&attr_done);
     }
     const cudaError_t e = vq_launch(4, scan_finish_kernel, dim3(b), dim3(kThreads), smem, stream, mode, cand_s, cand_r, cand_cnt, k_in, g_stride, cap, k_sel,
                                     store_f32, ld, dim, queries, query_norm, eps, k_out, out_scores, out_rows, out_bad, sort_cap);

@@ -177,11 +177,11 @@ template <int BT, int R, bool BF16>
 cudaError_t launch(const void* store, int n, int ld, const float* q, int k, float* ps, int* pr,
                    int grid, size_t smem, cudaStream_t stream) {
     auto kern = scan_fma_kernel<BT, R, BF16>;
-    static bool attr_done = false;   // per instantiation
-    if (!attr_done) {
+    static std::atomic<unsigned long long> attr_done{0};   // per instantiation, one bit per device
+    if (vq_first_use_on_device(&attr_done)) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         if (e != cudaSuccess) return e;
-        attr_done = true;
+        vq_mark_used(&attr_done);
     }
     kern<<<grid, kThreads, smem, stream>>>(store, n, ld, q, k, ps, pr);
     return cudaGetLastError();

@@ -891,11 +891,11 @@ cudaError_t launch_mma(const MmaPlan& p, const CUtensorMap& tmS, const __nv_bflo
                        int dbg, cudaStream_t stream) {
     auto kern = scan_mma_bf16_kernel<KL, NT, MODE>;
     constexpr bool BOOT = MODE == kModeBoot;
-    static bool attr_done = false;
-    if (!attr_done) {
+    static std::atomic<unsigned long long> attr_done{0};   // per instantiation, one bit per device
+    if (vq_first_use_on_device(&attr_done)) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return e;
-        attr_done = true;
+        vq_mark_used(&attr_done);
     }
     const int grid = BOOT ? p.boot_groups * p.n_qt : p.grid;
     const int cl = (MODE == kModeList || MODE == kModeExact) ? p.cl : 1;
@@ -1158,14 +1158,17 @@ ExactPlan plan_exact(int64_t n, int ld, int b, int k) {
     const long long n8 = (n + 7) / 8 * 8;
     if (cap > n8) cap = (int)n8;                  // a row is gathered at most once per query: cannot overflow
     // the bound must be valid from the first tile on (a CTA whose bound is still -inf gathers its first k
-    // rows unconditionally): bootstrap whenever the store holds two sample sets
+    // rows unconditionally, and on a short scan the CTA-local k-th best never gets tight): bootstrap whenever
+    // the store holds 2k full tiles — up to `bt` sample tiles, at most every second tile
     int bt = sms > 4 * k ? sms : 4 * k;
     if (bt > kMaxBootTiles) bt = kMaxBootTiles;
+    const long long full_tiles = n / p.nt;
+    if (bt > full_tiles / 2) bt = (int)(full_tiles / 2);
     static const bool boot_on = getenv("VQ_MMA_BOOT") ? atoi(getenv("VQ_MMA_BOOT")) != 0 : true;
-    if (boot_on && n_tiles >= 2LL * bt && bt >= k) {
+    if (boot_on && bt >= k && cap < n8) {
         p.boot_tiles = bt;
         p.boot_groups = bt < p.groups ? bt : p.groups;
-        p.boot_mul = (int)((n / p.nt) / bt);
+        p.boot_mul = (int)(full_tiles / bt);
         if (p.boot_mul < 1) p.boot_mul = 1;
     } else {
         p.boot_tiles = p.boot_groups = 0;

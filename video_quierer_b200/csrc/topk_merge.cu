@@ -130,11 +130,11 @@ int vq_topk_merge_launch(const float* scores, const int* rows, int g, long long 
         vq_set_error("topk_merge: k_out=%d too large", k_out);
         return VQ_EUNSUPPORTED;
     }
-    static bool attr_done = false;
-    if (!attr_done) {
+    static std::atomic<unsigned long long> attr_done{0};
+    if (vq_first_use_on_device(&attr_done)) {
         VQ_CUDA(cudaFuncSetAttribute(topk_merge_kernel<long long>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
         VQ_CUDA(cudaFuncSetAttribute(topk_merge_kernel<int>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-        attr_done = true;
+        vq_mark_used(&attr_done);
     }
     if (rows64)
         topk_merge_kernel<long long><<<b_out, kThreads, smem, stream>>>(scores, rows, g, g_stride, k_in, offsets, k_out,

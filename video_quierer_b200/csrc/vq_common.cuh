@@ -42,6 +42,19 @@ void vq_note_launch(const char* path_or_null, int launches);
     } while (0)
 
 int vq_num_sms();
+// Per-device once guard for a call site: cudaFuncSetAttribute (and __device__ symbols) apply to ONE device, a
+// process may drive several.  `vq_first_use_on_device(&flags)` returns true until `vq_mark_used(&flags)` has
+// run on the current device; the flags word is a static std::atomic at the call site (one bit per device).
+#include <atomic>
+inline unsigned long long vq_device_bit() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0) dev = 0;
+    return 1ull << (dev & 63);
+}
+inline bool vq_first_use_on_device(const std::atomic<unsigned long long>* flags) {
+    return (flags->load(std::memory_order_acquire) & vq_device_bit()) == 0;
+}
+inline void vq_mark_used(std::atomic<unsigned long long>* flags) { flags->fetch_or(vq_device_bit(), std::memory_order_release); }
 int vq_pdl_mask();           // bit i set: kernels of PDL class i are launched with the attribute
 int vq_launch_priority(int launch_class);   // CUDA priority of a launch class (0 = default), see api.cu
 

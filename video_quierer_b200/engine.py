@@ -203,6 +203,15 @@ class DeviceStore:
         b = self.bounds.cpu()
         return max(float(b[0] + b[1]), 1e-30)           # |x| <= |x^| + |x^ - x|
 
+    def max_row_norm_cached(self) -> float:
+        """`max_row_norm` read once per store size (the large-k route needs it on the host to scale its
+        threshold; reading it per search would put a device synchronisation on the search path)."""
+        c = getattr(self, "_mrn", None)
+        if c is None or c[0] != self.n:
+            c = (self.n, self.max_row_norm())
+            self._mrn = c
+        return c[1]
+
     def view(self, dtype: str = "fp32") -> torch.Tensor:
         t = self.f32 if _DT[dtype] == _lib.F32 else self.bf16
         if t is None:

@@ -128,6 +128,32 @@ class LazyRows:
     pop = __delitem__ = __setitem__ = insert = remove = clear = sort = reverse = _frozen
 
 
+class DeviceRows(LazyRows):
+    """`embeddings` of an index whose rows were handed over on the DEVICE (`add_frames` with a CUDA tensor,
+    `adopt_store`): they live only in the device matrix; reads copy single rows back on demand.  Same
+    contract as `LazyRows` (append / extend work, removing stored rows needs `materialise()`)."""
+
+    def __init__(self, store: DeviceStore):
+        self._store_ref, self._dim = store, store.dim
+        self._f32 = self._bf16 = None
+        self.base_n = store.n
+        self.tail = EmbeddingList()
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            return [self[j] for j in range(*i.indices(len(self)))]
+        if i < 0:
+            i += len(self)
+        if i >= self.base_n:
+            return self.tail[i - self.base_n]
+        return self._store_ref.rows_to_host(i, i + 1)[0]
+
+    def __iter__(self):
+        for lo in range(0, self.base_n, 1 << 16):             # chunked device-to-host copies
+            yield from self._store_ref.rows_to_host(lo, min(self.base_n, lo + (1 << 16)))
+        yield from self.tail
+
+
 # Worst-case |bf16-operand score - fp32 score| per unit of |q| |x|: each operand is rounded to 8 significant
 # bits (unit roundoff 2^-8), products are exact, so
 # |delta| <= (2*2^-8 + 2^-16) * sum|q_i x_i| <= (2^-7 + 2^-16) * |q| |x|  (Cauchy-Schwarz) plus the fp32
@@ -143,11 +169,11 @@ def exact_search(scanner: Scanner, st: DeviceStore, q_dev: torch.Tensor, k: int)
     """The exact fp32 top-k of the store at tensor-core speed.  k <= 64 and ld <= 768: ONE pass
     (`vq_search_exact`: scan of the bf16 copy that gathers everything within the operand-rounding bound of
     the running k-th best, fp32 re-score, exact by construction); larger k / wider rows: `large_k_search`.
-    Returns ([b,k] f32, [b,k] i32, overflow [b] i32 device tensor or None).  The caller re-runs queries
+    Returns ([b,k] f32, [b,k] i32, overflow [b] i32 device tensor).  The caller re-runs queries
     whose overflow flag is set (mass ties) with `exact_fallback` after its device->host read, so no sync
     is added here."""
     if k > MAX_TENSOR_K or st.ld > MAX_TENSOR_LD:
-        return large_k_search(scanner, st, q_dev, k) + (None,)
+        return large_k_search(scanner, st, q_dev, k)
     return scanner.exact(st, q_dev, k, _lib.NORM_EPS)
 
 
@@ -170,7 +196,7 @@ def two_stage_search(scanner: Scanner, st: DeviceStore, q_dev: torch.Tensor, k: 
     if max_row_norm is None:
         max_row_norm = st.max_row_norm()
     if k > MAX_TENSOR_K or st.ld > MAX_TENSOR_LD:
-        return large_k_search(scanner, st, q_dev, k, max_row_norm) + (None,)
+        return large_k_search(scanner, st, q_dev, k, max_row_norm)
     s_hi, rows, bad = scanner.two_stage(st.bf16, st.f32, st.n, st.dim, q_dev, k, kc, _lib.NORM_EPS,
                                         BF16_SCORE_EPS * max_row_norm)
     return s_hi, rows, (bad if kc < st.n else None)
@@ -194,26 +220,24 @@ def large_k_search(scanner: Scanner, st: DeviceStore, q_dev: torch.Tensor, k: in
          reached by k real rows, so it is a lower bound of the k-th best of the whole store;
       2. over the whole store with threshold s_k - eps: every row of the true top-k is gathered
          (about k * stride rows per query), all are re-scored in fp32, the best k are returned.
-    Exact by construction.  Queries whose gather overflows, and stores that are too small or too
-    wide for the tensor kernel, are answered by the fp32 FMA scan."""
-    if max_row_norm is None:
-        max_row_norm = st.max_row_norm()
+    Exact by construction; nothing here synchronises with the host (the two passes can be captured in a
+    CUDA graph).  Returns (scores, rows, overflow [b] i32): queries whose gather overflowed must be re-run
+    with `exact_fallback`; stores that are too small or too wide for the tensor kernel are answered by the
+    fp32 FMA scan right away (overflow all zero)."""
     tile = 128 if st.ld <= 512 else 64
     # the sample must hold k + 1 full tiles (the derived threshold is the k-th largest tile maximum); the
     # second pass gathers ~k * stride rows per query, which has to stay well inside LARGE_K_CAP
     stride = min(64, LARGE_K_CAP // (3 * k), st.n // ((k + 1) * tile)) if k <= 256 else 0
     if st.bf16 is None or st.ld > MAX_TENSOR_LD or stride < 2:
-        return scanner.scan(st.f32, st.n, st.dim, q_dev, k, _lib.NORM_EPS, "fma")
+        s, r = scanner.scan(st.f32, st.n, st.dim, q_dev, k, _lib.NORM_EPS, "fma")
+        return s, r, torch.zeros((q_dev.shape[0],), dtype=torch.int32, device=q_dev.device)
+    if max_row_norm is None:
+        max_row_norm = st.max_row_norm_cached()
     smp_f32, smp_bf16 = st.sample_f32(stride)       # rows 0, stride, 2*stride, ...
     s1, _, over1 = scanner.collect(smp_bf16, smp_f32, smp_f32.shape[0], st.dim, q_dev, k, None, LARGE_K_CAP)
     thr = s1[:, k - 1] - BF16_SCORE_EPS * max_row_norm
     thr = torch.where(over1 > 0, torch.full_like(thr, float("-inf")), thr)      # incomplete sample answer: no bound
-    s, r, over = scanner.collect(st.bf16, st.f32, st.n, st.dim, q_dev, k, thr, LARGE_K_CAP)
-    over_h = torch.nonzero(over).flatten()
-    if len(over_h):
-        sf, rf = exact_fallback(scanner, st, q_dev, k, over_h)
-        s[over_h], r[over_h] = sf, rf
-    return s, r
+    return scanner.collect(st.bf16, st.f32, st.n, st.dim, q_dev, k, thr, LARGE_K_CAP)
 
 
 def resolve_uncertified(scanner: Scanner, st: DeviceStore, q_dev: torch.Tensor, k: int, idx: torch.Tensor,
@@ -286,13 +310,52 @@ class B200FlatIndex:
             'frame_id': len(self._embeddings) - 1,
         })
 
-    def add_frames(self, embeddings: np.ndarray, video_names, timestamps):
-        """Bulk form of `add_frame` (same bookkeeping, one upload)."""
-        embeddings = np.asarray(embeddings, dtype=np.float32)
+    def add_frames(self, embeddings, video_names, timestamps):
+        """Bulk form of `add_frame` (same bookkeeping, one upload).  A CUDA tensor (the encoder's output,
+        video_search_overhaul.py:224-228 before its `.cpu().numpy()`) is appended to the device matrix
+        directly — no host round trip; `embeddings` then becomes a `DeviceRows` view."""
         base = len(self._embeddings)
-        self._embeddings.extend(list(embeddings))
+        if isinstance(embeddings, torch.Tensor) and embeddings.is_cuda:
+            with self._lock:
+                self._adopt_device_rows(embeddings.shape[-1])
+                self._sync()
+                self._store.append(embeddings.reshape(-1, embeddings.shape[-1]), _lib.NORM_NONE)
+                self._embeddings.base_n = self._store.n          # (the host tail was uploaded by _sync: it is part of the base now)
+                self._embeddings.tail = EmbeddingList()
+        else:
+            if isinstance(embeddings, torch.Tensor):
+                embeddings = embeddings.detach().cpu().numpy()
+            embeddings = np.asarray(embeddings, dtype=np.float32)
+            self._embeddings.extend(list(embeddings))
         for i, (vn, ts) in enumerate(zip(video_names, timestamps)):
             self.metadata.append({'video_name': vn, 'timestamp': ts, 'frame_id': base + i})
+
+    def _new_store(self, dim: int) -> DeviceStore:
+        bf = self.store_dtype == "bf16"
+        return DeviceStore(dim, self.device, keep_fp32=(not bf) or self.rescore, keep_bf16=bf)
+
+    def _adopt_device_rows(self, dim: int):
+        """Switch `embeddings` to the device-resident form (rows already listed on the host are uploaded first)."""
+        if isinstance(self._embeddings, DeviceRows):
+            return
+        if isinstance(self._embeddings, LazyRows):
+            raise NotImplementedError("device-resident appends to a raw-loaded index: call materialise() first")
+        self._sync()
+        if self._store is None:
+            self._store = self._new_store(int(dim))
+        self._embeddings = DeviceRows(self._store)
+
+    def adopt_store(self, store: DeviceStore, metadata: List[Dict]):
+        """Serve an existing device-resident store (e.g. built by the encoder pipeline) through the drop-in
+        surface without copying it; `metadata` is the parallel list of the reference's per-frame dicts."""
+        if len(metadata) != store.n:
+            raise ValueError(f"{len(metadata)} metadata entries for {store.n} rows")
+        with self._lock:
+            self._store = store
+            self.store_dtype = "bf16" if store.bf16 is not None else "fp32"
+            self.rescore = store.f32 is not None
+            self._embeddings = DeviceRows(store)
+            self.metadata = metadata
 
     def _sync(self):
         emb = self._embeddings
@@ -314,8 +377,7 @@ class B200FlatIndex:
             return
         dim = int(np.asarray(emb[0]).shape[-1])
         if self._store is None or self._store.dim != dim:
-            bf = self.store_dtype == "bf16"
-            self._store = DeviceStore(dim, self.device, keep_fp32=(not bf) or self.rescore, keep_bf16=bf)
+            self._store = self._new_store(dim)
             emb.valid_prefix = 0
         st = self._store
         keep = min(emb.valid_prefix, st.n, n)
@@ -357,13 +419,12 @@ class B200FlatIndex:
         s, r, over = exact_search(self._scanner, st, q, kk)
         s_h, r_h = s.cpu().numpy(), r.cpu().numpy()
         self.stats["exact_queries"] += int(q.shape[0])
-        if over is not None:
-            over_h = np.nonzero(over.cpu().numpy())[0]
-            if len(over_h):                      # mass ties: more rows within the error bound than the gather holds
-                self.stats["overflow_queries"] += len(over_h)
-                idx = torch.from_numpy(over_h).to(self.device)
-                s2, r2 = exact_fallback(self._scanner, st, q, kk, idx)
-                s_h[over_h], r_h[over_h] = s2.cpu().numpy(), r2.cpu().numpy()
+        over_h = np.nonzero(over.cpu().numpy())[0]
+        if len(over_h):                      # mass ties: more rows within the error bound than the gather holds
+            self.stats["overflow_queries"] += len(over_h)
+            idx = torch.from_numpy(over_h).to(self.device)
+            s2, r2 = exact_fallback(self._scanner, st, q, kk, idx)
+            s_h[over_h], r_h[over_h] = s2.cpu().numpy(), r2.cpu().numpy()
         return s_h, r_h
 
     def search(self, query_embedding: np.ndarray, k: int = 5) -> List[Dict]:
@@ -371,31 +432,20 @@ class B200FlatIndex:
         if not self._embeddings:
             return []
         scores, rows = self.search_arrays(query_embedding, k)
-        results = []
-        for s, r in zip(scores[0], rows[0]):
-            if r < 0:
-                continue
-            md = self.metadata[int(r)].copy()
-            md['score'] = float(s)
-            results.append(md)
-        return results
+        return self._hits(scores[0].tolist(), rows[0].tolist())
+
+    def _hits(self, scores: list, rows: list) -> List[Dict]:
+        """Metadata copies + 'score' (Python float), best first (video_search_overhaul.py:58-62).  Works on
+        plain Python lists: one `.tolist()` per batch instead of a numpy scalar conversion per hit."""
+        md = self.metadata
+        return [{**md[r], 'score': s} for s, r in zip(scores, rows) if r >= 0]
 
     def search_batch(self, queries, k: int = 5) -> List[List[Dict]]:
         """One launch for the whole batch (replaces the per-query loop of routes.py:627-634)."""
         if not self._embeddings:
             return [[] for _ in range(len(queries))]
-        scores, rows = self.search_arrays(np.asarray(queries), k)
-        out = []
-        for sb, rb in zip(scores, rows):
-            hits = []
-            for s, r in zip(sb, rb):
-                if r < 0:
-                    continue
-                md = self.metadata[int(r)].copy()
-                md['score'] = float(s)
-                hits.append(md)
-            out.append(hits)
-        return out
+        scores, rows = self.search_arrays(queries if isinstance(queries, torch.Tensor) else np.asarray(queries), k)
+        return [self._hits(sb, rb) for sb, rb in zip(scores.tolist(), rows.tolist())]
 
     # ------------------------------------------------------------------ persistence
     def save_to_disk(self, cache_path: Path):

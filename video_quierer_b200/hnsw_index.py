@@ -40,6 +40,9 @@ from . import _lib
 from .engine import DeviceStore, Scanner, Workspace, _ptr, _require_cuda, _stream, as_device_queries
 
 
+MAX_DEGREE = 25          # m_out limit of vq_hnsw_build_layer (csrc/hnsw.cu)
+
+
 class DeviceGraph:
     """Dense HNSW graph on the device (layout documented in DESIGN.md §3 / include/vq_search.h)."""
 
@@ -59,6 +62,9 @@ class B200HNSWIndex:
                  max_M: int = 16, level_generation_factor: float = 1.0 / math.log(2.0), num_threads: int = 4,
                  use_numpy_optimization: bool = True, device=None, search_dtype: str = "fp32",
                  rebuild_fraction: float = 0.10, select: str = "diverse", max_candidates: int = 63):
+        if max(int(M), int(max_M)) > MAX_DEGREE or min(int(M), int(max_M)) < 1:
+            raise ValueError(f"M={M} / max_M={max_M}: the device graph holds 1..{MAX_DEGREE} neighbours per node and layer "
+                             "(vq_hnsw_build_layer's m_out limit)")
         self.dimension = dimension
         self.M = M
         self.max_M = max_M
@@ -206,6 +212,25 @@ class B200HNSWIndex:
             self.build()
 
     # ------------------------------------------------------------------ search
+    def _launch_search(self, q: torch.Tensor, kk: int, ef: int, cap: int = 0):
+        """One `vq_hnsw_search` launch, nothing synchronises: (dist [b,kk] f32, rows [b,kk] i32, stats [b,4] i32)."""
+        st, g = self._store, self._graph
+        mat = st.bf16 if self.search_dtype == "bf16" else st.f32
+        dt = _lib.BF16 if self.search_dtype == "bf16" else _lib.F32
+        b = q.shape[0]
+        with torch.cuda.device(self.device):
+            out_d = torch.empty((b, kk), dtype=torch.float32, device=self.device)
+            out_r = torch.empty((b, kk), dtype=torch.int32, device=self.device)
+            stats = torch.zeros((b, 4), dtype=torch.int32, device=self.device)
+            ws = self._ws.get(self.lib.vq_hnsw_workspace_bytes(b, st.ld, ef))
+            rc = self.lib.vq_hnsw_search(_ptr(mat), g.n, st.dim, st.ld, dt, _ptr(g.levels), _ptr(g.adj0),
+                                         g.adj0.shape[1], _ptr(g.upper_off), _ptr(g.upper_adj),
+                                         g.upper_adj.shape[1], g.entry, g.max_level, ef, _ptr(q), b, kk,
+                                         _lib.NORM_PLAIN, _ptr(out_d), _ptr(out_r), _ptr(stats), cap, _ptr(ws),
+                                         ws.numel(), _stream(self.device))
+            _lib.check(rc, "vq_hnsw_search")
+        return out_d, out_r, stats
+
     def _search_rows(self, queries, k: int):
         """→ (dist [b,k'] float32, rows [b,k'] int64) numpy, ascending distance, -1 padded."""
         with self.lock:
@@ -213,25 +238,13 @@ class B200HNSWIndex:
             st, g = self._store, self._graph
             q = as_device_queries(queries, self.dimension, self.device)
             b = q.shape[0]
+            # rows superseded by a re-added id stay in the graph and are dropped by `_format`: over-fetch by their
+            # number so that k live hits remain (the reference overwrites data[node_id] in place and returns k)
+            want = int(k) + len(self._dead)
             ef = max(int(self.ef_search), int(k))                # hnsw.py:264
-            kk = min(int(k), g.n)
-            mat = st.bf16 if self.search_dtype == "bf16" else st.f32
-            dt = _lib.BF16 if self.search_dtype == "bf16" else _lib.F32
+            kk = min(want, ef, g.n)
             with torch.cuda.device(self.device):
-                out_d = torch.empty((b, kk), dtype=torch.float32, device=self.device)
-                out_r = torch.empty((b, kk), dtype=torch.int32, device=self.device)
-                stats = torch.zeros((b, 4), dtype=torch.int32, device=self.device)
-                ws = self._ws.get(self.lib.vq_hnsw_workspace_bytes(b, st.ld, ef))
-
-                def launch(qq, od, orr, stt, cap):
-                    rc = self.lib.vq_hnsw_search(_ptr(mat), g.n, st.dim, st.ld, dt, _ptr(g.levels), _ptr(g.adj0),
-                                                 g.adj0.shape[1], _ptr(g.upper_off), _ptr(g.upper_adj),
-                                                 g.upper_adj.shape[1], g.entry, g.max_level, ef, _ptr(qq), qq.shape[0], kk,
-                                                 _lib.NORM_PLAIN, _ptr(od), _ptr(orr), _ptr(stt), cap, _ptr(ws),
-                                                 ws.numel(), _stream(self.device))
-                    _lib.check(rc, "vq_hnsw_search")
-
-                launch(q, out_d, out_r, stats, 0)
+                out_d, out_r, stats = self._launch_search(q, kk, ef, 0)
                 dist = out_d.cpu().numpy()
                 rows = out_r.cpu().numpy().astype(np.int64)
                 self.last_stats = stats.cpu().numpy().astype(np.uint32)
@@ -240,17 +253,14 @@ class B200HNSWIndex:
                 while len(over) and cap <= 32768 * 2:             # visited set filled up: re-run those queries
                     idx = torch.from_numpy(over).to(self.device)
                     q2 = q[idx].contiguous()
-                    d2 = torch.empty((len(over), kk), dtype=torch.float32, device=self.device)
-                    r2 = torch.empty((len(over), kk), dtype=torch.int32, device=self.device)
-                    s2 = torch.zeros((len(over), 4), dtype=torch.int32, device=self.device)
-                    launch(q2, d2, r2, s2, min(cap, 32768))
+                    d2, r2, s2 = self._launch_search(q2, kk, ef, min(cap, 32768))
                     dist[over] = d2.cpu().numpy()
                     rows[over] = r2.cpu().numpy().astype(np.int64)
                     self.last_stats[over] = s2.cpu().numpy().astype(np.uint32)
                     over = over[np.nonzero(self.last_stats[over, 2])[0]]
                     cap *= 4
                 if st.n > g.n:                                    # rows newer than the graph: exact scan of the delta
-                    kd = min(int(k), st.n - g.n)
+                    kd = min(want, st.n - g.n)
                     s2, r2 = self._scanner.scan(st.f32[g.n:], st.n - g.n, st.dim, q, kd, _lib.NORM_PLAIN, "fma")
                     d2 = (1.0 - s2).cpu().numpy()
                     r2 = r2.cpu().numpy().astype(np.int64)
@@ -258,7 +268,7 @@ class B200HNSWIndex:
                     dist = np.concatenate([dist, d2], axis=1)
                     rows = np.concatenate([rows, r2], axis=1)
                     dist = np.where(rows >= 0, dist, np.inf)
-                    order = np.lexsort((rows, dist), axis=1)[:, :min(int(k), st.n)]
+                    order = np.lexsort((rows, dist), axis=1)[:, :min(want, st.n)]
                     dist = np.take_along_axis(dist, order, axis=1)
                     rows = np.take_along_axis(rows, order, axis=1)
             return dist, rows
@@ -312,16 +322,25 @@ class B200HNSWIndex:
         [b,k] int32, -1 = empty) on this index's device."""
         def local_search(queries: torch.Tensor, k: int):
             b = queries.shape[0]
-            scores = torch.full((b, k), float("-inf"), dtype=torch.float32, device=self.device)
-            rows = torch.full((b, k), -1, dtype=torch.int32, device=self.device)
             if self.element_count == 0 or b == 0:
+                return (torch.full((b, k), float("-inf"), dtype=torch.float32, device=self.device),
+                        torch.full((b, k), -1, dtype=torch.int32, device=self.device))
+            with self.lock:
+                self._ensure_graph()
+                g = self._graph
+                if self._store.n > g.n or self._dead:
+                    raise RuntimeError("as_local_search serves a built, append-only shard: call build() after ingest")
+                ef = max(int(self.ef_search), int(k))
+                kk = min(int(k), g.n)
+                q = queries.to(self.device, torch.float32).contiguous()
+                dist, rows, stats = self._launch_search(q, kk, ef, 0)     # device tensors, no host round trip
+                self.last_overflow = stats[:, 2]                          # visited-set overflow flags (device)
+                scores = torch.where(rows >= 0, 1.0 - dist, torch.full_like(dist, float("-inf")))
+                if kk < k:
+                    pad = k - kk
+                    scores = torch.cat([scores, torch.full((b, pad), float("-inf"), dtype=torch.float32, device=self.device)], dim=1)
+                    rows = torch.cat([rows, torch.full((b, pad), -1, dtype=torch.int32, device=self.device)], dim=1)
                 return scores, rows
-            dist, r = self._search_rows(queries, k)
-            kk = dist.shape[1]
-            ok = r >= 0
-            scores[:, :kk] = torch.from_numpy(np.where(ok, 1.0 - dist, -np.inf).astype(np.float32)).to(self.device)
-            rows[:, :kk] = torch.from_numpy(np.where(ok, r, -1).astype(np.int32)).to(self.device)
-            return scores, rows
         return local_search
 
     # ------------------------------------------------------------------ reference-format views

@@ -58,6 +58,7 @@ class ShardedSearcher:
         self.exchange = exchange
         self._peer = None
         self._peer_failed = False
+        self._broken = False
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
@@ -114,7 +115,40 @@ class ShardedSearcher:
     def check(self):
         """Raises if the peer exchange recorded a timeout (synchronises); no-op on the collective route."""
         if self._peer is not None:
-            self._peer.check()
+            try:
+                self._peer.check()
+            except Exception:
+                self._broken = True
+                raise
+
+    @property
+    def status(self) -> Optional[torch.Tensor]:
+        """Device int32[1], sticky: non-zero once a peer missed an exchange (its shard's candidates were then
+        replaced by empty slots, so every result since is PARTIAL).  None on the collective route.  Consumers
+        that replay a captured step copy it to the host together with the results (`search_checked` does)."""
+        return None if self._peer is None else self._peer.status
+
+    def search_checked(self, queries: torch.Tensor, k: int):
+        """`search` + device-to-host copy of the results AND of the exchange status in the same
+        synchronisation: raises instead of returning partial results when a peer did not arrive in time.
+        Returns (scores [b,k] float32, global rows [b,k] int64) numpy arrays.  After a failure the searcher
+        refuses further searches until `reset()` has been called on EVERY rank."""
+        s, r = self.search(queries, k)
+        st = self.status
+        s_h, r_h = s.cpu().numpy(), r.cpu().numpy()
+        if st is not None and int(st.cpu().item()) != 0:
+            self._broken = True
+            from ._lib import VQError
+            raise VQError(f"shard exchange on rank {self.rank}: a peer did not deliver its candidates in time; the merged "
+                          "top-k would be partial.  Call reset() on every rank to rebuild the exchange windows.")
+        return s_h, r_h
+
+    def reset(self):
+        """Collective: drop the exchange windows (their epoch counters may be out of step after a rank missed
+        an exchange); the next search rebuilds them with all ranks taking part."""
+        self.close()
+        self._broken = False
+        self._peer_failed = False
 
     def close(self):
         if self._peer is not None:
@@ -122,7 +156,11 @@ class ShardedSearcher:
             self._peer = None
 
     def search(self, queries: torch.Tensor, k: int):
-        """Returns (scores [b,k] fp32, global rows [b,k] int64), identical on every rank."""
+        """Returns (scores [b,k] fp32, global rows [b,k] int64), identical on every rank.  Everything is
+        stream-ordered (capturable); a peer that misses the exchange is reported through `status` — use
+        `search_checked` (or read `status` with the results) wherever the results leave the device."""
+        if self._broken:
+            raise RuntimeError("the shard exchange failed earlier (a peer timed out): call reset() on every rank first")
         s, r = self.local_search(queries, k)
         if self.world == 1 and self._merge is None:
             return s, r.to(torch.int64)                       # one shard: nothing to exchange or merge
