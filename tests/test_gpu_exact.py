@@ -461,3 +461,69 @@ def test_facade_chunks_very_large_batches(eng):
     assert np.array_equal(r0, r1) and np.array_equal(s0, s1)
     ro, so = exact.exact_search_batch(store, q, 5)
     assert compare.check_topk_batch(r1, s1, ro, so) == []
+
+
+def test_empty_store_fill_is_minus_inf(eng):
+    """n == 0 through the C-ABI: rows -1 and scores -inf as the header promises (not a NaN pattern)."""
+    engine, _lib, torch = eng
+    sc = engine.Scanner()
+    mat = torch.zeros((1, 64), dtype=torch.float32, device=sc.device)
+    q = torch.randn((3, 64), device=sc.device)
+    s, r = sc.scan(mat, 0, 64, q, 5)
+    torch.cuda.synchronize()
+    assert bool((r == -1).all()) and bool(torch.isinf(s).all()) and bool((s < 0).all())
+
+
+def test_add_frames_takes_cuda_tensors(eng):
+    """the encoder's output stays on the device (no .cpu().numpy() round trip); host appends
+    and device appends interleave, the list surface keeps working."""
+    engine, _lib, torch = eng
+    from video_quierer_b200.flat_index import B200FlatIndex, DeviceRows
+    store = synth.clip_like(9000, 512, seed=121)
+    q = synth.clip_like(6, 512, seed=122, n_store=9000)
+    idx = B200FlatIndex()
+    idx.add_frames(store[:2000], ["a.mp4"] * 2000, np.arange(2000, dtype=float))                  # host rows first
+    idx.add_frames(torch.from_numpy(store[2000:7000]).cuda(), ["b.mp4"] * 5000, np.arange(5000, dtype=float))
+    idx.add_frame(store[7000], "c.mp4", 0.0)                                                       # reference call
+    idx.add_frames(torch.from_numpy(store[7001:]).cuda(), ["d.mp4"] * 1999, np.arange(1999, dtype=float))
+    assert isinstance(idx.embeddings, DeviceRows) and len(idx.embeddings) == 9000 == len(idx.metadata)
+    assert np.array_equal(idx.embeddings[6999], store[6999]) and np.array_equal(idx.embeddings[-1], store[-1])
+    s, r = idx.search_arrays(q, 10)
+    ro, so = exact.exact_search_batch(store, q, 10)
+    assert compare.check_topk_batch(r, s, ro, so) == []
+    hit = idx.search(store[7000], 1)[0]
+    assert hit["video_name"] == "c.mp4" and hit["frame_id"] == 7000
+    idx.materialise()                                      # back to the reference's list form for handlers that pop rows
+    idx.embeddings.pop(7000); idx.metadata.pop(7000)
+    assert idx.search(store[7000], 1)[0]["frame_id"] != 7000 or idx.search(store[7000], 1)[0]["video_name"] != "c.mp4"
+
+
+def test_scheduler_and_microbatcher_over_real_index(eng):
+    """SURVEY.md 8(f) rank 1 on the device: BatchSearchScheduler (the body of /api/search/batch) and the MicroBatcher
+    over a real B200FlatIndex return what the reference's sequential loop returns."""
+    from video_quierer_b200.flat_index import B200FlatIndex
+    from video_quierer_b200.scheduler import BatchSearchScheduler, MicroBatcher
+    store = synth.clip_like(12000, 512, seed=131)
+    idx = B200FlatIndex()
+    idx.add_frames(store, [f"v{i // 500}.mp4" for i in range(12000)], [float(i % 500) for i in range(12000)])
+    texts = [f"query {i}" for i in range(40)]
+    vecs = {t: synth.clip_like(1, 512, seed=200 + i, n_store=12000)[0] for i, t in enumerate(texts)}
+    sched = BatchSearchScheduler(encode=lambda t: vecs[t], index=idx)
+    body = sched.batch_response(texts, 5)
+    assert body["query_count"] == 40 and body["total_results"] == 200
+    for t, entry in zip(texts, body["results"]):
+        ro, so = exact.exact_search(store, vecs[t], 5)
+        assert entry["query"] == t and entry["count"] == 5
+        assert compare.check_topk_batch(np.array([[h["frame_id"] for h in entry["results"]]]),
+                                        np.array([[h["score"] for h in entry["results"]]], dtype=np.float32), ro[None], so[None]) == []
+        assert all(h["formatted_time"] == f"{int(h['timestamp'] // 60)}m{int(h['timestamp'] % 60)}s" for h in entry["results"])
+    single = sched.single_response(texts[3], 5)
+    assert [h["frame_id"] for h in single["results"]] == [h["frame_id"] for h in body["results"][3]["results"]]
+    mb = MicroBatcher(idx, max_batch=16, max_wait_ms=5.0)
+    try:
+        futs = [mb.submit(vecs[t], 5) for t in texts]
+        got = [f.result(timeout=60) for f in futs]
+    finally:
+        mb.close()
+    assert [[h["frame_id"] for h in hits] for hits in got] == [[h["frame_id"] for h in e["results"]] for e in body["results"]]
+    assert mb.batches_flushed < 40                          # requests were coalesced

@@ -249,3 +249,30 @@ def test_sharded_subgraphs_merge(built_lib):
     rec = compare.recall_at_k(mr, truth)
     print(f"sharded HNSW: merged recall@10={rec:.3f}, per-shard {np.round(per_shard, 3)}")
     assert rec >= np.mean(per_shard) - 0.02
+
+
+def test_readded_ids_still_return_k_hits_and_degree_is_validated(built_lib):
+    """an id that is added again supersedes its old row (the reference overwrites data[node_id] in place
+    and still returns k hits); M / max_M beyond the device graph's degree limit fail at construction."""
+    from video_quierer_b200.hnsw_index import B200HNSWIndex, MAX_DEGREE
+    with pytest.raises(ValueError):
+        B200HNSWIndex(dimension=64, M=MAX_DEGREE + 1)
+    with pytest.raises(ValueError):
+        B200HNSWIndex(dimension=64, M=16, max_M=40)
+    x = synth.clip_like(3000, 64, seed=141)
+    h = B200HNSWIndex(dimension=64, M=16, ef_construction=200, ef_search=64, max_M=16)
+    h.add_batch(list(x), list(range(3000)))
+    h.build()
+    moved = synth.clip_like(20, 64, seed=142, n_store=3000)
+    for i in range(20):
+        h.add(moved[i], i)                                  # ids 0..19 re-added with new vectors
+    q = x[5]                                                # the OLD vector of id 5: its row is dead now
+    res = h.search(q, 10)
+    assert len(res) == 10 and len({r["id"] for r in res}) == 10
+    live = np.concatenate([moved, x[20:]])
+    live_ids = list(range(20)) + list(range(20, 3000))
+    truth = [live_ids[j] for j in np.argsort(-(live @ (q / np.linalg.norm(q))))[:10]]
+    assert len(set(truth) & {r["id"] for r in res}) >= 8
+    got5 = [r for r in res if r["id"] == 5]
+    if got5:                                                # if id 5 is returned it is scored with its NEW vector
+        assert abs(float(got5[0]["score"]) - float(moved[5] @ (q / np.linalg.norm(q)))) < 1e-4
