@@ -250,14 +250,14 @@ __device__ __forceinline__ void filter_insert(const uint32_t (&v)[32], int row_b
 // a row of the exact top-k has exact score >= s_k, i.e. bf16 score >= s_k - eps >= S_k - 2*eps >= thr_c at
 // any time (thr only grows towards S_k).  The collected set therefore contains the exact top-k.
 template <int KL, typename Flush>
-__device__ __forceinline__ void filter_collect(const uint32_t (&v)[32], int row_base, int left, float g_keep, const float& eps2,
+__device__ __forceinline__ float filter_collect(const uint32_t (&v)[32], int row_base, int left, float g_keep, const float& eps2,
                                                float& thr, float& thr_c, float (&ls)[KL], int (&lr)[KL],
                                                float* stage_s, int* stage_r, int& staged, Flush&& flush) {
     float m = __uint_as_float(v[0]);
 #pragma unroll
     for (int j = 1; j + 1 < 32; j += 2) m = fmaxf(fmaxf(m, __uint_as_float(v[j])), __uint_as_float(v[j + 1]));
     m = fmaxf(m, __uint_as_float(v[31]));
-    if (!(m >= thr_c)) return;
+    if (!(m >= thr_c)) return m;
     unsigned mask = 0;
 #pragma unroll
     for (int j = 0; j < 32; ++j) mask |= (__uint_as_float(v[j]) >= thr_c) ? (1u << j) : 0u;
@@ -288,6 +288,37 @@ __device__ __forceinline__ void filter_collect(const uint32_t (&v)[32], int row_
             thr_c = thr - eps2;
         }
     }
+    return m;
+}
+
+// Cooperative bound of the exact mode (one per launch, device pointers into the workspace):
+//   cmax    [b_pad][groups * ms]  running maximum of sub-stream j (tiles it % ms == j) of CTA `group` for the query
+//                                 — every entry is the score of a row no other entry covers, so the k-th largest
+//                                 entry of a query's row is a lower bound of its k-th best score over the store
+//   arrived [n_qt]                CTAs of a query tile that have published the maxima of their first boot_T tiles
+struct XShared { float* cmax; int* arrived; int ms; int boot_T; };
+constexpr int kMaxSub = 8;              // sub-streams per CTA at most
+
+// A lower bound of the k-th largest of the V published maxima of one query (warp-cooperative, all lanes return
+// it; -inf while fewer than k maxima are known).  Every lane keeps the two largest of its strided share, then k
+// rounds of (warp max, retire it on the lowest lane holding it, promote that lane's second value).  Where a lane
+// would have needed a third value the result is the k-th largest of a SUBSET of the maxima — smaller or equal,
+// i.e. still a valid bound.
+__device__ __forceinline__ float kth_largest_published(const float* __restrict__ cm, int V, int k, int lane) {
+    float t1 = VQ_NEG_INF, t2 = VQ_NEG_INF;
+    for (int i = lane; i < V; i += 32) {
+        const float v = __ldcg(cm + i);
+        if (v > t1) { t2 = t1; t1 = v; } else if (v > t2) t2 = v;
+    }
+    float kth = VQ_NEG_INF;
+    for (int j = 0; j < k; ++j) {
+        const unsigned key = ~vq_score_key(t1);                       // monotone increasing in the score
+        const unsigned mx = __reduce_max_sync(0xffffffffu, key);
+        const unsigned who = __ballot_sync(0xffffffffu, key == mx);
+        kth = vq_key_score(~mx);
+        if (lane == __ffs(who) - 1) { t1 = t2; t2 = VQ_NEG_INF; }
+    }
+    return kth;
 }
 
 template <int KL, int NT, int MODE>
@@ -298,7 +329,8 @@ scan_mma_bf16_kernel(const __grid_constant__ CUtensorMap tmS,
                      int n, int ld, int nkb, int n_qt, int k, int stages, int grp_log2, int cl, int tile_mul, int b_pad,
                      float* __restrict__ cand_s,              // [b_pad, cap] surviving candidates (BOOT: [tiles, b_pad] maxima)
                      int* __restrict__ cand_r, int* __restrict__ cand_cnt, int cap, int dbg,
-                     const float* __restrict__ qeps) {            // [b_pad] per-query score-error bound (exact mode)
+                     const float* __restrict__ qeps,              // [b_pad] per-query score-error bound (exact mode)
+                     const XShared xs) {                          // exact mode: cooperative bound (see XShared)
     constexpr int B_KB_BYTES = NT * 128;
     constexpr uint32_t A_COL0 = 2 * NT;                         // first TMEM column of the query tile
     extern __shared__ unsigned char smem_raw[];
@@ -316,6 +348,15 @@ scan_mma_bf16_kernel(const __grid_constant__ CUtensorMap tmS,
     const int q_tile = blockIdx.x % n_qt, group = blockIdx.x / n_qt, n_groups = gridDim.x / n_qt;
     const int n_tiles = (n + NT - 1) / NT;
     const int grp_mask = (1 << grp_log2) - 1;          // ring slots are released 2^grp_log2 at a time
+    // This CTA's tiles: group, group + n_groups, ...  Exact mode scans its first boot_T tiles twice: first for
+    // their maxima only (threshold bootstrap inside the kernel), again at the very end with the bound in place.
+    const int n_local = group < n_tiles ? (n_tiles - group + n_groups - 1) / n_groups : 0;
+    const int boot_T = MODE == kModeExact ? (xs.boot_T < n_local ? xs.boot_T : n_local) : 0;
+    const int n_iter = n_local + boot_T;
+    auto tile_at = [&](int it) { return group + (it < n_local ? it : it - n_local) * n_groups; };
+    // exact mode: bound per query of this tile (refreshed by warp 3), flags
+    float* sbound = reinterpret_cast<float*>(smem + (size_t)stages * B_KB_BYTES + 512 + (size_t)QT * kStage * 8);
+    int* sflags = reinterpret_cast<int*>(sbound + QT);          // [0] epilogue warps past the boot tiles, [1] bound ready, [2] epilogue warps done
 
     if (warp == 0 && lane == 0) tma_prefetch_desc(&tmS);
     if (warp == 1 && lane == 0) {
@@ -338,6 +379,11 @@ scan_mma_bf16_kernel(const __grid_constant__ CUtensorMap tmS,
     // everything above touched no global memory: it overlaps the previous kernel of the stream (PDL)
     vq_pdl_wait();
     vq_pdl_trigger();
+    if (MODE == kModeExact) {
+        if (threadIdx.x < QT) sbound[threadIdx.x] = gtau[q_tile * QT + threadIdx.x];    // -inf, or +inf for padding queries
+        if (threadIdx.x < 4) sflags[threadIdx.x] = 0;
+        __syncthreads();
+    }
 
     // Producer and MMA warps run their loops with ALL lanes (addresses, counters and descriptors stay
     // in uniform registers) and elect one lane only for the asynchronous instruction itself: a loop
@@ -346,7 +392,8 @@ scan_mma_bf16_kernel(const __grid_constant__ CUtensorMap tmS,
     if (warp == 0) {
         int stage = 0; uint32_t phase = 0;
         const uint32_t sB_addr = smem_u32(sB), full_addr = smem_u32(full);
-        for (int tile = group; tile < n_tiles; tile += n_groups) {
+        for (int it_p = 0; it_p < n_iter; ++it_p) {
+            const int tile = tile_at(it_p);
             for (int kb = 0; kb < nkb; ++kb) {
                 if ((stage & grp_mask) == 0) mbar_wait(&empty[stage >> grp_log2], phase ^ 1);   // whole group free
                 if (elect_one()) {
@@ -380,7 +427,7 @@ scan_mma_bf16_kernel(const __grid_constant__ CUtensorMap tmS,
         int stage = 0; uint32_t phase = 0; int it = 0;
         long long dbg_c0 = 0, dbg_t0 = 0;
         if (dbg & 128) { dbg_c0 = clock64(); asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(dbg_t0)); }
-        for (int tile = group; tile < n_tiles; tile += n_groups, ++it) {
+        for (; it < n_iter; ++it) {
             const int acc = it & 1;
             const uint32_t acc_phase = (it >> 1) & 1;
             mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
@@ -425,6 +472,44 @@ scan_mma_bf16_kernel(const __grid_constant__ CUtensorMap tmS,
             asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
             printf("[scan_mma dbg] issue loop: %d tiles, %lld cycles, %lld ns -> %.1f cycles/MMA, %.0f MHz\n", it, c1 - dbg_c0,
                    t1 - dbg_t0, (double)(c1 - dbg_c0) / ((double)it * nkb * 4), (double)(c1 - dbg_c0) / (double)(t1 - dbg_t0) * 1e3);
+        }
+    } else if (warp == 3 && MODE == kModeExact) {
+        // Bound refresher: sbound[query] = max(static bound, k-th largest of the maxima every CTA of this query tile
+        // has published so far).  First round after ALL CTAs have published their bootstrap tiles (bounded wait: the
+        // CTAs of a launch normally run in one wave, but nothing may depend on it), then periodically until the
+        // epilogue is done, backing off while nothing changes.
+        const int V = n_groups * xs.ms;
+        const float* cm_tile = xs.cmax + (size_t)(q_tile * QT) * V;
+        if (boot_T > 0) {
+            const long long t0 = clock64();
+            while (*reinterpret_cast<volatile int*>(&sflags[0]) < 4 && clock64() - t0 < 400000) __nanosleep(200);
+            __threadfence();
+            if (lane == 0) atomicAdd(xs.arrived + q_tile, 1);
+            while (*reinterpret_cast<volatile int*>(xs.arrived + q_tile) < n_groups && clock64() - t0 < 400000) __nanosleep(200);
+            __threadfence();
+        }
+        unsigned sleep_ns = 2000;
+        bool first = true;
+        while (true) {
+            bool changed = false;
+            for (int i = 0; i < QT; ++i) {
+                const float cur = *reinterpret_cast<volatile float*>(&sbound[i]);
+                if (cur == INFINITY) continue;                                 // padding query
+                const float kth = kth_largest_published(cm_tile + (size_t)i * V, V, k, lane);
+                if (kth > cur) {
+                    if (lane == 0) *reinterpret_cast<volatile float*>(&sbound[i]) = kth;
+                    changed = true;
+                }
+            }
+            if (first) {
+                __threadfence_block();
+                __syncwarp();
+                if (lane == 0) *reinterpret_cast<volatile int*>(&sflags[1]) = 1;
+                first = false;
+            }
+            if (*reinterpret_cast<volatile int*>(&sflags[2]) >= 4) break;
+            sleep_ns = changed ? 2000u : (sleep_ns < 32000u ? sleep_ns * 2 : sleep_ns);
+            __nanosleep(sleep_ns);
         }
     } else if (warp >= 4) {
         const int ew = warp - 4;                          // == warp % 4: TMEM lanes [32*ew, 32*ew+32)
@@ -509,13 +594,15 @@ scan_mma_bf16_kernel(const __grid_constant__ CUtensorMap tmS,
             if (staged) flush();
         } else if (MODE == kModeExact) {
             // single-pass exact search: register list for the running k-th best + collection of every row
-            // within 2*eps of it (see filter_collect)
+            // within 2*eps of the bound (see filter_collect).  The bound is max(own k-th best, sbound[query]):
+            // sbound is the k-th largest of the maxima all CTAs of this query tile have published (warp 3).
             float ls[KL];
             int lr[KL];
 #pragma unroll
             for (int i = 0; i < KL; ++i) { ls[i] = i < k ? VQ_NEG_INF : INFINITY; lr[i] = VQ_EMPTY_ROW; }
             float eps2 = 2.f * qeps[q];              // -inf once the buffer has overflowed: thr_c = +inf, nothing passes
             const size_t dst = (size_t)q * cap;
+            const int ql = lane * 4 + ew;
             float* stage_s = reinterpret_cast<float*>(smem + (size_t)stages * B_KB_BYTES + 512) + (ew * 32 + lane);
             int* stage_r = reinterpret_cast<int*>(smem + (size_t)stages * B_KB_BYTES + 512 + (size_t)QT * kStage * 4) + (ew * 32 + lane);
             int staged = 0;
@@ -526,42 +613,78 @@ scan_mma_bf16_kernel(const __grid_constant__ CUtensorMap tmS,
                 staged = 0;
                 if (at + kStage > cap) eps2 = VQ_NEG_INF;    // overflow (mass ties): the finish kernel flags the query
             };
-            float published = VQ_NEG_INF;
-            int it = 0;
-            float g_next = *reinterpret_cast<volatile float*>(gtau + q);
-            for (int tile = group; tile < n_tiles; tile += n_groups, ++it) {
+            // published maxima of this thread's query: sub-stream j = first-pass tiles with it % ms == j
+            float smax[kMaxSub];
+#pragma unroll
+            for (int j = 0; j < kMaxSub; ++j) smax[j] = VQ_NEG_INF;
+            const int ms = xs.ms;
+            float* my_cmax = xs.cmax + ((size_t)q * n_groups + group) * ms;
+            auto publish = [&](int sub, float m) {
+#pragma unroll
+                for (int j = 0; j < kMaxSub; ++j)
+                    if (j == sub && m > smax[j]) { smax[j] = m; *reinterpret_cast<volatile float*>(my_cmax + j) = m; }
+            };
+            for (int it = 0; it < n_iter; ++it) {
                 const int acc = it & 1;
                 const uint32_t acc_phase = (it >> 1) & 1;
-                const float g = g_next;
-                g_next = *reinterpret_cast<volatile float*>(gtau + q);
+                const int tile = tile_at(it);
+                const int row0 = tile * NT;
+                const int valid = (n - row0) < NT ? (n - row0) : NT;
+                constexpr int n_chunks = NT / 32;
+                if (it < boot_T) {
+                    // ---- bootstrap tiles: only the maximum is taken (they are scanned again at the end)
+                    mbar_wait(&tmem_full[acc], acc_phase);
+                    tc_fence_after();
+                    float m = VQ_NEG_INF;
+#pragma unroll 1
+                    for (int c0 = 0; c0 < NT; c0 += 32) {
+                        uint32_t v[32];
+                        tmem_ld32(lane_base + (uint32_t)(acc * NT + c0), v);
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) m = (c0 + j < valid) ? fmaxf(m, __uint_as_float(v[j])) : m;
+                    }
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+                    publish(it % ms, m);
+                    if (it == boot_T - 1) {
+                        // all maxima of this warp are out: tell warp 3, then wait (bounded) for the first bound
+                        __threadfence();
+                        __syncwarp();
+                        if (lane == 0) atomicAdd(&sflags[0], 1);
+                        const long long t0 = clock64();
+                        while (*reinterpret_cast<volatile int*>(&sflags[1]) == 0 && clock64() - t0 < 200000) __nanosleep(100);
+                    }
+                    continue;
+                }
+                const float g = *reinterpret_cast<volatile float*>(&sbound[ql]);
                 const float g_keep = (g == VQ_NEG_INF) ? g : nextafterf(g, VQ_NEG_INF);
                 float thr = fmaxf(ls[0], g_keep);
                 float thr_c = thr - eps2;
                 mbar_wait(&tmem_full[acc], acc_phase);
                 tc_fence_after();
-                const int row0 = tile * NT;
-                const int valid = (n - row0) < NT ? (n - row0) : NT;
-                constexpr int n_chunks = NT / 32;
                 uint32_t va[32], vb[32];
+                float tmax = VQ_NEG_INF;
                 tmem_ld32_issue(lane_base + (uint32_t)(acc * NT), va);
 #pragma unroll 1
                 for (int c = 0; c < n_chunks; c += 2) {
                     tmem_ld_wait(va);
                     tmem_ld32_issue(lane_base + (uint32_t)(acc * NT + (c + 1) * 32), vb);
-                    filter_collect<KL>(va, row0 + c * 32, valid - c * 32, g_keep, eps2, thr, thr_c, ls, lr, stage_s, stage_r, staged, flush);
+                    tmax = fmaxf(tmax, filter_collect<KL>(va, row0 + c * 32, valid - c * 32, g_keep, eps2, thr, thr_c, ls, lr, stage_s, stage_r, staged, flush));
                     tmem_ld_wait(vb);
                     if (c + 2 < n_chunks) tmem_ld32_issue(lane_base + (uint32_t)(acc * NT + (c + 2) * 32), va);
-                    filter_collect<KL>(vb, row0 + (c + 1) * 32, valid - (c + 1) * 32, g_keep, eps2, thr, thr_c, ls, lr, stage_s, stage_r, staged, flush);
+                    tmax = fmaxf(tmax, filter_collect<KL>(vb, row0 + (c + 1) * 32, valid - (c + 1) * 32, g_keep, eps2, thr, thr_c, ls, lr, stage_s, stage_r, staged, flush));
                 }
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&tmem_empty[acc]);
-                if (ls[0] > published) {
-                    published = ls[0];
-                    atomic_max_float(gtau + q, published);
-                }
+                // first pass over a full tile: its maximum feeds the cooperative bound (a partial tile's maximum would
+                // include the zero scores of the padding rows; re-scanned tiles were counted in their first pass)
+                if (it < n_local && valid == NT) publish(it % ms, tmax);
             }
             if (staged) flush();
+            __syncwarp();
+            if (lane == 0) atomicAdd(&sflags[2], 1);
         } else if (MODE == kModeBoot) {
             // threshold bootstrap: only the per-query maximum of every sample tile is kept
             int it = 0;
@@ -670,12 +793,18 @@ prep_queries_bf16_kernel(const float* __restrict__ src, int b, int dim, int src_
                          int b_pad, int mode, float* __restrict__ gtau, int* __restrict__ cand_cnt,
                          const float* __restrict__ thr_in,     // collect pass: per-query thresholds (NULL otherwise)
                          const float* __restrict__ bounds,     // exact mode: {max |x^|, max |x^ - x|} over the store's rows
-                         float* __restrict__ qeps) {           // exact mode: per-query bound on |bf16 score - fp32 score|
+                         float* __restrict__ qeps,             // exact mode: per-query bound on |bf16 score - fp32 score|
+                         float* __restrict__ cmax, int cmax_v, // exact mode: published maxima [b_pad][cmax_v], reset to -inf
+                         int* __restrict__ arrived, int n_qt) {
     const int lane = threadIdx.x & 31;
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     vq_pdl_wait();                     // the previous search's kernels still read gtau / cand_cnt / dst
     vq_pdl_trigger();
     if (row >= b_pad) return;
+    if (cmax) {
+        for (int c = lane; c < cmax_v; c += 32) cmax[(size_t)row * cmax_v + c] = VQ_NEG_INF;
+        if (lane == 0 && row < n_qt) arrived[row] = 0;
+    }
     __nv_bfloat16* o = dst + (size_t)row * ld;
     // padding queries (zero rows of the last query tile) must neither keep nor gather anything: bound +inf
     if (lane == 0) { gtau[row] = row < b ? (thr_in ? thr_in[row] : VQ_NEG_INF) : INFINITY; cand_cnt[row] = 0; }
@@ -852,7 +981,7 @@ MmaPlan plan(int64_t n, int ld, int b, int k) {
     // each other, a prefix of the store would only know the first few videos
     p.boot_mul = p.boot_tiles ? (int)((n / p.nt) / p.boot_tiles) : 1;
     if (p.boot_mul < 1) p.boot_mul = 1;
-    p.smem = 1024 + (size_t)p.stages * stage_bytes + 512 + (size_t)QT * kStage * 8;
+    p.smem = 1024 + (size_t)p.stages * stage_bytes + 512 + (size_t)QT * kStage * 8 + (size_t)QT * 4 + 64;
     // candidate capacity is sized for the largest group count any batch <= b can get (the HNSW builder
     // reuses one workspace for a shrinking last batch)
     const int max_groups = sms > p.n_qt ? sms : p.n_qt;
@@ -870,12 +999,13 @@ MmaPlan plan(int64_t n, int ld, int b, int k) {
 }
 
 struct MmaWs {
-    float* gtau; int* cnt; float* cand_s; int* cand_r; float* boot_max; __nv_bfloat16* qbf; float* qeps;
+    float* gtau; int* cnt; float* cand_s; int* cand_r; float* boot_max; __nv_bfloat16* qbf; float* qeps; XShared xs;
 };
 MmaWs carve(const MmaPlan& p, void* ws_v) {
     unsigned char* ws = (unsigned char*)ws_v;
     MmaWs w;
     w.qeps = nullptr;
+    w.xs = XShared{nullptr, nullptr, 1, 0};
     w.gtau = (float*)(ws + p.off_tau);
     w.cnt = (int*)(ws + p.off_cnt);
     w.cand_s = (float*)(ws + p.off_cand_s);
@@ -883,6 +1013,7 @@ MmaWs carve(const MmaPlan& p, void* ws_v) {
     w.boot_max = (float*)(ws + p.off_boot);
     w.qbf = (__nv_bfloat16*)(ws + p.off_qbf);
     w.qeps = nullptr;
+    w.xs = XShared{nullptr, nullptr, 1, 0};
     return w;
 }
 
@@ -901,7 +1032,7 @@ cudaError_t launch_mma(const MmaPlan& p, const CUtensorMap& tmS, const __nv_bflo
     const int cl = (MODE == kModeList || MODE == kModeExact) ? p.cl : 1;
     return vq_launch_cluster(BOOT ? 1 : 3, cl, kern, dim3(grid), dim3(kThreads), p.smem, stream, tmS, qbf, w.gtau, n, ld, p.nkb, p.n_qt,
                              k, p.stages, p.grp_log2, cl, BOOT ? p.boot_mul : 1, p.b_pad, BOOT ? w.boot_max : w.cand_s, w.cand_r, w.cnt, p.cap, dbg,
-                             (const float*)w.qeps);
+                             (const float*)w.qeps, w.xs);
 }
 
 // [boot pass ->] main pass; gtau / cnt must have been reset by the caller's prologue kernel.
@@ -1036,7 +1167,7 @@ int vq_scan_mma_run(const void* store, int64_t n, int dim, int ld, int store_dty
     }
     const MmaWs w = carve(p, ws_v);
     if (vq_launch(0, prep_queries_bf16_kernel, dim3((p.b_pad + 7) / 8), dim3(256), 0, stream, queries, b, dim, dim, w.qbf, ld,
-                  p.b_pad, query_norm, w.gtau, w.cnt, (const float*)nullptr, (const float*)nullptr, (float*)nullptr) != cudaSuccess) {
+                  p.b_pad, query_norm, w.gtau, w.cnt, (const float*)nullptr, (const float*)nullptr, (float*)nullptr, (float*)nullptr, 0, (int*)nullptr, 0) != cudaSuccess) {
         vq_set_error("launch of prep_queries_bf16_kernel failed: %s", cudaGetErrorString(cudaGetLastError()));
         return VQ_ECUDA;
     }
@@ -1079,6 +1210,7 @@ int vq_scan_mma_collect(const void* store_bf16, const float* store_f32, int64_t 
     unsigned char* ws = (unsigned char*)ws_v;
     MmaWs w;
     w.qeps = nullptr;
+    w.xs = XShared{nullptr, nullptr, 1, 0};
     w.gtau = (float*)(ws + p.off_tau);
     w.cnt = (int*)(ws + p.off_cnt);
     const size_t cand_bytes = align256((size_t)p.b_pad * cap * 4);
@@ -1088,7 +1220,7 @@ int vq_scan_mma_collect(const void* store_bf16, const float* store_f32, int64_t 
     w.boot_max = (float*)(ws + p.off_cand_s + 2 * cand_bytes + align256((size_t)p.b_pad * ld * 2));
     p.cap = cap;
     if (vq_launch(0, prep_queries_bf16_kernel, dim3((p.b_pad + 7) / 8), dim3(256), 0, stream, queries, b, dim, dim, w.qbf, ld,
-                  p.b_pad, query_norm, w.gtau, w.cnt, thresholds, (const float*)nullptr, (float*)nullptr) != cudaSuccess) {
+                  p.b_pad, query_norm, w.gtau, w.cnt, thresholds, (const float*)nullptr, (float*)nullptr, (float*)nullptr, 0, (int*)nullptr, 0) != cudaSuccess) {
         vq_set_error("launch of prep_queries_bf16_kernel failed");
         return VQ_ECUDA;
     }
@@ -1142,41 +1274,47 @@ int vq_exact_finish_launch(const float* cand_s, const int* cand_r, const int* ca
 namespace {
 // Exact-mode plan: the scan plan for lists of k entries with a candidate buffer of `cap` slots per query
 // (appends of the whole scan, not just list survivors) and the per-query eps array.
-struct ExactPlan { MmaPlan p; int k_sel; size_t off_eps; };
+struct ExactPlan { MmaPlan p; int k_sel, ms, boot_T; size_t off_eps, off_cmax, off_arrived; };
 ExactPlan plan_exact(int64_t n, int ld, int b, int k) {
     ExactPlan x;
     MmaPlan& p = x.p;
     p = plan(n, ld, b, k);
     const int sms = vq_num_sms();
     const long long n_tiles = (n + p.nt - 1) / p.nt;
-    // rows a query may gather: the rows within 2 eps of its k-th best plus the transient while the shared
-    // bound warms up (measured: a few hundred on iid data, 1-3 thousand on tightly clustered data at <= 8
-    // query tiles; with more query tiles every CTA sees a larger part of the store and its own bound is better)
+    // rows a query may gather: the rows within 2 eps of its k-th best plus the transient while the bound warms up
+    // (measured: a few hundred on iid data, 1-2 thousand on tightly clustered data)
     int cap = p.n_qt <= 8 ? 4096 : (p.n_qt <= 16 ? 2048 : 1024);
     static const int cap_env = getenv("VQ_EXACT_CAP") ? atoi(getenv("VQ_EXACT_CAP")) : 0;
     if (cap_env > 0) cap = cap_env;
     const long long n8 = (n + 7) / 8 * 8;
     if (cap > n8) cap = (int)n8;                  // a row is gathered at most once per query: cannot overflow
-    // the bound must be valid from the first tile on (a CTA whose bound is still -inf gathers its first k
-    // rows unconditionally, and on a short scan the CTA-local k-th best never gets tight): bootstrap whenever
-    // the store holds 2k full tiles — up to `bt` sample tiles, at most every second tile
+    // The bootstrap runs inside the scan (the first boot_T tiles of every CTA only publish their maxima and are
+    // scanned again at the end), so the launch has no boot pass of its own.
+    p.boot_tiles = p.boot_groups = 0;
+    p.boot_mul = 1;
+    // every CTA needs a few tiles for that: short stores run fewer groups (8 tiles each)
+    if ((long long)p.groups * 8 > n_tiles) {
+        p.groups = (int)(n_tiles / 8 > 0 ? n_tiles / 8 : 1);
+        p.grid = p.groups * p.n_qt;
+    }
+    // sub-streams per CTA: about 3k published maxima per query, so that their k-th largest is a strong bound
+    static const int ms_env = getenv("VQ_EXACT_SUB") ? atoi(getenv("VQ_EXACT_SUB")) : 0;
+    int ms = ms_env > 0 ? ms_env : (3 * k + p.groups - 1) / p.groups;
+    x.ms = ms < 1 ? 1 : (ms > kMaxSub ? kMaxSub : ms);
+    // bootstrap sample: max(#SMs, 4k) tiles per query tile (capped), at most a quarter of a CTA's tiles
+    static const int boot_env = getenv("VQ_EXACT_BOOT") ? atoi(getenv("VQ_EXACT_BOOT")) : -1;
     int bt = sms > 4 * k ? sms : 4 * k;
     if (bt > kMaxBootTiles) bt = kMaxBootTiles;
-    const long long full_tiles = n / p.nt;
-    if (bt > full_tiles / 2) bt = (int)(full_tiles / 2);
-    static const bool boot_on = getenv("VQ_MMA_BOOT") ? atoi(getenv("VQ_MMA_BOOT")) != 0 : true;
-    if (boot_on && bt >= k && cap < n8) {
-        p.boot_tiles = bt;
-        p.boot_groups = bt < p.groups ? bt : p.groups;
-        p.boot_mul = (int)(full_tiles / bt);
-        if (p.boot_mul < 1) p.boot_mul = 1;
-    } else {
-        p.boot_tiles = p.boot_groups = 0;
-        p.boot_mul = 1;
-        if (cap < n8 && (long long)p.groups * k > cap / 2) {     // no bootstrap: groups * k unconditional appends
-            p.groups = cap / (2 * k) > 0 ? cap / (2 * k) : 1;
-            p.grid = p.groups * p.n_qt;
-        }
+    int T = (bt + p.groups - 1) / p.groups;
+    if (T < x.ms) T = x.ms;                       // every sub-stream sees a bootstrap tile
+    if (T > 16) T = 16;
+    const long long per_cta = n_tiles / p.groups;
+    if (T > per_cta / 4) T = (int)(per_cta / 4);
+    if ((long long)p.groups * x.ms < k || cap >= n8) T = 0;       // no usable bound / nothing to protect
+    x.boot_T = boot_env >= 0 ? boot_env : T;
+    if (x.boot_T == 0 && cap < n8 && (long long)p.groups * k > cap / 2) {     // no bound at all: groups * k unconditional appends
+        p.groups = cap / (2 * k) > 0 ? cap / (2 * k) : 1;
+        p.grid = p.groups * p.n_qt;
     }
     p.cap = cap;
     x.k_sel = k <= 16 ? 32 : (k + (k / 2 > 22 ? k / 2 : 22));
@@ -1184,9 +1322,11 @@ ExactPlan plan_exact(int64_t n, int ld, int b, int k) {
     size_t o = p.off_cand_s;
     p.off_cand_r = o + cand_bytes;
     o += 2 * cand_bytes;
-    p.off_boot = o;   o += align256((size_t)kMaxBootTiles * p.b_pad * 4);
-    p.off_qbf = o;    o += align256((size_t)p.b_pad * ld * 2);
-    x.off_eps = o;    o += align256((size_t)p.b_pad * 4);
+    p.off_boot = o;    o += 256;                                       // (unused in exact mode)
+    p.off_qbf = o;     o += align256((size_t)p.b_pad * ld * 2);
+    x.off_eps = o;     o += align256((size_t)p.b_pad * 4);
+    x.off_cmax = o;    o += align256((size_t)p.b_pad * sms * kMaxSub * 4 / (p.n_qt > 0 ? p.n_qt : 1) + 1024);
+    x.off_arrived = o; o += align256((size_t)p.n_qt * 4);
     p.total = o;
     return x;
 }
@@ -1215,8 +1355,9 @@ int vq_scan_mma_exact(const void* store_bf16, const float* store_f32, int64_t n,
     }
     MmaWs w = carve(p, ws_v);
     w.qeps = (float*)((unsigned char*)ws_v + x.off_eps);
+    w.xs = XShared{(float*)((unsigned char*)ws_v + x.off_cmax), (int*)((unsigned char*)ws_v + x.off_arrived), x.ms, x.boot_T};
     if (vq_launch(0, prep_queries_bf16_kernel, dim3((p.b_pad + 7) / 8), dim3(256), 0, stream, queries, b, dim, dim, w.qbf, ld,
-                  p.b_pad, query_norm, w.gtau, w.cnt, (const float*)nullptr, bounds, w.qeps) != cudaSuccess) {
+                  p.b_pad, query_norm, w.gtau, w.cnt, (const float*)nullptr, bounds, w.qeps, w.xs.cmax, p.groups * w.xs.ms, w.xs.arrived, p.n_qt) != cudaSuccess) {
         vq_set_error("launch of prep_queries_bf16_kernel failed: %s", cudaGetErrorString(cudaGetLastError()));
         return VQ_ECUDA;
     }
