@@ -737,6 +737,54 @@ def run_ours(args):
                 "what": "B200FlatIndex.search_batch(host numpy [B, dim], k) -> list of B lists of k metadata dicts (+ 'score'), synchronous, "
                         "one step in flight; arrays_only = search_arrays (same call without building the dicts)"}
 
+    def hnsw_sharded_leg(n_queries=8192, efs=(64, 128, 256)):
+        """North-star: 'HNSW is partitioned as per-shard sub-graphs searched in parallel and merged the same way'.
+        Every rank builds the sub-graph of ITS shard of the store (rows already on the device), the per-shard beams are
+        exchanged + merged by the same peer-memory kernel as the exact path; recall@10 against the sharded exact search."""
+        from video_quierer_b200.hnsw_index import B200HNSWIndex
+        st0 = stores[0]
+        h = B200HNSWIndex(dimension=DIM, M=16, ef_construction=200, ef_search=64, max_M=16, device=dev)
+        t0 = time.perf_counter()
+        ok = 1
+        try:
+            h.add_device_rows(st0.f32[: st0.n, :DIM], level_seed=rank)
+            h.build()
+            torch.cuda.synchronize()
+        except Exception as e:  # noqa: BLE001 — every rank must learn about it before the first collective of the leg
+            print(f"[bench] rank {rank}: HNSW shard build failed ({type(e).__name__}: {e})", file=sys.stderr)
+            ok = 0
+        t_ok = torch.tensor([ok], dtype=torch.int32, device=dev)
+        if world > 1:
+            dist.all_reduce(t_ok, op=dist.ReduceOp.MIN)
+        if int(t_ok.item()) == 0:
+            return {"error": "HNSW shard build failed on a rank (see stderr)"}
+        build_s = time.perf_counter() - t0
+        q = device_queries(args.data, n_queries, DIM, dev, centres, seed=11).to(dev)
+        lanes[0].copy = 0
+        truth = torch.cat([lanes[0].search(q[s0:s0 + 1024].contiguous(), 10)[1] for s0 in range(0, n_queries, 1024)]).cpu().numpy()
+        sh = ShardedSearcher(h.as_local_search(), N_ROWS, device=dev, exchange=args.exchange)
+        runs = []
+        for ef in efs:
+            h.ef_search = ef
+            sh.search(q, 10)
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            s, r = sh.search(q, 10)
+            e1.record()
+            barrier()
+            t = torch.tensor([e0.elapsed_time(e1), float(h.last_overflow.sum().item())], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            rows = r.cpu().numpy()
+            rec = float(np.mean([len(set(rows[i]) & set(truth[i])) / 10 for i in range(n_queries)]))
+            runs.append({"ef": ef, "recall@10": round(rec, 4), "qps": round(n_queries / (float(t[0]) * 1e-3)), "ms": round(float(t[0]), 3),
+                         "visited_overflow_queries": int(t[1])})
+        sh.check()
+        sh.close()
+        return {"workload": f"HNSW per-shard sub-graphs, M=16 ef_construction=200 max_M=16, {N_ROWS}x{DIM} ({args.data}) over {world} GPU(s), "
+                            f"{n_queries} queries, k=10; recall vs the sharded exact search", "build_s_per_shard": round(build_s, 2), "runs": runs}
+
     with ClockSampler(local) as clocks:
         main = measure(args.batch, args.steps, args.warmup, True, sustain_s=args.sustain, with_parity=True)
         sweep = []
@@ -745,6 +793,12 @@ def run_ours(args):
                 if B != args.batch:
                     sweep.append(measure(B, min(args.steps, 30), 3, False))
         api = measure_api(main["host_q"], max(3, min(args.steps, 20))) if (world == 1 and exact and not args.no_api) else None
+        hnsw_sharded = None
+        if world > 1 and exact and args.config == 2 and not args.no_hnsw:
+            try:
+                hnsw_sharded = hnsw_sharded_leg()
+            except Exception as e:  # noqa: BLE001 — the headline line must survive a failure of the extra leg
+                hnsw_sharded = {"error": f"{type(e).__name__}: {e}"[:300]}
         if not args.no_sweep and args.config == 2:
             # the other distribution at the headline batch: same store shape, rows regenerated in place
             other = "gauss" if args.data == "clip" else "clip"
@@ -839,6 +893,8 @@ def run_ours(args):
             line["sustained"] = main["sustained"]
         if api is not None:
             line["e2e_api"] = api
+        if hnsw_sharded is not None:
+            line["hnsw_sharded"] = hnsw_sharded
         if world == 1 and not args.no_hnsw and args.config == 2:
             # BASELINE config 3 next to the headline: HNSW M=16 ef_construction=200 on 1M x 512 clustered
             # (CLIP-like) rows, ef_search 64-256, recall@10 against the exact scan, QPS and the

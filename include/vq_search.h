@@ -177,7 +177,12 @@ int vq_rescore_topk(const float* store_f32, int64_t n, int dim, int ld,
  * >= S_final - eps_q, so every row of the exact top-k has bf16 score >= s_k - eps_q >= S - 2*eps_q and is
  * gathered.  exact_finish re-scores the best candidates in fp32, which yields a lower bound s_lb <= s_k
  * reached by k real rows, then every other candidate with bf16 score >= s_lb - eps_q, and returns the best k
- * by (exact score desc, row asc).  k <= 64. */
+ * by (exact score desc, row asc).
+ * k <= 64: the running k-th best comes from per-query register lists plus the k-th largest of the maxima all
+ * CTAs publish (cooperative bound); 64 < k <= 128 (BASELINE config 4: k = 100): the cooperative bound alone.
+ * vq_search_exact_supported says whether a shape is served (ld <= 768, ld % 64 == 0, k <= 128, and for k > 64 a
+ * store large enough to bootstrap the bound); otherwise use vq_search_collect / vq_scan_topk. */
+int    vq_search_exact_supported(int64_t n, int dim, int ld, int b, int k);
 size_t vq_search_exact_workspace_bytes(int64_t n, int dim, int ld, int b, int k);
 int vq_search_exact(const void* store_bf16, const float* store_f32, int64_t n, int dim, int ld,
                     const float* queries, int b, int k, int query_norm, const float* store_bounds,
@@ -217,12 +222,16 @@ int vq_search_two_stage(const void* store_bf16, const float* store_f32, int64_t 
  *                rows are gathered, and the k-th exact score returned is a lower bound of the k-th best of
  *                any store containing these rows (step 1 of the large-k search);
  *   cap          candidate slots per query (k <= cap <= 16384), k <= 1024
+ *   store_bounds NULL: every gathered row is re-scored in fp32.  Else the store's device float[2] of vq_store_bounds:
+ *                only the best candidates by bf16 score and those within the per-query rounding bound of the k-th
+ *                exact score among them are re-scored (same argument and final stage as vq_search_exact) — what
+ *                makes k = 100 over millions of rows cheap (BASELINE config 4)
  *   out_overflow [b] int32: 1 = more than cap rows reached the threshold, the result is incomplete
  *                (re-run that query with vq_scan_topk on the fp32 store). [kernels: scan_mma_bf16<collect>, scan_finish] */
 size_t vq_search_collect_workspace_bytes(int64_t n, int dim, int ld, int b, int cap);
 int vq_search_collect(const void* store_bf16, const float* store_f32, int64_t n, int dim, int ld,
                       const float* queries, int b, int k, int query_norm, const float* thresholds, int cap,
-                      float* out_scores, int32_t* out_rows, int32_t* out_overflow,
+                      const float* store_bounds, float* out_scores, int32_t* out_rows, int32_t* out_overflow,
                       void* workspace, size_t workspace_bytes, void* stream);
 
 /* (d) HNSW greedy/beam search, one warp per query.                     [kernel: hnsw_search]

@@ -245,7 +245,14 @@ def _exact(eng, store, q, k, norm=None):
     st = engine.DeviceStore(store.shape[1], keep_fp32=True, keep_bf16=True)
     st.append(store)
     sc = engine.Scanner()
-    s, r, over = sc.exact(st, engine.as_device_queries(q, store.shape[1], st.device), k, _lib.NORM_EPS if norm is None else norm)
+    qd = engine.as_device_queries(q, store.shape[1], st.device)
+    if k <= 64:
+        s, r, over = sc.exact(st, qd, k, _lib.NORM_EPS if norm is None else norm)
+        assert sc.last_path == "scan_mma_bf16<exact>+finish"
+    else:           # the router: single pass where the gather cannot overflow, else sample pass + collect pass
+        from video_quierer_b200.flat_index import exact_search
+        s, r, over = exact_search(sc, st, qd, k)
+        assert sc.last_path.startswith("scan_mma_bf16<")
     torch.cuda.synchronize()
     return s.cpu().numpy(), r.cpu().numpy(), over.cpu().numpy(), st
 
@@ -254,10 +261,14 @@ def _exact(eng, store, q, k, norm=None):
     ("gauss", 1, 512, 1, 1), ("gauss", 7, 64, 3, 5), ("gauss", 127, 128, 4, 10), ("gauss", 129, 96, 4, 10),
     ("gauss", 4097, 512, 5, 10), ("gauss", 10001, 100, 17, 10), ("clip", 20000, 512, 130, 10),
     ("clip", 60000, 768, 300, 16), ("gauss", 40000, 256, 33, 32), ("clip", 50000, 512, 24, 50),
-    ("gauss", 30000, 512, 9, 64), ("clip", 300000, 512, 40, 10), ("ties", 8000, 128, 12, 20)])
+    ("gauss", 30000, 512, 9, 64), ("clip", 300000, 512, 40, 10), ("ties", 8000, 128, 12, 20),
+    ("gauss", 30000, 768, 12, 100), ("gauss", 120000, 768, 12, 100), ("clip", 90000, 512, 40, 100), ("gauss", 200000, 512, 300, 128),
+    ("clip", 150000, 768, 260, 100)])
 def test_vq_search_exact_vs_oracle(eng, gen, n, dim, b, k):
-    """vq_search_exact over ragged shapes, every list width (k <= 16 / 32 / 64), with and without the
-    threshold bootstrap, clustered data and exact duplicates: ids and scores of the oracle."""
+    """vq_search_exact over ragged shapes, every list width (k <= 16 / 32 / 64), bootstrap as a separate pass (one query
+    tile) and inside the scan (several), clustered data and exact duplicates; k = 100 / 128 (BASELINE config 4) through
+    the router (listless single pass on small stores, sample + collect passes with the exact_finish stage beyond):
+    ids and scores of the oracle."""
     store = {"gauss": synth.gauss, "clip": synth.clip_like, "ties": synth.with_ties}[gen](n, dim, seed=101)
     if gen == "ties":
         q = store[np.arange(b) * 7 % n] + 0.0

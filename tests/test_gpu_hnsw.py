@@ -276,3 +276,20 @@ def test_readded_ids_still_return_k_hits_and_degree_is_validated(built_lib):
     got5 = [r for r in res if r["id"] == 5]
     if got5:                                                # if id 5 is returned it is scored with its NEW vector
         assert abs(float(got5[0]["score"]) - float(moved[5] @ (q / np.linalg.norm(q)))) < 1e-4
+
+
+@pytest.mark.parametrize("kind", ["clip", "gauss"])
+def test_recall_at_100k_meets_the_reference_bar(built_lib, kind):
+    """North-star: 'HNSW must reach recall@10 >= the reference's recall at the same M/ef' — at 100k x 512, where the
+    reference's Python build is infeasible, the bar comes from its C++ restatement (oracle/hnsw_ref.cpp, validated
+    edge for edge on the reference's own 10k graphs; numbers in tests/golden/hnsw_ref_recall.json, produced by
+    tools/ref_recall_at_scale.py on these very rows and queries)."""
+    import json
+    import os
+    from tools.hnsw_recall_at_scale import measure
+    ref = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "hnsw_ref_recall.json")))[f"{kind}_100000"]
+    store = (synth.clip_like if kind == "clip" else synth.gauss)(100_000, 512, seed=synth.STORE_SEED)
+    assert synth.sha256_of(store) == ref["store_sha"], "numpy RNG stream changed; regenerate the reference recall"
+    got = measure(kind, 100_000)
+    for ef in ("64", "128", "256"):
+        assert got["runs"][ef]["recall@10"] >= ref["runs"][ef]["recall@10"] - 0.005, (ef, got["runs"][ef], ref["runs"][ef])

@@ -74,6 +74,20 @@ def _worker(rank, world, port, n, dim, k, ret):
         s, r = ss.search(torch.from_numpy(queries), k)
         ro, so = exact.exact_search_batch(store, queries, min(k, n))
         bad = compare.check_topk_batch(r.numpy()[:, : min(k, n)], s.numpy()[:, : min(k, n)], ro, so)
+        # checked read-out: on the collective route there is no exchange status, results come back as numpy; a
+        # searcher whose exchange failed refuses to search until every rank has reset it
+        assert ss.status is None
+        s2, r2 = ss.search_checked(torch.from_numpy(queries), k)
+        assert np.array_equal(r2, r.numpy()) and np.array_equal(s2, s.numpy())
+        ss._broken = True
+        try:
+            ss.search(torch.from_numpy(queries), k)
+            refused = False
+        except RuntimeError:
+            refused = True
+        ss.reset()
+        s3, r3 = ss.search_checked(torch.from_numpy(queries), k)
+        assert refused and np.array_equal(r3, r.numpy())
         ret[rank] = (len(bad), ss.world, ss.rank)
     finally:
         dist.destroy_process_group()

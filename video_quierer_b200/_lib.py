@@ -44,11 +44,12 @@ SIGNATURES = {
     "vq_search_two_stage_workspace_bytes": (_sz, [_i64, _i32, _i32, _i32, _i32]),
     "vq_search_two_stage": (_i32, [_vp, _vp, _i64, _i32, _i32, _vp, _i32, _i32, _i32, _i32, C.c_float,
                                    _vp, _vp, _vp, _vp, _sz, _vp]),
+    "vq_search_exact_supported": (_i32, [_i64, _i32, _i32, _i32, _i32]),
     "vq_search_exact_workspace_bytes": (_sz, [_i64, _i32, _i32, _i32, _i32]),
     "vq_search_exact": (_i32, [_vp, _vp, _i64, _i32, _i32, _vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "vq_store_bounds": (_i32, [_vp, _vp, _i64, _i32, _vp, _vp]),
     "vq_search_collect_workspace_bytes": (_sz, [_i64, _i32, _i32, _i32, _i32]),
-    "vq_search_collect": (_i32, [_vp, _vp, _i64, _i32, _i32, _vp, _i32, _i32, _i32, _vp, _i32,
+    "vq_search_collect": (_i32, [_vp, _vp, _i64, _i32, _i32, _vp, _i32, _i32, _i32, _vp, _i32, _vp,
                                  _vp, _vp, _vp, _vp, _sz, _vp]),
     "vq_hnsw_workspace_bytes": (_sz, [_i32, _i32, _i32]),
     "vq_hnsw_search": (_i32, [_vp, _i64, _i32, _i32, _i32, _vp, _vp, _i32, _vp, _vp, _i32, _i32, _i32, _i32,

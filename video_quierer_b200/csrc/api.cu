@@ -30,13 +30,14 @@ int vq_scan_mma_run(const void* store, int64_t n, int dim, int ld, int store_dty
 
 size_t vq_scan_mma_collect_workspace(int64_t n, int ld, int b, int cap);
 int vq_scan_mma_collect(const void* store_bf16, const float* store_f32, int64_t n, int dim, int ld, const float* queries,
-                        int query_norm, int b, const float* thresholds, int cap, int k, float* out_scores, int32_t* out_rows,
-                        int32_t* out_overflow, void* ws, size_t ws_bytes, cudaStream_t stream, int* launches);
+                        int query_norm, int b, const float* thresholds, int cap, const float* bounds, int k, float* out_scores,
+                        int32_t* out_rows, int32_t* out_overflow, void* ws, size_t ws_bytes, cudaStream_t stream, int* launches);
 
 size_t vq_scan_mma_exact_workspace(int64_t n, int ld, int b, int k);
 int vq_scan_mma_exact(const void* store_bf16, const float* store_f32, int64_t n, int dim, int ld, const float* queries,
                       int query_norm, int b, int k, const float* bounds, float* out_scores, int32_t* out_rows,
                       int32_t* out_overflow, int32_t* out_stats, void* ws, size_t ws_bytes, cudaStream_t stream, int* launches);
+bool vq_scan_mma_exact_supported(int64_t n, int ld, int b, int k);
 int vq_store_bounds_launch(const float* f32, const void* bf16, long long rows, int ld, float* bounds, cudaStream_t stream);
 int vq_fill_empty_launch(float* scores, int* rows, long long count, cudaStream_t stream);
 
@@ -356,6 +357,11 @@ size_t vq_search_exact_workspace_bytes(int64_t n, int dim, int ld, int b, int k)
     return vq_scan_mma_exact_workspace(n, ld, b, k) + 256;
 }
 
+int vq_search_exact_supported(int64_t n, int dim, int ld, int b, int k) {
+    (void)dim;
+    return vq_scan_mma_exact_supported(n, ld, b, k) ? 1 : 0;
+}
+
 int vq_search_exact(const void* store_bf16, const float* store_f32, int64_t n, int dim, int ld,
                     const float* queries, int b, int k, int query_norm, const float* store_bounds,
                     float* out_scores, int32_t* out_rows, int32_t* out_overflow, int32_t* out_stats,
@@ -363,7 +369,7 @@ int vq_search_exact(const void* store_bf16, const float* store_f32, int64_t n, i
     cudaStream_t stream = (cudaStream_t)stream_v;
     int rc = check_store(n, dim, ld, VQ_BF16);
     if (rc) return rc;
-    VQ_CHECK_ARG(b >= 0 && k > 0 && k <= 64, "need b >= 0 and 0 < k <= 64 (b=%d k=%d)", b, k);
+    VQ_CHECK_ARG(b >= 0 && k > 0 && k <= 128, "need b >= 0 and 0 < k <= 128 (b=%d k=%d)", b, k);
     VQ_CHECK_ARG(query_norm >= VQ_NORM_NONE && query_norm <= VQ_NORM_PLAIN, "bad query_norm %d", query_norm);
     if (b == 0) { vq_note_launch("none", 0); return VQ_OK; }
     VQ_CHECK_ARG(n > 0, "exact search needs a non-empty store");
@@ -386,7 +392,7 @@ size_t vq_search_collect_workspace_bytes(int64_t n, int dim, int ld, int b, int 
 }
 
 int vq_search_collect(const void* store_bf16, const float* store_f32, int64_t n, int dim, int ld,
-                      const float* queries, int b, int k, int query_norm, const float* thresholds, int cap,
+                      const float* queries, int b, int k, int query_norm, const float* thresholds, int cap, const float* store_bounds,
                       float* out_scores, int32_t* out_rows, int32_t* out_overflow,
                       void* workspace, size_t workspace_bytes, void* stream_v) {
     cudaStream_t stream = (cudaStream_t)stream_v;
@@ -400,7 +406,7 @@ int vq_search_collect(const void* store_bf16, const float* store_f32, int64_t n,
                  "NULL pointer argument");                       // thresholds may be NULL (derived from the store)
     VQ_CHECK_ARG(((uintptr_t)workspace & 255) == 0, "workspace must be 256-byte aligned");
     int launches = 0;
-    rc = vq_scan_mma_collect(store_bf16, store_f32, n, dim, ld, queries, query_norm, b, thresholds, cap, k, out_scores, out_rows,
+    rc = vq_scan_mma_collect(store_bf16, store_f32, n, dim, ld, queries, query_norm, b, thresholds, cap, store_bounds, k, out_scores, out_rows,
                              out_overflow, workspace, workspace_bytes, stream, &launches);
     if (rc) return rc;
     vq_note_launch("scan_mma_bf16<collect>+rescore", launches);

@@ -21,7 +21,7 @@ namespace {
 
 constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
-constexpr int kXMax = 1024;              // rows re-scored per query at most
+constexpr int kXMax = 2048;              // rows re-scored per query at most
 constexpr int kSelStop = 64;             // the bisection stops once this few keys (>= k_sel) are left
 
 // exact fp32 scores of rows[0..cnt) -> 64-bit (exact score key, row) keys; one warp per row, 4 rows of a

@@ -249,7 +249,7 @@ __device__ __forceinline__ void filter_insert(const uint32_t (&v)[32], int row_b
 // score.  The k rows that reach it have exact score >= S_k - eps, so the exact k-th best s_k >= S_k - eps;
 // a row of the exact top-k has exact score >= s_k, i.e. bf16 score >= s_k - eps >= S_k - 2*eps >= thr_c at
 // any time (thr only grows towards S_k).  The collected set therefore contains the exact top-k.
-template <int KL, typename Flush>
+template <int KL, bool LIST, typename Flush>
 __device__ __forceinline__ float filter_collect(const uint32_t (&v)[32], int row_base, int left, float g_keep, const float& eps2,
                                                float& thr, float& thr_c, float (&ls)[KL], int (&lr)[KL],
                                                float* stage_s, int* stage_r, int& staged, Flush&& flush) {
@@ -271,7 +271,7 @@ __device__ __forceinline__ float filter_collect(const uint32_t (&v)[32], int row
         stage_s[staged * QT] = s;
         stage_r[staged * QT] = row_base + j;
         if (++staged == kStage) flush();
-        if (s > thr) {
+        if (LIST && s > thr) {
             ls[0] = s;
             lr[0] = row_base + j;
 #pragma unroll
@@ -295,30 +295,46 @@ __device__ __forceinline__ float filter_collect(const uint32_t (&v)[32], int row
 //   cmax    [b_pad][groups * ms]  running maximum of sub-stream j (tiles it % ms == j) of CTA `group` for the query
 //                                 — every entry is the score of a row no other entry covers, so the k-th largest
 //                                 entry of a query's row is a lower bound of its k-th best score over the store
-//   arrived [n_qt]                CTAs of a query tile that have published the maxima of their first boot_T tiles
-struct XShared { float* cmax; int* arrived; int ms; int boot_T; };
+//   arrived [n_qt][4]             CTAs of a query tile whose epilogue warp w has published the maxima of its first boot_T tiles
+struct XShared { float* cmax; int* arrived; int ms; int boot_T; int refresh_ns; };   // refresh_ns: first sleep of the refresher (0 = no periodic refresh)
 constexpr int kMaxSub = 8;              // sub-streams per CTA at most
 
-// A lower bound of the k-th largest of the V published maxima of one query (warp-cooperative, all lanes return
-// it; -inf while fewer than k maxima are known).  Every lane keeps the two largest of its strided share, then k
-// rounds of (warp max, retire it on the lowest lane holding it, promote that lane's second value).  Where a lane
-// would have needed a third value the result is the k-th largest of a SUBSET of the maxima — smaller or equal,
-// i.e. still a valid bound.
-__device__ __forceinline__ float kth_largest_published(const float* __restrict__ cm, int V, int k, int lane) {
-    float t1 = VQ_NEG_INF, t2 = VQ_NEG_INF;
-    for (int i = lane; i < V; i += 32) {
-        const float v = __ldcg(cm + i);
-        if (v > t1) { t2 = t1; t1 = v; } else if (v > t2) t2 = v;
+// Lower bounds of the k-th largest of the V published maxima of 8 queries at once (warp-cooperative; all lanes
+// get all 8 results; -inf while fewer than k maxima are known).  The loads of the 8 queries (up to 5 per lane and
+// query: V <= 160) are issued together so that one L2 round trip serves the batch.  Every lane keeps the two
+// largest of its strided share per query, then k rounds of (warp max, retire it on the lowest lane holding it,
+// promote that lane's second value).  Where a lane would have needed a third value the result is the k-th largest of
+// a SUBSET of the maxima — smaller or equal, i.e. still a valid bound.
+constexpr int kMaxPublished = 160;
+__device__ __forceinline__ void kth_largest_batch8(const float* __restrict__ cm_tile, int V, int k, int lane, int ql0, int ql_step,
+                                                   float (&out)[8]) {
+    float t1[8], t2[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) { t1[u] = VQ_NEG_INF; t2[u] = VQ_NEG_INF; }
+#pragma unroll
+    for (int ii = 0; ii < kMaxPublished / 32; ++ii) {
+        const int i = lane + 32 * ii;
+        float v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = i < V ? __ldcg(cm_tile + (size_t)(ql0 + u * ql_step) * V + i) : VQ_NEG_INF;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            if (v[u] > t1[u]) { t2[u] = t1[u]; t1[u] = v[u]; } else if (v[u] > t2[u]) t2[u] = v[u];
+        }
     }
-    float kth = VQ_NEG_INF;
+    // the 8 selections advance in lockstep: 8 independent dependency chains per round hide the redux / ballot latency
+#pragma unroll
+    for (int u = 0; u < 8; ++u) out[u] = VQ_NEG_INF;
     for (int j = 0; j < k; ++j) {
-        const unsigned key = ~vq_score_key(t1);                       // monotone increasing in the score
-        const unsigned mx = __reduce_max_sync(0xffffffffu, key);
-        const unsigned who = __ballot_sync(0xffffffffu, key == mx);
-        kth = vq_key_score(~mx);
-        if (lane == __ffs(who) - 1) { t1 = t2; t2 = VQ_NEG_INF; }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const unsigned key = ~vq_score_key(t1[u]);                // monotone increasing in the score
+            const unsigned mx = __reduce_max_sync(0xffffffffu, key);
+            const unsigned who = __ballot_sync(0xffffffffu, key == mx);
+            out[u] = vq_key_score(~mx);
+            if (lane == __ffs(who) - 1) { t1[u] = t2[u]; t2[u] = VQ_NEG_INF; }
+        }
     }
-    return kth;
 }
 
 template <int KL, int NT, int MODE>
@@ -474,42 +490,33 @@ scan_mma_bf16_kernel(const __grid_constant__ CUtensorMap tmS,
                    t1 - dbg_t0, (double)(c1 - dbg_c0) / ((double)it * nkb * 4), (double)(c1 - dbg_c0) / (double)(t1 - dbg_t0) * 1e3);
         }
     } else if (warp == 3 && MODE == kModeExact) {
-        // Bound refresher: sbound[query] = max(static bound, k-th largest of the maxima every CTA of this query tile
-        // has published so far).  First round after ALL CTAs have published their bootstrap tiles (bounded wait: the
-        // CTAs of a launch normally run in one wave, but nothing may depend on it), then periodically until the
-        // epilogue is done, backing off while nothing changes.
+        // Bound refresher: sbound[query] = max(itself, k-th largest of the maxima every CTA of this query tile has
+        // published so far), recomputed periodically until the epilogue is done, backing off while nothing changes.
+        // (The first bound of a query comes from its epilogue warp, right after the bootstrap tiles.)
         const int V = n_groups * xs.ms;
         const float* cm_tile = xs.cmax + (size_t)(q_tile * QT) * V;
         if (boot_T > 0) {
             const long long t0 = clock64();
-            while (*reinterpret_cast<volatile int*>(&sflags[0]) < 4 && clock64() - t0 < 400000) __nanosleep(200);
-            __threadfence();
-            if (lane == 0) atomicAdd(xs.arrived + q_tile, 1);
-            while (*reinterpret_cast<volatile int*>(xs.arrived + q_tile) < n_groups && clock64() - t0 < 400000) __nanosleep(200);
-            __threadfence();
+            while (*reinterpret_cast<volatile int*>(&sflags[0]) < 4 && clock64() - t0 < 8000000) __nanosleep(500);
         }
-        unsigned sleep_ns = 2000;
-        bool first = true;
-        while (true) {
-            bool changed = false;
-            for (int i = 0; i < QT; ++i) {
-                const float cur = *reinterpret_cast<volatile float*>(&sbound[i]);
-                if (cur == INFINITY) continue;                                 // padding query
-                const float kth = kth_largest_published(cm_tile + (size_t)i * V, V, k, lane);
-                if (kth > cur) {
-                    if (lane == 0) *reinterpret_cast<volatile float*>(&sbound[i]) = kth;
-                    changed = true;
-                }
-            }
-            if (first) {
-                __threadfence_block();
-                __syncwarp();
-                if (lane == 0) *reinterpret_cast<volatile int*>(&sflags[1]) = 1;
-                first = false;
-            }
-            if (*reinterpret_cast<volatile int*>(&sflags[2]) >= 4) break;
-            sleep_ns = changed ? 2000u : (sleep_ns < 32000u ? sleep_ns * 2 : sleep_ns);
+        unsigned sleep_ns = (unsigned)xs.refresh_ns;
+        while (sleep_ns > 0 && *reinterpret_cast<volatile int*>(&sflags[2]) < 4) {
             __nanosleep(sleep_ns);
+            bool changed = false;
+            for (int q0 = 0; q0 < QT; q0 += 8) {
+                float cur = VQ_NEG_INF;
+                if (lane < 8) cur = *reinterpret_cast<volatile float*>(&sbound[q0 + lane]);
+                if (__all_sync(0xffffffffu, lane >= 8 || cur == INFINITY)) continue;           // 8 padding queries
+                float kth[8];
+                kth_largest_batch8(cm_tile, V, k, lane, q0, 1, kth);
+                float mine = VQ_NEG_INF;
+#pragma unroll
+                for (int u = 0; u < 8; ++u) mine = (lane == u) ? kth[u] : mine;
+                const bool up = lane < 8 && mine > cur;
+                if (up) *reinterpret_cast<volatile float*>(&sbound[q0 + lane]) = mine;
+                changed = changed || __any_sync(0xffffffffu, up);
+            }
+            sleep_ns = changed ? (unsigned)xs.refresh_ns : (sleep_ns < 16u * (unsigned)xs.refresh_ns ? sleep_ns * 2 : sleep_ns);
         }
     } else if (warp >= 4) {
         const int ew = warp - 4;                          // == warp % 4: TMEM lanes [32*ew, 32*ew+32)
@@ -596,10 +603,14 @@ scan_mma_bf16_kernel(const __grid_constant__ CUtensorMap tmS,
             // single-pass exact search: register list for the running k-th best + collection of every row
             // within 2*eps of the bound (see filter_collect).  The bound is max(own k-th best, sbound[query]):
             // sbound is the k-th largest of the maxima all CTAs of this query tile have published (warp 3).
+            // KL == 1: LISTLESS (k beyond the register lists, up to 128): the bound is the cooperative one alone —
+            // with about as many published maxima as k, their k-th largest sits within a few hundred ranks of the true
+            // k-th best, which is as tight as a gather for k ~ 100 needs to be.
+            constexpr bool LIST = KL > 1;
             float ls[KL];
             int lr[KL];
 #pragma unroll
-            for (int i = 0; i < KL; ++i) { ls[i] = i < k ? VQ_NEG_INF : INFINITY; lr[i] = VQ_EMPTY_ROW; }
+            for (int i = 0; i < KL; ++i) { ls[i] = (LIST && i < k) ? VQ_NEG_INF : INFINITY; lr[i] = VQ_EMPTY_ROW; }
             float eps2 = 2.f * qeps[q];              // -inf once the buffer has overflowed: thr_c = +inf, nothing passes
             const size_t dst = (size_t)q * cap;
             const int ql = lane * 4 + ew;
@@ -648,18 +659,36 @@ scan_mma_bf16_kernel(const __grid_constant__ CUtensorMap tmS,
                     if (lane == 0) mbar_arrive(&tmem_empty[acc]);
                     publish(it % ms, m);
                     if (it == boot_T - 1) {
-                        // all maxima of this warp are out: tell warp 3, then wait (bounded) for the first bound
+                        // The maxima of this warp's 32 queries are out.  Arrive on the (query tile, epilogue warp)
+                        // counter and wait — bounded — for the same warp of every other CTA: the k-th largest of what
+                        // they published is the first bound of these 32 queries (the threshold bootstrap).
                         __threadfence();
                         __syncwarp();
-                        if (lane == 0) atomicAdd(&sflags[0], 1);
+                        int* arr = xs.arrived + q_tile * 4 + ew;
+                        if (lane == 0) atomicAdd(arr, 1);
                         const long long t0 = clock64();
-                        while (*reinterpret_cast<volatile int*>(&sflags[1]) == 0 && clock64() - t0 < 200000) __nanosleep(100);
+                        while (*reinterpret_cast<volatile int*>(arr) < n_groups && clock64() - t0 < 4000000) __nanosleep(64);
+                        __threadfence();
+                        const float cur = *reinterpret_cast<volatile float*>(&sbound[ql]);
+                        const unsigned real = __ballot_sync(0xffffffffu, cur != INFINITY);      // bit j: lane j's query is not padding
+                        const float* cm_tile = xs.cmax + (size_t)(q_tile * QT) * (n_groups * ms);
+                        float mine = cur;
+                        for (int bq = 0; bq < 4; ++bq) {
+                            if (((real >> (8 * bq)) & 0xffu) == 0) continue;
+                            float kth[8];
+                            kth_largest_batch8(cm_tile, n_groups * ms, k, lane, (8 * bq) * 4 + ew, 4, kth);
+#pragma unroll
+                            for (int u = 0; u < 8; ++u) mine = (lane == 8 * bq + u) ? fmaxf(mine, kth[u]) : mine;
+                        }
+                        if (cur != INFINITY) *reinterpret_cast<volatile float*>(&sbound[ql]) = mine;
+                        __syncwarp();
+                        if (lane == 0) atomicAdd(&sflags[0], 1);
                     }
                     continue;
                 }
                 const float g = *reinterpret_cast<volatile float*>(&sbound[ql]);
                 const float g_keep = (g == VQ_NEG_INF) ? g : nextafterf(g, VQ_NEG_INF);
-                float thr = fmaxf(ls[0], g_keep);
+                float thr = LIST ? fmaxf(ls[0], g_keep) : g_keep;
                 float thr_c = thr - eps2;
                 mbar_wait(&tmem_full[acc], acc_phase);
                 tc_fence_after();
@@ -670,10 +699,10 @@ scan_mma_bf16_kernel(const __grid_constant__ CUtensorMap tmS,
                 for (int c = 0; c < n_chunks; c += 2) {
                     tmem_ld_wait(va);
                     tmem_ld32_issue(lane_base + (uint32_t)(acc * NT + (c + 1) * 32), vb);
-                    tmax = fmaxf(tmax, filter_collect<KL>(va, row0 + c * 32, valid - c * 32, g_keep, eps2, thr, thr_c, ls, lr, stage_s, stage_r, staged, flush));
+                    tmax = fmaxf(tmax, filter_collect<KL, LIST>(va, row0 + c * 32, valid - c * 32, g_keep, eps2, thr, thr_c, ls, lr, stage_s, stage_r, staged, flush));
                     tmem_ld_wait(vb);
                     if (c + 2 < n_chunks) tmem_ld32_issue(lane_base + (uint32_t)(acc * NT + (c + 2) * 32), va);
-                    tmax = fmaxf(tmax, filter_collect<KL>(vb, row0 + (c + 1) * 32, valid - (c + 1) * 32, g_keep, eps2, thr, thr_c, ls, lr, stage_s, stage_r, staged, flush));
+                    tmax = fmaxf(tmax, filter_collect<KL, LIST>(vb, row0 + (c + 1) * 32, valid - (c + 1) * 32, g_keep, eps2, thr, thr_c, ls, lr, stage_s, stage_r, staged, flush));
                 }
                 tc_fence_before();
                 __syncwarp();
@@ -795,7 +824,8 @@ prep_queries_bf16_kernel(const float* __restrict__ src, int b, int dim, int src_
                          const float* __restrict__ bounds,     // exact mode: {max |x^|, max |x^ - x|} over the store's rows
                          float* __restrict__ qeps,             // exact mode: per-query bound on |bf16 score - fp32 score|
                          float* __restrict__ cmax, int cmax_v, // exact mode: published maxima [b_pad][cmax_v], reset to -inf
-                         int* __restrict__ arrived, int n_qt) {
+                         int* __restrict__ arrived, int n_qt,
+                         float eps_const) {                    // bounds == NULL: qeps[q] = eps_const (caller-supplied bound)
     const int lane = threadIdx.x & 31;
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     vq_pdl_wait();                     // the previous search's kernels still read gtau / cand_cnt / dst
@@ -803,7 +833,7 @@ prep_queries_bf16_kernel(const float* __restrict__ src, int b, int dim, int src_
     if (row >= b_pad) return;
     if (cmax) {
         for (int c = lane; c < cmax_v; c += 32) cmax[(size_t)row * cmax_v + c] = VQ_NEG_INF;
-        if (lane == 0 && row < n_qt) arrived[row] = 0;
+        if (lane == 0 && row < 4 * n_qt) arrived[row] = 0;
     }
     __nv_bfloat16* o = dst + (size_t)row * ld;
     // padding queries (zero rows of the last query tile) must neither keep nor gather anything: bound +inf
@@ -840,8 +870,12 @@ prep_queries_bf16_kernel(const float* __restrict__ src, int b, int dim, int src_
         e2 = vq_warp_sum(e2);
         n2 = vq_warp_sum(n2);
         if (lane == 0) {
-            const float qn = sqrtf(n2), b0 = bounds[0], b1 = bounds[1];
-            qeps[row] = 1.001f * (sqrtf(e2) * b0 + qn * b1 + 3.f * (float)ld * 5.9604645e-8f * qn * b0);
+            if (bounds) {
+                const float qn = sqrtf(n2), b0 = bounds[0], b1 = bounds[1];
+                qeps[row] = 1.001f * (sqrtf(e2) * b0 + qn * b1 + 3.f * (float)ld * 5.9604645e-8f * qn * b0);
+            } else {
+                qeps[row] = eps_const;
+            }
         }
     }
 }
@@ -1005,7 +1039,7 @@ MmaWs carve(const MmaPlan& p, void* ws_v) {
     unsigned char* ws = (unsigned char*)ws_v;
     MmaWs w;
     w.qeps = nullptr;
-    w.xs = XShared{nullptr, nullptr, 1, 0};
+    w.xs = XShared{nullptr, nullptr, 1, 0, 0};
     w.gtau = (float*)(ws + p.off_tau);
     w.cnt = (int*)(ws + p.off_cnt);
     w.cand_s = (float*)(ws + p.off_cand_s);
@@ -1013,7 +1047,7 @@ MmaWs carve(const MmaPlan& p, void* ws_v) {
     w.boot_max = (float*)(ws + p.off_boot);
     w.qbf = (__nv_bfloat16*)(ws + p.off_qbf);
     w.qeps = nullptr;
-    w.xs = XShared{nullptr, nullptr, 1, 0};
+    w.xs = XShared{nullptr, nullptr, 1, 0, 0};
     return w;
 }
 
@@ -1073,11 +1107,13 @@ int run_scan(const MmaPlan& p, const void* store, int64_t n, int ld, const __nv_
         if (p.nt == 128)
             e = k <= 16 ? launch_mma<16, 128, kModeExact>(p, tmM, qbf, w, (int)n, ld, k, dbg, stream)
               : k <= 32 ? launch_mma<32, 128, kModeExact>(p, tmM, qbf, w, (int)n, ld, k, dbg, stream)
-                        : launch_mma<64, 128, kModeExact>(p, tmM, qbf, w, (int)n, ld, k, dbg, stream);
+              : k <= 64 ? launch_mma<64, 128, kModeExact>(p, tmM, qbf, w, (int)n, ld, k, dbg, stream)
+                        : launch_mma<1, 128, kModeExact>(p, tmM, qbf, w, (int)n, ld, k, dbg, stream);
         else
             e = k <= 16 ? launch_mma<16, 64, kModeExact>(p, tmM, qbf, w, (int)n, ld, k, dbg, stream)
               : k <= 32 ? launch_mma<32, 64, kModeExact>(p, tmM, qbf, w, (int)n, ld, k, dbg, stream)
-                        : launch_mma<64, 64, kModeExact>(p, tmM, qbf, w, (int)n, ld, k, dbg, stream);
+              : k <= 64 ? launch_mma<64, 64, kModeExact>(p, tmM, qbf, w, (int)n, ld, k, dbg, stream)
+                        : launch_mma<1, 64, kModeExact>(p, tmM, qbf, w, (int)n, ld, k, dbg, stream);
     } else if (p.nt == 128)
         e = k <= 16 ? launch_mma<16, 128, kModeList>(p, tmM, qbf, w, (int)n, ld, k, dbg, stream)
           : k <= 32 ? launch_mma<32, 128, kModeList>(p, tmM, qbf, w, (int)n, ld, k, dbg, stream)
@@ -1167,7 +1203,7 @@ int vq_scan_mma_run(const void* store, int64_t n, int dim, int ld, int store_dty
     }
     const MmaWs w = carve(p, ws_v);
     if (vq_launch(0, prep_queries_bf16_kernel, dim3((p.b_pad + 7) / 8), dim3(256), 0, stream, queries, b, dim, dim, w.qbf, ld,
-                  p.b_pad, query_norm, w.gtau, w.cnt, (const float*)nullptr, (const float*)nullptr, (float*)nullptr, (float*)nullptr, 0, (int*)nullptr, 0) != cudaSuccess) {
+                  p.b_pad, query_norm, w.gtau, w.cnt, (const float*)nullptr, (const float*)nullptr, (float*)nullptr, (float*)nullptr, 0, (int*)nullptr, 0, 0.f) != cudaSuccess) {
         vq_set_error("launch of prep_queries_bf16_kernel failed: %s", cudaGetErrorString(cudaGetLastError()));
         return VQ_ECUDA;
     }
@@ -1189,15 +1225,21 @@ int vq_scan_mma_run(const void* store, int64_t n, int dim, int ld, int store_dty
 size_t vq_scan_mma_collect_workspace(int64_t n, int ld, int b, int cap) {
     const MmaPlan p = plan(n, ld, b, 1);
     return p.off_cand_s + 2 * align256((size_t)p.b_pad * cap * 4) + align256((size_t)p.b_pad * ld * 2) +
-           align256((size_t)kMaxBootTiles * p.b_pad * 4) + 256;
+           align256((size_t)kMaxBootTiles * p.b_pad * 4) + align256((size_t)p.b_pad * 4) + 256;
 }
 // thresholds == NULL: the threshold of every query is derived from the store itself — a boot pass scores
 // min(256, tiles) sample tiles and the k-th largest tile maximum (reached by k distinct rows) is used, so at
 // least k rows are gathered.  The exact top-k of THOSE rows is then a set of k real rows: its k-th exact
 // score is a valid lower bound of the k-th best of any store that contains them (large-k search, step 1).
+int vq_exact_finish_launch(const float* cand_s, const int* cand_r, const int* cand_cnt, int cap, int b, int k_sel,
+                           const float* qeps, const float* store_f32, int ld, int dim, const float* queries, int query_norm,
+                           int k_out, float* out_scores, int* out_rows, int* out_overflow, int* out_stats, cudaStream_t stream);
+// bounds != NULL (the store's {max |x^|, max |x^ - x|}, as for the exact mode): the final stage re-scores only the best
+// candidates by bf16 score and those within the per-query rounding bound of the k-th (exact_finish) instead of
+// everything gathered.
 int vq_scan_mma_collect(const void* store_bf16, const float* store_f32, int64_t n, int dim, int ld, const float* queries,
-                        int query_norm, int b, const float* thresholds, int cap, int k, float* out_scores, int32_t* out_rows,
-                        int32_t* out_overflow, void* ws_v, size_t ws_bytes, cudaStream_t stream, int* launches) {
+                        int query_norm, int b, const float* thresholds, int cap, const float* bounds, int k, float* out_scores,
+                        int32_t* out_rows, int32_t* out_overflow, void* ws_v, size_t ws_bytes, cudaStream_t stream, int* launches) {
     if (!vq_scan_mma_supported(n, dim, ld, VQ_BF16, b, 1) || cap < k) {
         vq_set_error("scan_mma_collect: unsupported shape n=%lld dim=%d ld=%d b=%d cap=%d k=%d", (long long)n, dim, ld, b, cap, k);
         return VQ_EUNSUPPORTED;
@@ -1210,7 +1252,7 @@ int vq_scan_mma_collect(const void* store_bf16, const float* store_f32, int64_t 
     unsigned char* ws = (unsigned char*)ws_v;
     MmaWs w;
     w.qeps = nullptr;
-    w.xs = XShared{nullptr, nullptr, 1, 0};
+    w.xs = XShared{nullptr, nullptr, 1, 0, 0};
     w.gtau = (float*)(ws + p.off_tau);
     w.cnt = (int*)(ws + p.off_cnt);
     const size_t cand_bytes = align256((size_t)p.b_pad * cap * 4);
@@ -1218,9 +1260,10 @@ int vq_scan_mma_collect(const void* store_bf16, const float* store_f32, int64_t 
     w.cand_r = (int*)(ws + p.off_cand_s + cand_bytes);
     w.qbf = (__nv_bfloat16*)(ws + p.off_cand_s + 2 * cand_bytes);
     w.boot_max = (float*)(ws + p.off_cand_s + 2 * cand_bytes + align256((size_t)p.b_pad * ld * 2));
+    float* qeps = (float*)(ws + p.off_cand_s + 2 * cand_bytes + align256((size_t)p.b_pad * ld * 2) + align256((size_t)kMaxBootTiles * p.b_pad * 4));
     p.cap = cap;
     if (vq_launch(0, prep_queries_bf16_kernel, dim3((p.b_pad + 7) / 8), dim3(256), 0, stream, queries, b, dim, dim, w.qbf, ld,
-                  p.b_pad, query_norm, w.gtau, w.cnt, thresholds, (const float*)nullptr, (float*)nullptr, (float*)nullptr, 0, (int*)nullptr, 0) != cudaSuccess) {
+                  p.b_pad, query_norm, w.gtau, w.cnt, thresholds, bounds, bounds ? qeps : (float*)nullptr, (float*)nullptr, 0, (int*)nullptr, 0, 0.f) != cudaSuccess) {
         vq_set_error("launch of prep_queries_bf16_kernel failed");
         return VQ_ECUDA;
     }
@@ -1259,8 +1302,14 @@ int vq_scan_mma_collect(const void* store_bf16, const float* store_f32, int64_t 
         vq_set_error("launch of scan_mma_bf16_kernel<collect> failed: %s", cudaGetErrorString(e));
         return VQ_ECUDA;
     }
-    const int rc = vq_scan_finish_launch(2, w.cand_s, w.cand_r, w.cnt, cap, b, k, store_f32, ld, dim, queries, query_norm, 0.f, k,
-                                         out_scores, out_rows, out_overflow, stream);
+    int rc;
+    const int k_sel = k <= 16 ? 32 : (k + (k / 2 > 22 ? k / 2 : 22));
+    if (bounds != nullptr && k_sel <= 512 && cap >= k_sel)
+        rc = vq_exact_finish_launch(w.cand_s, w.cand_r, w.cnt, cap, b, k_sel, qeps, store_f32, ld, dim, queries, query_norm, k,
+                                    out_scores, out_rows, out_overflow, nullptr, stream);
+    else
+        rc = vq_scan_finish_launch(2, w.cand_s, w.cand_r, w.cnt, cap, b, k, store_f32, ld, dim, queries, query_norm, 0.f, k,
+                                   out_scores, out_rows, out_overflow, stream);
     if (rc) return rc;
     return VQ_OK;
 }
@@ -1274,7 +1323,7 @@ int vq_exact_finish_launch(const float* cand_s, const int* cand_r, const int* ca
 namespace {
 // Exact-mode plan: the scan plan for lists of k entries with a candidate buffer of `cap` slots per query
 // (appends of the whole scan, not just list survivors) and the per-query eps array.
-struct ExactPlan { MmaPlan p; int k_sel, ms, boot_T; size_t off_eps, off_cmax, off_arrived; };
+struct ExactPlan { MmaPlan p; int k_sel, ms, boot_T, refresh_ns; size_t off_eps, off_cmax, off_arrived; };
 ExactPlan plan_exact(int64_t n, int ld, int b, int k) {
     ExactPlan x;
     MmaPlan& p = x.p;
@@ -1288,52 +1337,99 @@ ExactPlan plan_exact(int64_t n, int ld, int b, int k) {
     if (cap_env > 0) cap = cap_env;
     const long long n8 = (n + 7) / 8 * 8;
     if (cap > n8) cap = (int)n8;                  // a row is gathered at most once per query: cannot overflow
-    // The bootstrap runs inside the scan (the first boot_T tiles of every CTA only publish their maxima and are
-    // scanned again at the end), so the launch has no boot pass of its own.
-    p.boot_tiles = p.boot_groups = 0;
-    p.boot_mul = 1;
-    // every CTA needs a few tiles for that: short stores run fewer groups (8 tiles each)
-    if ((long long)p.groups * 8 > n_tiles) {
-        p.groups = (int)(n_tiles / 8 > 0 ? n_tiles / 8 : 1);
-        p.grid = p.groups * p.n_qt;
-    }
-    // sub-streams per CTA: about 3k published maxima per query, so that their k-th largest is a strong bound
-    static const int ms_env = getenv("VQ_EXACT_SUB") ? atoi(getenv("VQ_EXACT_SUB")) : 0;
-    int ms = ms_env > 0 ? ms_env : (3 * k + p.groups - 1) / p.groups;
-    x.ms = ms < 1 ? 1 : (ms > kMaxSub ? kMaxSub : ms);
-    // bootstrap sample: max(#SMs, 4k) tiles per query tile (capped), at most a quarter of a CTA's tiles
     static const int boot_env = getenv("VQ_EXACT_BOOT") ? atoi(getenv("VQ_EXACT_BOOT")) : -1;
-    int bt = sms > 4 * k ? sms : 4 * k;
-    if (bt > kMaxBootTiles) bt = kMaxBootTiles;
-    int T = (bt + p.groups - 1) / p.groups;
-    if (T < x.ms) T = x.ms;                       // every sub-stream sees a bootstrap tile
-    if (T > 16) T = 16;
-    const long long per_cta = n_tiles / p.groups;
-    if (T > per_cta / 4) T = (int)(per_cta / 4);
-    if ((long long)p.groups * x.ms < k || cap >= n8) T = 0;       // no usable bound / nothing to protect
-    x.boot_T = boot_env >= 0 ? boot_env : T;
-    if (x.boot_T == 0 && cap < n8 && (long long)p.groups * k > cap / 2) {     // no bound at all: groups * k unconditional appends
-        p.groups = cap / (2 * k) > 0 ? cap / (2 * k) : 1;
+    static const int ms_env = getenv("VQ_EXACT_SUB") ? atoi(getenv("VQ_EXACT_SUB")) : 0;
+    int bt = sms > 4 * k ? sms : 4 * k;           // bootstrap sample: max(#SMs, 4k) tiles per query tile
+    if (bt > kMaxPublished) bt = kMaxPublished;
+    // Where the threshold bootstrap runs:
+    //  * one query tile (batch <= 128, HBM-bound): as a separate sample pass + boot_select in front of the scan, like
+    //    the list mode.  Inside the kernel the CTAs would stall on each other right after their first tile, and an
+    //    HBM-bound scan pays for every microsecond its loads are not in flight (measured with three steps in flight:
+    //    0.167 -> 0.182 ms at batch 1); the two small launches hide behind the neighbouring steps instead.
+    //  * several query tiles (tensor-bound): INSIDE the scan — the first boot_T tiles of every CTA only publish their
+    //    maxima and are scanned again at the end; no extra launches (which cannot overlap a neighbouring scan: they
+    //    need its shared memory) and no second prologue.
+    const bool inside = boot_env >= 0 ? boot_env > 0 : p.n_qt >= 2;
+    // with the bootstrap inside, short stores run fewer groups so that every CTA has 16 tiles to take its share from
+    if (inside && (long long)p.groups * 16 > n_tiles) {
+        p.groups = (int)(n_tiles / 16 > 0 ? n_tiles / 16 : 1);
         p.grid = p.groups * p.n_qt;
     }
+    const long long per_cta = n_tiles / p.groups;
+    int T = 0;
+    if (inside) {
+        p.boot_tiles = p.boot_groups = 0;
+        p.boot_mul = 1;
+        T = boot_env > 0 ? boot_env : (bt + p.groups - 1) / p.groups;
+        const long long t_max = per_cta / 16 > 1 ? per_cta / 16 : (per_cta >= 4 ? 1 : 0);
+        if (T > t_max) T = (int)t_max;
+    } else {
+        const long long full_tiles = n / p.nt;
+        int bs = bt < kMaxBootTiles ? bt : kMaxBootTiles;
+        if (bs > full_tiles / 2) bs = (int)(full_tiles / 2);
+        if (bs >= k && cap < n8 && boot_env != 0) {
+            p.boot_tiles = bs;
+            p.boot_groups = bs < p.groups ? bs : p.groups;
+            p.boot_mul = (int)(full_tiles / bs);
+            if (p.boot_mul < 1) p.boot_mul = 1;
+        } else {
+            p.boot_tiles = p.boot_groups = 0;
+            p.boot_mul = 1;
+        }
+    }
+    // sub-streams per CTA: as many published maxima per query as the bootstrap sample holds tiles, so that their
+    // k-th largest is as strong a bound as the k-th largest tile maximum of that sample; with the bootstrap inside
+    // the kernel every sub-stream must see one of the boot_T tiles
+    {
+        int ms = ms_env > 0 ? ms_env : (bt + p.groups - 1) / p.groups;
+        if (ms > kMaxPublished / p.groups) ms = kMaxPublished / p.groups;
+        if (inside && T > 0 && ms > T) ms = T;
+        x.ms = ms < 1 ? 1 : (ms > kMaxSub ? kMaxSub : ms);
+    }
+    if (inside && ((long long)p.groups * x.ms < k || cap >= n8)) T = 0;       // no usable bound / nothing to protect
+    x.boot_T = T;
+    if (x.boot_T == 0 && p.boot_tiles == 0 && cap < n8 && (long long)p.groups * k > cap / 2) {
+        p.groups = cap / (2 * k) > 0 ? cap / (2 * k) : 1;     // no bound at all: groups * k unconditional appends
+        p.grid = p.groups * p.n_qt;
+    }
+    // Periodic refresh of the cooperative bound (warp 3): it shares an issue port with an epilogue warp, so it only
+    // runs where the scan is long enough for a tighter bound to pay (>= 128 tiles per CTA), sleeping 16 us between
+    // rounds and backing off to 256 us while nothing changes.  VQ_EXACT_REFRESH_NS overrides (0 = off).
+    static const int refresh_env = getenv("VQ_EXACT_REFRESH_NS") ? atoi(getenv("VQ_EXACT_REFRESH_NS")) : -1;
+    x.refresh_ns = refresh_env >= 0 ? refresh_env : (n_tiles / p.groups >= 128 ? 16000 : 0);
     p.cap = cap;
     x.k_sel = k <= 16 ? 32 : (k + (k / 2 > 22 ? k / 2 : 22));
     const size_t cand_bytes = align256((size_t)p.b_pad * cap * 4);
     size_t o = p.off_cand_s;
     p.off_cand_r = o + cand_bytes;
     o += 2 * cand_bytes;
-    p.off_boot = o;    o += 256;                                       // (unused in exact mode)
+    p.off_boot = o;    o += align256((size_t)kMaxBootTiles * p.b_pad * 4);     // tile maxima of the separate sample pass (one query tile)
     p.off_qbf = o;     o += align256((size_t)p.b_pad * ld * 2);
     x.off_eps = o;     o += align256((size_t)p.b_pad * 4);
     x.off_cmax = o;    o += align256((size_t)p.b_pad * sms * kMaxSub * 4 / (p.n_qt > 0 ? p.n_qt : 1) + 1024);
-    x.off_arrived = o; o += align256((size_t)p.n_qt * 4);
+    x.off_arrived = o; o += align256((size_t)p.n_qt * 4 * 4);
     p.total = o;
     return x;
 }
 }  // namespace
 
+constexpr int kMaxExactK = 128;          // 64 < k <= 128: listless exact mode (needs a bootstrap bound)
+// k beyond the register lists is served only where a bound exists before the first row is gathered
+bool vq_scan_mma_exact_supported(int64_t n, int ld, int b, int k) {
+    if (b < 1 || k < 1 || k > kMaxExactK || n < 1 || ld > 768 || ld % KB_ELEMS != 0) return false;
+    if ((b + QT - 1) / QT > vq_num_sms()) return false;
+    if (k <= kMaxK) return true;
+    // Listless mode (64 < k <= 128): the bound is only the k-th largest of <= 160 published maxima, which at bootstrap
+    // time cover a small sample — measured on 1.25M x 768, k = 100: tens of thousands of rows pass before the bound
+    // tightens and every gather overflows.  Served only where that cannot happen (the buffer holds a tenth of the
+    // store) unless VQ_EXACT_LISTLESS=1; larger stores go through the two-pass route (vq_search_collect).
+    static const bool listless_env = getenv("VQ_EXACT_LISTLESS") ? atoi(getenv("VQ_EXACT_LISTLESS")) != 0 : false;
+    const ExactPlan x = plan_exact(n, ld, b, k);
+    if (!(x.boot_T > 0 || x.p.boot_tiles > 0 || x.p.cap >= n)) return false;
+    return listless_env || (long long)x.p.cap * 10 >= n;
+}
 size_t vq_scan_mma_exact_workspace(int64_t n, int ld, int b, int k) {
-    if (b < 1 || k < 1 || k > kMaxK || n < 1 || ld > 768 || ld % KB_ELEMS != 0) return 0;
+    if (!vq_scan_mma_exact_supported(n, ld, b, k)) return 0;
     return plan_exact(n, ld, b, k).p.total + 256;
 }
 
@@ -1343,7 +1439,7 @@ size_t vq_scan_mma_exact_workspace(int64_t n, int ld, int b, int k) {
 int vq_scan_mma_exact(const void* store_bf16, const float* store_f32, int64_t n, int dim, int ld, const float* queries,
                       int query_norm, int b, int k, const float* bounds, float* out_scores, int32_t* out_rows,
                       int32_t* out_overflow, int32_t* out_stats, void* ws_v, size_t ws_bytes, cudaStream_t stream, int* launches) {
-    if (!vq_scan_mma_supported(n, dim, ld, VQ_BF16, b, k)) {
+    if (!vq_scan_mma_exact_supported(n, ld, b, k)) {
         vq_set_error("exact search: unsupported shape n=%lld dim=%d ld=%d b=%d k=%d", (long long)n, dim, ld, b, k);
         return VQ_EUNSUPPORTED;
     }
@@ -1355,9 +1451,9 @@ int vq_scan_mma_exact(const void* store_bf16, const float* store_f32, int64_t n,
     }
     MmaWs w = carve(p, ws_v);
     w.qeps = (float*)((unsigned char*)ws_v + x.off_eps);
-    w.xs = XShared{(float*)((unsigned char*)ws_v + x.off_cmax), (int*)((unsigned char*)ws_v + x.off_arrived), x.ms, x.boot_T};
+    w.xs = XShared{(float*)((unsigned char*)ws_v + x.off_cmax), (int*)((unsigned char*)ws_v + x.off_arrived), x.ms, x.boot_T, x.refresh_ns};
     if (vq_launch(0, prep_queries_bf16_kernel, dim3((p.b_pad + 7) / 8), dim3(256), 0, stream, queries, b, dim, dim, w.qbf, ld,
-                  p.b_pad, query_norm, w.gtau, w.cnt, (const float*)nullptr, bounds, w.qeps, w.xs.cmax, p.groups * w.xs.ms, w.xs.arrived, p.n_qt) != cudaSuccess) {
+                  p.b_pad, query_norm, w.gtau, w.cnt, (const float*)nullptr, bounds, w.qeps, w.xs.cmax, p.groups * w.xs.ms, w.xs.arrived, p.n_qt, 0.f) != cudaSuccess) {
         vq_set_error("launch of prep_queries_bf16_kernel failed: %s", cudaGetErrorString(cudaGetLastError()));
         return VQ_ECUDA;
     }

@@ -308,9 +308,10 @@ class Scanner:
         return out_s, out_r, over
 
     def collect(self, bf16: torch.Tensor, f32: torch.Tensor, n: int, dim: int, queries: torch.Tensor, k: int,
-                thresholds: torch.Tensor, cap: int = 4096, norm: int = _lib.NORM_EPS):
-        """`vq_search_collect`: gather every row whose bf16 score reaches thresholds[q], re-score all of
-        them exactly, best k.  Returns (scores [b,k] f32, rows [b,k] i32, overflow [b] i32)."""
+                thresholds: torch.Tensor, cap: int = 4096, norm: int = _lib.NORM_EPS, bounds: torch.Tensor | None = None):
+        """`vq_search_collect`: gather every row whose bf16 score reaches thresholds[q], re-score them exactly
+        (all of them, or with the store's `bounds` only those that can still belong to the top-k), best k.
+        Returns (scores [b,k] f32, rows [b,k] i32, overflow [b] i32)."""
         ld = bf16.stride(0)
         b = queries.shape[0]
         with torch.cuda.device(self.device):
@@ -325,7 +326,7 @@ class Scanner:
             with self.lock:
                 ws = self.ws.get(need)
                 rc = self.lib.vq_search_collect(_ptr(bf16), _ptr(f32), n, dim, ld, _ptr(queries), b, k, norm, _ptr(thresholds),
-                                                cap, _ptr(out_s), _ptr(out_r), _ptr(over), _ptr(ws), ws.numel(),
+                                                cap, _ptr(bounds), _ptr(out_s), _ptr(out_r), _ptr(over), _ptr(ws), ws.numel(),
                                                 _stream(self.device))
                 _lib.check(rc, "vq_search_collect")
                 self.last_path = _lib.last_scan_path()

@@ -166,13 +166,13 @@ MAX_BATCH = 8192                             # queries per launch chain of the f
 
 
 def exact_search(scanner: Scanner, st: DeviceStore, q_dev: torch.Tensor, k: int):
-    """The exact fp32 top-k of the store at tensor-core speed.  k <= 64 and ld <= 768: ONE pass
+    """The exact fp32 top-k of the store at tensor-core speed.  k <= 128 and ld <= 768: ONE pass
     (`vq_search_exact`: scan of the bf16 copy that gathers everything within the operand-rounding bound of
     the running k-th best, fp32 re-score, exact by construction); larger k / wider rows: `large_k_search`.
     Returns ([b,k] f32, [b,k] i32, overflow [b] i32 device tensor).  The caller re-runs queries
     whose overflow flag is set (mass ties) with `exact_fallback` after its device->host read, so no sync
     is added here."""
-    if k > MAX_TENSOR_K or st.ld > MAX_TENSOR_LD:
+    if st.ld > MAX_TENSOR_LD or not scanner.lib.vq_search_exact_supported(st.n, st.dim, st.ld, q_dev.shape[0], k):
         return large_k_search(scanner, st, q_dev, k)
     return scanner.exact(st, q_dev, k, _lib.NORM_EPS)
 
@@ -237,7 +237,8 @@ def large_k_search(scanner: Scanner, st: DeviceStore, q_dev: torch.Tensor, k: in
     s1, _, over1 = scanner.collect(smp_bf16, smp_f32, smp_f32.shape[0], st.dim, q_dev, k, None, LARGE_K_CAP)
     thr = s1[:, k - 1] - BF16_SCORE_EPS * max_row_norm
     thr = torch.where(over1 > 0, torch.full_like(thr, float("-inf")), thr)      # incomplete sample answer: no bound
-    return scanner.collect(st.bf16, st.f32, st.n, st.dim, q_dev, k, thr, LARGE_K_CAP)
+    # second pass: only the best candidates by bf16 score and those within eps of the k-th are re-scored (exact_finish)
+    return scanner.collect(st.bf16, st.f32, st.n, st.dim, q_dev, k, thr, LARGE_K_CAP, bounds=st.bounds)
 
 
 def resolve_uncertified(scanner: Scanner, st: DeviceStore, q_dev: torch.Tensor, k: int, idx: torch.Tensor,

@@ -138,6 +138,40 @@ class B200HNSWIndex:
         for vector, node_id in zip(vectors, node_ids):
             self.add(vector, node_id)
 
+    def add_device_rows(self, rows: torch.Tensor, node_ids=None, level_seed: int = 0) -> None:
+        """Bulk ingest of [m, dimension] embeddings that are already ON THE DEVICE (the encoder's output, a shard of a
+        larger store): normalised by the ingest kernel (hnsw.py:157), appended without a host round trip.  ids default
+        to the row numbers.  Levels follow the reference's distribution int(-ln(U) * mL) (hnsw.py:68-74), drawn in one
+        vectorised call from `np.random.default_rng(level_seed)` — same law, not the stream of Python's global `random`
+        that `add` replays.  Call `build()` (or just search) afterwards."""
+        with self.lock:
+            self._upload()
+            m = int(rows.shape[0])
+            if m == 0:
+                return
+            if rows.shape[1] != self.dimension:
+                raise ValueError(f"vector dimension {rows.shape[1]} != index dimension {self.dimension}")
+            start = len(self._ids)
+            ids = range(start, start + m) if node_ids is None else list(node_ids)
+            if len(ids) != m:
+                raise ValueError("node_ids and rows differ in length")
+            u = np.random.default_rng(level_seed + start).random(m)
+            lv = (-np.log(np.maximum(u, 1e-300)) * self.level_generation_factor).astype(np.int32)
+            for nid, row in zip(ids, range(start, start + m)):
+                old = self._row_of.get(nid)
+                if old is not None:
+                    self._dead.add(old)
+                self._row_of[nid] = row
+            self._ids.extend(ids)
+            self._level_list.extend(lv.tolist())
+            self.levels.update(zip(ids, lv.tolist()))
+            self._store.append(rows, _lib.NORM_PLAIN)
+            top = int(lv.max())
+            if self.entry_point is None or top > self._level_list[self._entry_row]:
+                self._entry_row = start + int(np.argmax(lv == top))
+                self.entry_point = self._ids[self._entry_row]
+            self.element_count += m
+
     def _upload(self):
         if self._pending:
             chunk = 1 << 16
