@@ -1341,15 +1341,15 @@ ExactPlan plan_exact(int64_t n, int ld, int b, int k) {
     static const int ms_env = getenv("VQ_EXACT_SUB") ? atoi(getenv("VQ_EXACT_SUB")) : 0;
     int bt = sms > 4 * k ? sms : 4 * k;           // bootstrap sample: max(#SMs, 4k) tiles per query tile
     if (bt > kMaxPublished) bt = kMaxPublished;
-    // Where the threshold bootstrap runs:
-    //  * one query tile (batch <= 128, HBM-bound): as a separate sample pass + boot_select in front of the scan, like
-    //    the list mode.  Inside the kernel the CTAs would stall on each other right after their first tile, and an
-    //    HBM-bound scan pays for every microsecond its loads are not in flight (measured with three steps in flight:
-    //    0.167 -> 0.182 ms at batch 1); the two small launches hide behind the neighbouring steps instead.
-    //  * several query tiles (tensor-bound): INSIDE the scan — the first boot_T tiles of every CTA only publish their
-    //    maxima and are scanned again at the end; no extra launches (which cannot overlap a neighbouring scan: they
-    //    need its shared memory) and no second prologue.
-    const bool inside = boot_env >= 0 ? boot_env > 0 : p.n_qt >= 2;
+    // Where the threshold bootstrap runs: as a separate sample pass + boot_select in front of the scan (like the list
+    // mode).  The alternative — INSIDE the scan: the first boot_T tiles of every CTA only publish their maxima, the
+    // CTAs of a query tile meet at a counter, and those tiles are scanned again at the end; no extra launches — was
+    // built and measured (VQ_EXACT_INSIDE=1 selects it) and is NOT the default: with three steps in flight the two
+    // small launches hide behind the neighbouring steps, while the in-kernel barrier stalls every CTA right after
+    // its first tiles and the re-scan is paid in full (1M rows x 1024 queries: 1.039 ms separate vs 1.06-1.09 ms inside;
+    // 125k-row shard: 0.225 vs 0.254 ms; batch 1: 0.167 vs 0.182 ms).
+    static const int inside_env = getenv("VQ_EXACT_INSIDE") ? atoi(getenv("VQ_EXACT_INSIDE")) : -1;
+    const bool inside = inside_env > 0 || (inside_env < 0 && boot_env > 0);
     // with the bootstrap inside, short stores run fewer groups so that every CTA has 16 tiles to take its share from
     if (inside && (long long)p.groups * 16 > n_tiles) {
         p.groups = (int)(n_tiles / 16 > 0 ? n_tiles / 16 : 1);
