@@ -844,7 +844,7 @@ def run_ours(args):
             if m["kernel_ms"] is None:
                 return None
             # DRAM bytes per launch from the committed ncu --set full capture of this kernel / shard / batch class
-            traffic = traffic_tab.get(f"rows{n_local}_b{'le128' if m['B'] <= 128 else m['B']}")
+            traffic = traffic_tab.get(f"rows{n_local}_b{'le128' if m['B'] <= 128 else m['B']}_{m['data']}")
             bytes_ = n_local * store.ld * elem + min(m["B"], 128) * DIM * elem
             flops = 2.0 * m["B"] * n_local * DIM
             gbs = bytes_ / (m["kernel_ms"] * 1e-3) / 1e9

@@ -264,7 +264,11 @@ int vq_hnsw_search(const void* store, int64_t n, int dim, int ld, int store_dtyp
  * added and every list is pruned back to `m_out` closest (hnsw.py:197-223 semantics).
  *   members    [n_members] int32 node ids participating in this layer (NULL = all n rows)
  *   adj_out    [n_members, m_out] int32 (-1 padded), neighbours as node ids
- *   diversify  0 = closest-m (reference hnsw.py:123-148), 1 = HNSW diversity heuristic */
+ *   diversify  0 = closest-m of the exact k nearest (reference selection rule hnsw.py:123-148 on exact candidates),
+ *              1 = HNSW diversity heuristic over the exact k_cand nearest,
+ *              2 = incremental (k_cand == m_out): the reference's construction ORDER — node i links to its m_out nearest
+ *                  among the nodes before it (hnsw.py:183-199), every node keeps the closest m_out of all links it ever
+ *                  received (:202-223) — computed data-parallel (causal scan + one sort), not insert by insert */
 size_t vq_hnsw_layer_workspace_bytes(int64_t n_members, int dim, int ld, int store_dtype, int k_cand, int m_out);
 int vq_hnsw_build_layer(const void* store, int64_t n, int dim, int ld, int store_dtype,
                         const int32_t* members, int64_t n_members,

@@ -253,21 +253,38 @@ template <int KL, bool LIST, typename Flush>
 __device__ __forceinline__ float filter_collect(const uint32_t (&v)[32], int row_base, int left, float g_keep, const float& eps2,
                                                float& thr, float& thr_c, float (&ls)[KL], int (&lr)[KL],
                                                float* stage_s, int* stage_r, int& staged, Flush&& flush) {
-    float m = __uint_as_float(v[0]);
+    // maxima of the four groups of 8 scores, then of the chunk: almost no chunk holds a candidate once the bound is warm
+    float g[4];
 #pragma unroll
-    for (int j = 1; j + 1 < 32; j += 2) m = fmaxf(fmaxf(m, __uint_as_float(v[j])), __uint_as_float(v[j + 1]));
-    m = fmaxf(m, __uint_as_float(v[31]));
+    for (int q4 = 0; q4 < 4; ++q4) {
+        const int o = 8 * q4;
+        g[q4] = fmaxf(fmaxf(fmaxf(__uint_as_float(v[o]), __uint_as_float(v[o + 1])), fmaxf(__uint_as_float(v[o + 2]), __uint_as_float(v[o + 3]))),
+                      fmaxf(fmaxf(__uint_as_float(v[o + 4]), __uint_as_float(v[o + 5])), fmaxf(__uint_as_float(v[o + 6]), __uint_as_float(v[o + 7]))));
+    }
+    const float m = fmaxf(fmaxf(g[0], g[1]), fmaxf(g[2], g[3]));
     if (!(m >= thr_c)) return m;
+    // slow path (a warp takes it when ANY of its 32 queries has a candidate, i.e. in most chunks while the bound is still
+    // loose): the per-score mask is built only for the groups of 8 that hold a candidate, and a lone candidate is the
+    // chunk maximum itself — no 32-way extraction
     unsigned mask = 0;
 #pragma unroll
-    for (int j = 0; j < 32; ++j) mask |= (__uint_as_float(v[j]) >= thr_c) ? (1u << j) : 0u;
+    for (int q4 = 0; q4 < 4; ++q4) {
+        if (g[q4] >= thr_c) {
+#pragma unroll
+            for (int j = 8 * q4; j < 8 * q4 + 8; ++j) mask |= (__uint_as_float(v[j]) >= thr_c) ? (1u << j) : 0u;
+        }
+    }
     if (left < 32) mask &= left > 0 ? ((1u << left) - 1u) : 0u;
+    const bool lone = (mask & (mask - 1u)) == 0u;
     while (mask) {
         const int j = __ffs(mask) - 1;
         mask &= mask - 1;
-        float s = __uint_as_float(v[0]);
+        float s = m;
+        if (!lone) {
+            s = __uint_as_float(v[0]);
 #pragma unroll
-        for (int jj = 1; jj < 32; ++jj) s = (j == jj) ? __uint_as_float(v[jj]) : s;
+            for (int jj = 1; jj < 32; ++jj) s = (j == jj) ? __uint_as_float(v[jj]) : s;
+        }
         stage_s[staged * QT] = s;
         stage_r[staged * QT] = row_base + j;
         if (++staged == kStage) flush();
@@ -1105,7 +1122,8 @@ int run_scan(const MmaPlan& p, const void* store, int64_t n, int ld, const __nv_
     vq_prof_begin(stream);
     if (exact) {
         if (p.nt == 128)
-            e = k <= 16 ? launch_mma<16, 128, kModeExact>(p, tmM, qbf, w, (int)n, ld, k, dbg, stream)
+            e = k == 10 ? launch_mma<10, 128, kModeExact>(p, tmM, qbf, w, (int)n, ld, k, dbg, stream)      // the contract's k: no sentinel slots to bubble through
+              : k <= 16 ? launch_mma<16, 128, kModeExact>(p, tmM, qbf, w, (int)n, ld, k, dbg, stream)
               : k <= 32 ? launch_mma<32, 128, kModeExact>(p, tmM, qbf, w, (int)n, ld, k, dbg, stream)
               : k <= 64 ? launch_mma<64, 128, kModeExact>(p, tmM, qbf, w, (int)n, ld, k, dbg, stream)
                         : launch_mma<1, 128, kModeExact>(p, tmM, qbf, w, (int)n, ld, k, dbg, stream);

@@ -221,7 +221,11 @@ class B200HNSWIndex:
 
     def _build_layer(self, members, n_members: int, m_out: int, adj_out: torch.Tensor):
         st = self._store
-        if self.select == "closest":
+        if self.select == "incremental":
+            # the reference's insertion order (hnsw.py:150-229): every node links to its M nearest EARLIER nodes,
+            # every node keeps the closest M of all links it ever received
+            k_cand, div = m_out, 2
+        elif self.select == "closest":
             # closest-M only ever looks at the M nearest candidates, so the exact pool is m_out wide
             k_cand, div = m_out, 0
         else:
