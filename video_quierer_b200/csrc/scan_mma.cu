@@ -413,7 +413,6 @@ scan_mma_bf16_kernel(const __grid_constant__ CUtensorMap tmS,
     vq_pdl_wait();
     vq_pdl_trigger();
     if (MODE == kModeExact) {
-        if (threadIdx.x < QT) sbound[threadIdx.x] = gtau[q_tile * QT + threadIdx.x];    // -inf, or +inf for padding queries
         if (threadIdx.x < 4) sflags[threadIdx.x] = 0;
         __syncthreads();
     }
@@ -507,30 +506,36 @@ scan_mma_bf16_kernel(const __grid_constant__ CUtensorMap tmS,
                    t1 - dbg_t0, (double)(c1 - dbg_c0) / ((double)it * nkb * 4), (double)(c1 - dbg_c0) / (double)(t1 - dbg_t0) * 1e3);
         }
     } else if (warp == 3 && MODE == kModeExact) {
-        // Bound refresher: sbound[query] = max(itself, k-th largest of the maxima every CTA of this query tile has
-        // published so far), recomputed periodically until the epilogue is done, backing off while nothing changes.
-        // (The first bound of a query comes from its epilogue warp, right after the bootstrap tiles.)
+        // Bound refresher.  The k-th largest of the maxima all CTAs of a query tile have published is the same number
+        // whichever CTA computes it, so the work is SPLIT: CTA `group` refreshes only its share of the tile's 128 queries
+        // (~128 / n_groups of them, one batch of 8 per round) and publishes the result with an atomic max in the global
+        // bound array every epilogue thread reads (one tile ahead) anyway.  A round is a handful of L2 loads plus ~100
+        // instructions — cheap enough to run every few microseconds next to an epilogue warp, for scans of any length
+        // (a private refresher over all 128 queries per CTA cost 16 such batches per round and slowed short scans down).
         const int V = n_groups * xs.ms;
         const float* cm_tile = xs.cmax + (size_t)(q_tile * QT) * V;
+        const int q_lo = (int)(((long long)group * QT) / n_groups), q_hi = (int)(((long long)(group + 1) * QT) / n_groups);
         if (boot_T > 0) {
             const long long t0 = clock64();
             while (*reinterpret_cast<volatile int*>(&sflags[0]) < 4 && clock64() - t0 < 8000000) __nanosleep(500);
         }
         unsigned sleep_ns = (unsigned)xs.refresh_ns;
-        while (sleep_ns > 0 && *reinterpret_cast<volatile int*>(&sflags[2]) < 4) {
+        while (sleep_ns > 0 && q_hi > q_lo && *reinterpret_cast<volatile int*>(&sflags[2]) < 4) {
             __nanosleep(sleep_ns);
             bool changed = false;
-            for (int q0 = 0; q0 < QT; q0 += 8) {
+            for (int q0 = q_lo; q0 < q_hi; q0 += 8) {
+                const int ql = q0 + lane < q_hi ? q0 + lane : q_hi - 1;              // lanes 0..7: the batch's queries (clamped)
                 float cur = VQ_NEG_INF;
-                if (lane < 8) cur = *reinterpret_cast<volatile float*>(&sbound[q0 + lane]);
-                if (__all_sync(0xffffffffu, lane >= 8 || cur == INFINITY)) continue;           // 8 padding queries
+                if (lane < 8) cur = *reinterpret_cast<volatile float*>(gtau + q_tile * QT + ql);
+                if (__all_sync(0xffffffffu, lane >= 8 || cur == INFINITY)) continue;   // padding queries
                 float kth[8];
-                kth_largest_batch8(cm_tile, V, k, lane, q0, 1, kth);
+                kth_largest_batch8(cm_tile, V, k, lane, q0 + 7 < QT ? q0 : QT - 8, 1, kth);
+                const int shift = q0 + 7 < QT ? 0 : q0 - (QT - 8);                    // batch start was pulled back at the tile's end
                 float mine = VQ_NEG_INF;
 #pragma unroll
-                for (int u = 0; u < 8; ++u) mine = (lane == u) ? kth[u] : mine;
-                const bool up = lane < 8 && mine > cur;
-                if (up) *reinterpret_cast<volatile float*>(&sbound[q0 + lane]) = mine;
+                for (int u = 0; u < 8; ++u) mine = (lane + shift == u) ? kth[u] : mine;
+                const bool up = lane < 8 && q0 + lane < q_hi && mine > cur;
+                if (up) atomic_max_float(gtau + q_tile * QT + ql, mine);
                 changed = changed || __any_sync(0xffffffffu, up);
             }
             sleep_ns = changed ? (unsigned)xs.refresh_ns : (sleep_ns < 16u * (unsigned)xs.refresh_ns ? sleep_ns * 2 : sleep_ns);
@@ -652,6 +657,7 @@ scan_mma_bf16_kernel(const __grid_constant__ CUtensorMap tmS,
                 for (int j = 0; j < kMaxSub; ++j)
                     if (j == sub && m > smax[j]) { smax[j] = m; *reinterpret_cast<volatile float*>(my_cmax + j) = m; }
             };
+            float g_next = *reinterpret_cast<volatile float*>(gtau + q);      // static / bootstrap bound, then the refreshed one
             for (int it = 0; it < n_iter; ++it) {
                 const int acc = it & 1;
                 const uint32_t acc_phase = (it >> 1) & 1;
@@ -686,7 +692,7 @@ scan_mma_bf16_kernel(const __grid_constant__ CUtensorMap tmS,
                         const long long t0 = clock64();
                         while (*reinterpret_cast<volatile int*>(arr) < n_groups && clock64() - t0 < 4000000) __nanosleep(64);
                         __threadfence();
-                        const float cur = *reinterpret_cast<volatile float*>(&sbound[ql]);
+                        const float cur = *reinterpret_cast<volatile float*>(gtau + q);
                         const unsigned real = __ballot_sync(0xffffffffu, cur != INFINITY);      // bit j: lane j's query is not padding
                         const float* cm_tile = xs.cmax + (size_t)(q_tile * QT) * (n_groups * ms);
                         float mine = cur;
@@ -697,13 +703,15 @@ scan_mma_bf16_kernel(const __grid_constant__ CUtensorMap tmS,
 #pragma unroll
                             for (int u = 0; u < 8; ++u) mine = (lane == 8 * bq + u) ? fmaxf(mine, kth[u]) : mine;
                         }
-                        if (cur != INFINITY) *reinterpret_cast<volatile float*>(&sbound[ql]) = mine;
+                        if (cur != INFINITY && mine > cur) atomic_max_float(gtau + q, mine);
+                        g_next = fmaxf(g_next, mine);
                         __syncwarp();
                         if (lane == 0) atomicAdd(&sflags[0], 1);
                     }
                     continue;
                 }
-                const float g = *reinterpret_cast<volatile float*>(&sbound[ql]);
+                const float g = g_next;                                        // loaded one tile ago: no L2 round trip here
+                g_next = *reinterpret_cast<volatile float*>(gtau + q);
                 const float g_keep = (g == VQ_NEG_INF) ? g : nextafterf(g, VQ_NEG_INF);
                 float thr = LIST ? fmaxf(ls[0], g_keep) : g_keep;
                 float thr_c = thr - eps2;
@@ -1314,8 +1322,10 @@ int vq_scan_mma_collect(const void* store_bf16, const float* store_f32, int64_t 
         }
         *launches = 5;
     }
+    vq_prof_begin(stream);
     e = p.nt == 128 ? launch_mma<1, 128, kModeCollect>(p, tmS, w.qbf, w, (int)n, ld, 1, dbg, stream)
                     : launch_mma<1, 64, kModeCollect>(p, tmS, w.qbf, w, (int)n, ld, 1, dbg, stream);
+    vq_prof_end(stream);
     if (e != cudaSuccess) {
         vq_set_error("launch of scan_mma_bf16_kernel<collect> failed: %s", cudaGetErrorString(e));
         return VQ_ECUDA;
@@ -1410,11 +1420,10 @@ ExactPlan plan_exact(int64_t n, int ld, int b, int k) {
         p.groups = cap / (2 * k) > 0 ? cap / (2 * k) : 1;     // no bound at all: groups * k unconditional appends
         p.grid = p.groups * p.n_qt;
     }
-    // Periodic refresh of the cooperative bound (warp 3): it shares an issue port with an epilogue warp, so it only
-    // runs where the scan is long enough for a tighter bound to pay (>= 128 tiles per CTA), sleeping 16 us between
-    // rounds and backing off to 256 us while nothing changes.  VQ_EXACT_REFRESH_NS overrides (0 = off).
+    // Periodic refresh of the cooperative bound (warp 3 of every CTA, each for its share of the tile's queries): first
+    // sleep 4 us, backing off to 64 us while nothing changes.  VQ_EXACT_REFRESH_NS overrides (0 = off).
     static const int refresh_env = getenv("VQ_EXACT_REFRESH_NS") ? atoi(getenv("VQ_EXACT_REFRESH_NS")) : -1;
-    x.refresh_ns = refresh_env >= 0 ? refresh_env : (n_tiles / p.groups >= 128 ? 16000 : 0);
+    x.refresh_ns = refresh_env >= 0 ? refresh_env : 4000;
     p.cap = cap;
     x.k_sel = k <= 16 ? 32 : (k + (k / 2 > 22 ? k / 2 : 22));
     const size_t cand_bytes = align256((size_t)p.b_pad * cap * 4);
