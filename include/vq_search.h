@@ -268,7 +268,10 @@ int vq_hnsw_search(const void* store, int64_t n, int dim, int ld, int store_dtyp
  *              1 = HNSW diversity heuristic over the exact k_cand nearest,
  *              2 = incremental (k_cand == m_out): the reference's construction ORDER — node i links to its m_out nearest
  *                  among the nodes before it (hnsw.py:183-199), every node keeps the closest m_out of all links it ever
- *                  received (:202-223) — computed data-parallel (causal scan + one sort), not insert by insert */
+ *                  received (:202-223) — computed data-parallel (causal scan + one sort), not insert by insert,
+ *              3 = sequential (k_cand == m_out): the reference's add() with exact candidates, batch by batch — links in both
+ *                  directions, closest-m_out prune that removes the dropped link at BOTH ends (:217-223), so lists stay
+ *                  short of m_out and the long links of early inserts survive */
 size_t vq_hnsw_layer_workspace_bytes(int64_t n_members, int dim, int ld, int store_dtype, int k_cand, int m_out);
 int vq_hnsw_build_layer(const void* store, int64_t n, int dim, int ld, int store_dtype,
                         const int32_t* members, int64_t n_members,

@@ -47,7 +47,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--n", type=int, default=100_000)
     ap.add_argument("--kinds", default="clip,gauss")
-    ap.add_argument("--select", default="diverse")
+    ap.add_argument("--select", default="hybrid")
     ap.add_argument("--max-candidates", type=int, default=63)
     a = ap.parse_args()
     ref = json.load(open(REF)) if os.path.exists(REF) else {}

@@ -1423,7 +1423,9 @@ ExactPlan plan_exact(int64_t n, int ld, int b, int k) {
     // Periodic refresh of the cooperative bound (warp 3 of every CTA, each for its share of the tile's queries): first
     // sleep 4 us, backing off to 64 us while nothing changes.  VQ_EXACT_REFRESH_NS overrides (0 = off).
     static const int refresh_env = getenv("VQ_EXACT_REFRESH_NS") ? atoi(getenv("VQ_EXACT_REFRESH_NS")) : -1;
-    x.refresh_ns = refresh_env >= 0 ? refresh_env : 4000;
+    // Off for a single query tile: that scan is HBM-bound with an idle epilogue, a smaller gather buys nothing there and
+    // the refresher measurably costs (batch 1 / 32 at 1M rows: kernel 0.166 -> 0.184 ms with it).
+    x.refresh_ns = refresh_env >= 0 ? refresh_env : (p.n_qt >= 2 ? 4000 : 0);
     p.cap = cap;
     x.k_sel = k <= 16 ? 32 : (k + (k / 2 > 22 ? k / 2 : 22));
     const size_t cand_bytes = align256((size_t)p.b_pad * cap * 4);
