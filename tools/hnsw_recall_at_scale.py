@@ -34,8 +34,7 @@ def measure(kind, n, dim=512, nq=1000, efs=(64, 128, 256), **kw):
     h.add_batch(list(store), list(range(n)))
     h.build()
     build_s = time.time() - t0
-    out = {"kind": kind, "n": n, "build_s": round(build_s, 2), "layer0": getattr(h, "layer0_selection", None),
-           "probe": getattr(h, "layer0_probe_recall", None), "runs": {}}
+    out = {"kind": kind, "n": n, "build_s": round(build_s, 2), "select": h.select, "runs": {}}
     for ef in efs:
         h.ef_search = ef
         _, rows = h.search_arrays(queries, 10)
@@ -48,7 +47,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--n", type=int, default=100_000)
     ap.add_argument("--kinds", default="clip,gauss")
-    ap.add_argument("--select", default="auto")
+    ap.add_argument("--select", default="hybrid")
     ap.add_argument("--max-candidates", type=int, default=63)
     a = ap.parse_args()
     ref = json.load(open(REF)) if os.path.exists(REF) else {}

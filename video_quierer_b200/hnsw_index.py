@@ -61,7 +61,7 @@ class B200HNSWIndex:
     def __init__(self, dimension: int = 512, M: int = 16, ef_construction: int = 200, ef_search: int = 50,
                  max_M: int = 16, level_generation_factor: float = 1.0 / math.log(2.0), num_threads: int = 4,
                  use_numpy_optimization: bool = True, device=None, search_dtype: str = "fp32",
-                 rebuild_fraction: float = 0.10, select: str = "auto", max_candidates: int = 63):
+                 rebuild_fraction: float = 0.10, select: str = "hybrid", max_candidates: int = 63):
         if max(int(M), int(max_M)) > MAX_DEGREE or min(int(M), int(max_M)) < 1:
             raise ValueError(f"M={M} / max_M={max_M}: the device graph holds 1..{MAX_DEGREE} neighbours per node and layer "
                              "(vq_hnsw_build_layer's m_out limit)")
@@ -76,10 +76,11 @@ class B200HNSWIndex:
         self.search_dtype = "bf16" if search_dtype in ("bf16", "bfloat16") else "fp32"
         self.rebuild_fraction = float(rebuild_fraction)
         # neighbour selection of the GPU builder:
-        #   "auto" (default)    upper layers "diverse"; layer 0 built BOTH ways ("sequential" and "diverse") and the one with
-        #                       the higher recall@10 on 2048 sampled stored rows (truth from the exact scan) is kept
-        #   "hybrid"            layer 0 = "sequential", upper layers = "diverse" — at or above the reference's recall at
-        #                       100k and 1M clustered rows, a statistical tie on 10k iid gaussian rows
+        #   "hybrid" (default)  layer 0 = "sequential", upper layers = "diverse" — above the reference's recall on clustered
+        #                       rows at 10k, 100k and 1M and on iid gaussian rows at 100k, a statistical tie on 10k iid
+        #                       gaussian rows.  (Choosing between "sequential" and "diverse" for layer 0 by
+        #                       probing with stored rows was tried and dropped: in-sample queries favour the exact-nearest
+        #                       graph, whose links ARE the probe's answers, and picked the wrong one at 1M.)
         #   "sequential"        the reference's add() with exact candidates, batch by batch (hnsw.py:183-223): links in both
         #                       directions, closest-M prune that removes the dropped link at both ends
         #   "diverse"           the HNSW diversity heuristic `_select_neighbors_heuristic` is named after, over a candidate
@@ -205,7 +206,7 @@ class B200HNSWIndex:
             with torch.cuda.device(dev):
                 levels = torch.from_numpy(levels_np).to(dev)
                 adj0 = torch.full((n, self.max_M), -1, dtype=torch.int32, device=dev)
-                self._build_layer(None, n, self.max_M, adj0, "hybrid" if self.select == "auto" else self.select)
+                self._build_layer(None, n, self.max_M, adj0)
                 up_cnt = np.where(levels_np > 0, levels_np, 0).astype(np.int64)
                 off_np = np.cumsum(up_cnt) - up_cnt
                 slots = int(up_cnt.sum())
@@ -218,57 +219,16 @@ class B200HNSWIndex:
                         continue
                     members = torch.from_numpy(members_np).to(dev)
                     adj = torch.full((len(members_np), self.M), -1, dtype=torch.int32, device=dev)
-                    self._build_layer(members, len(members_np), self.M, adj, "hybrid" if self.select == "auto" else self.select)
+                    self._build_layer(members, len(members_np), self.M, adj)
                     dst = (upper_off[members.long()] + (lv - 1)).long()
                     upper_adj[dst] = adj
                 torch.cuda.synchronize(dev)
             self._graph = DeviceGraph(levels, adj0, upper_off, upper_adj, entry, max_level)
             self._entry_row = entry
             self.entry_point = self._ids[entry]
-            self.layer0_selection = "sequential" if self.select in ("hybrid", "auto", "sequential") else self.select
-            if self.select == "auto" and n >= 4096:
-                self._auto_pick_layer0(levels, upper_off, upper_adj, entry, max_level)
             self.build_time = time.time() - t0
 
-    def _auto_pick_layer0(self, levels, upper_off, upper_adj, entry, max_level, n_probe: int = 2048, ef: int = 64):
-        """`select="auto"`: both layer-0 constructions are built under the same (diverse) upper layers and the one that
-        finds more of the exact 10 nearest neighbours of `n_probe` sampled stored rows at ef = 64 is kept — the reference's
-        construction order wins on clustered rows (the realistic case, by 0.03-0.08 at 1M), the diversity-pruned
-        exact-nearest graph on iid gaussian rows (by 0.02 at 10k); costs one more layer-0 build and two small searches."""
-        st, n, dev = self._store, self._store.n, self.device
-        with torch.cuda.device(dev):
-            rows = torch.linspace(0, n - 1, n_probe, device=dev).long()
-            q = st.f32[rows, : self.dimension].contiguous()
-            _, truth, over = self._scanner.exact(st, q, 10, _lib.NORM_PLAIN)
-            if int(over.sum().item()):                                           # mass duplicates: the fp32 scan answers
-                _, truth = self._scanner.scan(st.f32, n, st.dim, q, 10, _lib.NORM_PLAIN, "fma")
-            truth = truth.cpu().numpy()
-            seq_graph = self._graph
-            alt = torch.full((n, self.max_M), -1, dtype=torch.int32, device=dev)
-            self._build_layer(None, n, self.max_M, alt, "diverse")
-            div_graph = DeviceGraph(levels, alt, upper_off, upper_adj, entry, max_level)
-            old_ef, scores = self.ef_search, {}
-            self.ef_search = ef
-            try:
-                for name, g in (("sequential", seq_graph), ("diverse", div_graph)):
-                    self._graph = g
-                    _, found = self._search_rows(q, 10)
-                    scores[name] = float(np.mean([len(set(found[i]) & set(truth[i])) / 10 for i in range(n_probe)]))
-            finally:
-                self.ef_search = old_ef
-            self.layer0_selection = max(scores, key=scores.get)
-            self.layer0_probe_recall = scores
-            self._graph = seq_graph if self.layer0_selection == "sequential" else div_graph
-
-    def _build_layer(self, members, n_members: int, m_out: int, adj_out: torch.Tensor, select: str | None = None):
-        st = self._store
-        sel_saved, self.select = self.select, (select or self.select)
-        try:
-            self._build_layer_as(members, n_members, m_out, adj_out)
-        finally:
-            self.select = sel_saved
-
-    def _build_layer_as(self, members, n_members: int, m_out: int, adj_out: torch.Tensor):
+    def _build_layer(self, members, n_members: int, m_out: int, adj_out: torch.Tensor):
         st = self._store
         if self.select == "sequential" or (self.select == "hybrid" and members is None):
             # the reference's add() with exact candidates, batch by batch: links in both directions, closest-M prune
