@@ -702,6 +702,31 @@ def run_ours(args):
             ln.searcher.check()                         # a peer-exchange wait that timed out voids the run
             if getattr(ln, "rowgather", None) is not None:
                 ln.rowgather.check()
+        # where a step's time goes, one step at a time (eager, CUDA events, max over ranks): the scan kernel alone, the
+        # whole local search (prep + bootstrap + scan + finish) and the same plus the shard exchange + merge
+        breakdown = None
+        if world > 1 and with_e2e:
+            def timed_eager(fn, n_it=10):
+                fn()
+                barrier()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for it_b in range(n_it):
+                    lanes[0].copy = it_b % n_copies
+                    fn()
+                e1.record()
+                barrier()
+                t = torch.tensor([e0.elapsed_time(e1) / n_it], dtype=torch.float64, device=dev)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                return float(t.item())
+            t_local = timed_eager(lambda: lanes[0].local_search(dev_q, K_TOP))
+            t_full = timed_eager(lambda: lanes[0].search(dev_q, K_TOP))
+            step_ms = dev_ms / steps
+            breakdown = {"scan_kernel_ms": kmed, "local_search_ms": t_local, "local_search_plus_exchange_ms": t_full,
+                         "pipelined_step_ms": step_ms,
+                         "bound": "scan kernel" if kmed and kmed >= 0.75 * step_ms else
+                                  ("latency-bound kernels around the scan (prep, bootstrap, finish)" if t_full - t_local < 0.5 * (t_local - (kmed or 0)) else "shard exchange + merge"),
+                         "note": "eager, one step in flight; the pipelined step overlaps everything but the scan kernels of consecutive steps"}
         # rows gathered / re-scored per query by the exact search (its out_stats), one eager call
         gathered = None
         if exact and K_TOP <= 64:
@@ -711,7 +736,7 @@ def run_ours(args):
             gathered = {"rows_gathered_per_query": float(sh[0]), "rows_rescored_per_query": float(sh[1])}
         return {"B": B, "steps": steps, "dev_ms": dev_ms, "e2e_ms": e2e_ms, "kernel_ms": kmed, "kernel_hot_ms": khot, "launches": launches, "path": path,
                 "graph": graphs is not None, "host_graph": hgraphs is not None, "ingest": ingest_mode[0], "overflow": unc, "depth": depth, "cap": cap,
-                "fallbacks": n_fallback[0], "e2e_host": e2e_host, "sustained": sustained, "parity": parity, "gathered": gathered,
+                "fallbacks": n_fallback[0], "e2e_host": e2e_host, "sustained": sustained, "parity": parity, "gathered": gathered, "breakdown": breakdown,
                 "host_q": host_q, "data": data or args.data}
 
     def measure_api(host_q, steps):
@@ -891,6 +916,8 @@ def run_ours(args):
         }
         if main["sustained"] is not None:
             line["sustained"] = main["sustained"]
+        if main["breakdown"] is not None:
+            line["step_breakdown"] = main["breakdown"]
         if api is not None:
             line["e2e_api"] = api
         if hnsw_sharded is not None:
