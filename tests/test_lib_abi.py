@@ -56,14 +56,41 @@ def test_two_stage_argument_validation_without_gpu(built_lib):
     assert lib.vq_search_two_stage_workspace_bytes(1000000, 512, 512, 1024, 32) > (1 << 20)
 
 
-def test_no_product_import_of_oracle():
-    """The product package must never import the oracle (it is test infrastructure)."""
+def test_exact_search_argument_validation_without_gpu(built_lib):
+    """vq_search_exact / vq_store_bounds / vq_search_collect check their arguments before any CUDA call."""
+    lib = _lib.load()
+    one = ctypes.c_void_p(256)                   # non-NULL, 256-byte aligned placeholder: validation must fail before any dereference
+
+    def call(n=1000, dim=512, ld=512, b=4, k=10, norm=1, bounds=one, ws=one):
+        return lib.vq_search_exact(one, one, n, dim, ld, one, b, k, norm, bounds, one, one, one, None, ws, 1 << 30, None)
+    assert call(k=0) == -1 and call(k=129) == -1 and b"k" in lib.vq_last_error()
+    assert call(ld=520) == -1 and b"ld" in lib.vq_last_error()              # bf16 stores need ld % 64 == 0
+    assert call(norm=7) == -1
+    assert call(bounds=None) == -1 and b"NULL" in lib.vq_last_error()         # the rounding bounds are not optional
+    assert call(n=0) == -1
+    assert call(b=0) == 0                                                     # empty batch: nothing to do
+    assert lib.vq_search_exact_supported(1_000_000, 512, 512, 1024, 10) == 1
+    assert lib.vq_search_exact_supported(1_000_000, 512, 512, 1024, 64) == 1
+    assert lib.vq_search_exact_supported(10_000_000, 768, 768, 1024, 100) == 0    # k > 64 on a large store: two-pass route
+    assert lib.vq_search_exact_supported(20_000, 768, 768, 12, 100) == 1          # listless mode where the gather cannot overflow
+    assert lib.vq_search_exact_supported(1_000_000, 1024, 1024, 8, 10) == 0       # rows wider than the tensor-memory budget
+    assert lib.vq_search_exact_workspace_bytes(1_000_000, 512, 512, 1024, 10) > (32 << 20)    # 1024 x 4096 gather slots
+    assert lib.vq_store_bounds(one, one, 10, 500, one, None) == -1
+    assert lib.vq_store_bounds(one, one, 10, 512, None, None) == -1
+    assert lib.vq_store_bounds(None, None, 0, 512, one, None) == 0
+    rc = lib.vq_search_collect(one, one, 1000, 512, 512, one, 4, 10, 1, None, 8, None, one, one, one, one, 1 << 30, None)
+    assert rc == -1 and b"cap" in lib.vq_last_error()                         # cap < k
+
+
+def test_no_product_import_of_oracle_or_baseline():
+    """The product package must never import the oracle or the vendored reference (test / baseline infrastructure)."""
     pkg = os.path.join(ROOT, "video_quierer_b200")
     for dirpath, _, files in os.walk(pkg):
         for f in files:
             if f.endswith((".py", ".cu", ".cuh")):
                 src = open(os.path.join(dirpath, f)).read()
-                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
+                assert not re.search(r"^\s*(from|import)\s+(oracle|baseline)\b", src, flags=re.M), f
+                assert "baseline/_ref" not in src and "hnsw_ref" not in src, f
 
 
 def test_peer_exchange_argument_validation_without_gpu(built_lib):
