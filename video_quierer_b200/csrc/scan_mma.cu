@@ -324,7 +324,7 @@ constexpr int kMaxSub = 8;              // sub-streams per CTA at most
 // a SUBSET of the maxima — smaller or equal, i.e. still a valid bound.
 constexpr int kMaxPublished = 160;
 __device__ __forceinline__ void kth_largest_batch8(const float* __restrict__ cm_tile, int V, int k, int lane, int ql0, int ql_step,
-                                                   float (&out)[8]) {
+                                                   float (&out)[8], int nq = 8) {      // only the first nq queries are computed
     float t1[8], t2[8];
 #pragma unroll
     for (int u = 0; u < 8; ++u) { t1[u] = VQ_NEG_INF; t2[u] = VQ_NEG_INF; }
@@ -333,23 +333,25 @@ __device__ __forceinline__ void kth_largest_batch8(const float* __restrict__ cm_
         const int i = lane + 32 * ii;
         float v[8];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) v[u] = i < V ? __ldcg(cm_tile + (size_t)(ql0 + u * ql_step) * V + i) : VQ_NEG_INF;
+        for (int u = 0; u < 8; ++u) v[u] = (i < V && u < nq) ? __ldcg(cm_tile + (size_t)(ql0 + u * ql_step) * V + i) : VQ_NEG_INF;
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
             if (v[u] > t1[u]) { t2[u] = t1[u]; t1[u] = v[u]; } else if (v[u] > t2[u]) t2[u] = v[u];
         }
     }
-    // the 8 selections advance in lockstep: 8 independent dependency chains per round hide the redux / ballot latency
+    // the selections advance in lockstep: independent dependency chains per round hide the redux / ballot latency
 #pragma unroll
     for (int u = 0; u < 8; ++u) out[u] = VQ_NEG_INF;
     for (int j = 0; j < k; ++j) {
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
-            const unsigned key = ~vq_score_key(t1[u]);                // monotone increasing in the score
-            const unsigned mx = __reduce_max_sync(0xffffffffu, key);
-            const unsigned who = __ballot_sync(0xffffffffu, key == mx);
-            out[u] = vq_key_score(~mx);
-            if (lane == __ffs(who) - 1) { t1[u] = t2[u]; t2[u] = VQ_NEG_INF; }
+            if (u < nq) {
+                const unsigned key = ~vq_score_key(t1[u]);            // monotone increasing in the score
+                const unsigned mx = __reduce_max_sync(0xffffffffu, key);
+                const unsigned who = __ballot_sync(0xffffffffu, key == mx);
+                out[u] = vq_key_score(~mx);
+                if (lane == __ffs(who) - 1) { t1[u] = t2[u]; t2[u] = VQ_NEG_INF; }
+            }
         }
     }
 }
@@ -529,8 +531,9 @@ scan_mma_bf16_kernel(const __grid_constant__ CUtensorMap tmS,
                 if (lane < 8) cur = *reinterpret_cast<volatile float*>(gtau + q_tile * QT + ql);
                 if (__all_sync(0xffffffffu, lane >= 8 || cur == INFINITY)) continue;   // padding queries
                 float kth[8];
-                kth_largest_batch8(cm_tile, V, k, lane, q0 + 7 < QT ? q0 : QT - 8, 1, kth);
-                const int shift = q0 + 7 < QT ? 0 : q0 - (QT - 8);                    // batch start was pulled back at the tile's end
+                const int shift = q0 + 7 < QT ? 0 : q0 - (QT - 8);                    // batch start pulled back at the tile's end
+                const int nq = (q_hi - q0 < 8 ? q_hi - q0 : 8) + shift;               // CTAs of a 148-group launch own ONE query each
+                kth_largest_batch8(cm_tile, V, k, lane, q0 - shift, 1, kth, nq);
                 float mine = VQ_NEG_INF;
 #pragma unroll
                 for (int u = 0; u < 8; ++u) mine = (lane + shift == u) ? kth[u] : mine;
@@ -1423,9 +1426,10 @@ ExactPlan plan_exact(int64_t n, int ld, int b, int k) {
     // Periodic refresh of the cooperative bound (warp 3 of every CTA, each for its share of the tile's queries): first
     // sleep 4 us, backing off to 64 us while nothing changes.  VQ_EXACT_REFRESH_NS overrides (0 = off).
     static const int refresh_env = getenv("VQ_EXACT_REFRESH_NS") ? atoi(getenv("VQ_EXACT_REFRESH_NS")) : -1;
-    // Off for a single query tile: that scan is HBM-bound with an idle epilogue, a smaller gather buys nothing there and
-    // the refresher measurably costs (batch 1 / 32 at 1M rows: kernel 0.166 -> 0.184 ms with it).
-    x.refresh_ns = refresh_env >= 0 ? refresh_env : (p.n_qt >= 2 ? 4000 : 0);
+    // A single query tile (HBM-bound scan, 148 CTAs that each see 1/148 of the store) refreshes at a slower cadence: at
+    // 4 us the refresher cost batch 1 / 32 at 1M rows 0.166 -> 0.184 ms of kernel time, but without it the CTA-local
+    // bounds let the gather grow with the store (2900 rows per query at 1M, buffer overflow at 12.5M rows per GPU).
+    x.refresh_ns = refresh_env >= 0 ? refresh_env : (p.n_qt >= 2 ? 4000 : 16000);
     p.cap = cap;
     x.k_sel = k <= 16 ? 32 : (k + (k / 2 > 22 ? k / 2 : 22));
     const size_t cand_bytes = align256((size_t)p.b_pad * cap * 4);
