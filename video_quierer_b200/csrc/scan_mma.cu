@@ -523,7 +523,9 @@ scan_mma_bf16_kernel(const __grid_constant__ CUtensorMap tmS,
         }
         unsigned sleep_ns = (unsigned)xs.refresh_ns;
         while (sleep_ns > 0 && q_hi > q_lo && *reinterpret_cast<volatile int*>(&sflags[2]) < 4) {
-            __nanosleep(sleep_ns);
+            // sleep in 1 us slices: the CTA cannot retire before this warp has seen the epilogue's done flag
+            for (unsigned slept = 0; slept < sleep_ns && *reinterpret_cast<volatile int*>(&sflags[2]) < 4; slept += 1000) __nanosleep(1000);
+            if (*reinterpret_cast<volatile int*>(&sflags[2]) >= 4) break;
             bool changed = false;
             for (int q0 = q_lo; q0 < q_hi; q0 += 8) {
                 const int ql = q0 + lane < q_hi ? q0 + lane : q_hi - 1;              // lanes 0..7: the batch's queries (clamped)
@@ -1363,7 +1365,7 @@ ExactPlan plan_exact(int64_t n, int ld, int b, int k) {
     const long long n_tiles = (n + p.nt - 1) / p.nt;
     // rows a query may gather: the rows within 2 eps of its k-th best plus the transient while the bound warms up
     // (measured: a few hundred on iid data, 1-2 thousand on tightly clustered data)
-    int cap = p.n_qt <= 8 ? 4096 : (p.n_qt <= 16 ? 2048 : 1024);
+    int cap = p.n_qt <= 16 ? 4096 : 2048;        // (config 5, 32 query tiles over 12.5M clustered rows: 700 rows per query on average, 235 of 4096 queries beyond 1024)
     static const int cap_env = getenv("VQ_EXACT_CAP") ? atoi(getenv("VQ_EXACT_CAP")) : 0;
     if (cap_env > 0) cap = cap_env;
     const long long n8 = (n + 7) / 8 * 8;
