@@ -12,6 +12,9 @@ ncu --set full --clock-control none --import-source on -k regex:scan_mma_bf16_ke
 ncu --set full --clock-control none --import-source on -k regex:scan_mma_bf16_kernel -s 11 -c 1 -f -o gpurun_out/r02_scan_exact_b32_clip $P --n 1000000 --batch 32 > gpurun_out/r02_ncu_c.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:scan_mma_bf16_kernel -s 11 -c 1 -f -o gpurun_out/r02_scan_exact_b1024_shard125k $P --n 125000 > gpurun_out/r02_ncu_d.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:exact_finish_kernel -s 6 -c 1 -f -o gpurun_out/r02_exact_finish_b1024_clip $P --n 1000000 > gpurun_out/r02_ncu_e.log 2>&1
+# DRAM traffic of the per-GPU shard shapes of N = 2 / 4 (roofline.traffic at N > 1)
+ncu --set full --clock-control none -k regex:scan_mma_bf16_kernel -s 11 -c 1 -f -o gpurun_out/r02_scan_exact_b1024_shard250k $P --n 250000 > gpurun_out/r02_ncu_f.log 2>&1
+ncu --set full --clock-control none -k regex:scan_mma_bf16_kernel -s 11 -c 1 -f -o gpurun_out/r02_scan_exact_b1024_shard500k $P --n 500000 > gpurun_out/r02_ncu_g.log 2>&1
 # smoke() under a kernel-serialising profiler must pass
 ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file gpurun_out/r02_launches_smoke.csv python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/r02_ncu_smoke.log 2>&1; echo "smoke under ncu rc=$?" >> gpurun_out/r02_ncu_smoke.log
 ls -la gpurun_out/*.ncu-rep
