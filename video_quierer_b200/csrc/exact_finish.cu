@@ -21,7 +21,8 @@ namespace {
 
 constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
-constexpr int kXMax = 2048;              // rows re-scored per query at most
+constexpr int kXMaxLarge = 2048;         // rows re-scored per query at most (k_sel > 64: the large-k route)
+constexpr int kXMaxSmall = 1024;         // ... for k <= 64 (measured: <= 140 on clustered 1M-row stores): 12 KB less shared memory, 4 instead of 3 CTAs per SM
 constexpr int kSelStop = 64;             // the bisection stops once this few keys (>= k_sel) are left
 
 // exact fp32 scores of rows[0..cnt) -> 64-bit (exact score key, row) keys; one warp per row, 4 rows of a
@@ -63,7 +64,7 @@ __global__ void __launch_bounds__(kThreads)
 exact_finish_kernel(const float* __restrict__ cand_s, const int* __restrict__ cand_r, const int* __restrict__ cand_cnt,
                     int cap, int k_sel, const float* __restrict__ qeps, const float* __restrict__ store_f32, int ld, int dim,
                     const float* __restrict__ queries, int query_norm, int k_out,
-                    float* __restrict__ out_s, int* __restrict__ out_r, int* __restrict__ out_over, int* __restrict__ out_stats, int sort_cap) {
+                    float* __restrict__ out_s, int* __restrict__ out_r, int* __restrict__ out_over, int* __restrict__ out_stats, int sort_cap, int kXMax) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     unsigned long long* keys = reinterpret_cast<unsigned long long*>(smem_raw);          // [sort_cap] bf16-score keys
     unsigned long long* xkey = keys + sort_cap;                                           // [kXMax] exact-score keys
@@ -199,6 +200,7 @@ int vq_exact_finish_launch(const float* cand_s, const int* cand_r, const int* ca
                            const float* qeps, const float* store_f32, int ld, int dim, const float* queries, int query_norm,
                            int k_out, float* out_scores, int* out_rows, int* out_overflow, int* out_stats, cudaStream_t stream) {
     if (b <= 0) return VQ_OK;
+    const int kXMax = k_sel <= 64 ? kXMaxSmall : kXMaxLarge;
     if (k_out > k_sel || k_sel > kXMax / 2) {
         vq_set_error("exact_finish: need k_out <= k_sel <= %d (k_sel=%d k_out=%d)", kXMax / 2, k_sel, k_out);
         return VQ_EUNSUPPORTED;
@@ -215,7 +217,7 @@ int vq_exact_finish_launch(const float* cand_s, const int* cand_r, const int* ca
         vq_mark_used(&attr_done);
     }
     const cudaError_t e = vq_launch(4, exact_finish_kernel, dim3(b), dim3(kThreads), smem, stream, cand_s, cand_r, cand_cnt, cap, k_sel,
-                                    qeps, store_f32, ld, dim, queries, query_norm, k_out, out_scores, out_rows, out_overflow, out_stats, sort_cap);
+                                    qeps, store_f32, ld, dim, queries, query_norm, k_out, out_scores, out_rows, out_overflow, out_stats, sort_cap, kXMax);
     if (e != cudaSuccess) {
         vq_set_error("launch of exact_finish_kernel failed: %s", cudaGetErrorString(e));
         return VQ_ECUDA;
