@@ -57,7 +57,12 @@ namespace {
 constexpr int QT = 128;                 // queries per tile   (UMMA M)
 constexpr int KB_ELEMS = 64;            // bf16 per k-block = one 128-byte swizzle span
 constexpr int TMEM_COLS = 512;          // whole tensor memory: 2 accumulators + resident query tile
-constexpr int kThreads = 256;
+
+// Epilogue warps: 4 (one per quarter of the 128 TMEM lanes) or, in the exact mode with lists of <= 32 entries, 8 — warps w and
+// w + 4 serve the same 32 queries and split the columns (store rows) of every tile, halving the per-tile critical path of the
+// epilogue, which is as long as the tile's MMAs as soon as the gather slow path runs (12 warps x 168 registers still fit).
+constexpr int epi_warps(int kl, int mode) { return (mode == 3 && kl <= 32) ? 8 : 4; }
+constexpr int kThreadsFor(int epi) { return (4 + epi) * 32; }
 constexpr int kMaxK = 64;
 constexpr int kModeList = 0, kModeBoot = 1, kModeCollect = 2, kModeExact = 3;   // epilogue of scan_mma_bf16_kernel
 constexpr int kStage = 8;               // collect mode: candidates a thread stages in shared memory per global atomic
@@ -252,7 +257,7 @@ __device__ __forceinline__ void filter_insert(const uint32_t (&v)[32], int row_b
 template <int KL, bool LIST, typename Flush>
 __device__ __forceinline__ float filter_collect(const uint32_t (&v)[32], int row_base, int left, float g_keep, const float& eps2,
                                                float& thr, float& thr_c, float (&ls)[KL], int (&lr)[KL],
-                                               float* stage_s, int* stage_r, int& staged, Flush&& flush) {
+                                               float* stage_s, int* stage_r, int sstride, int& staged, Flush&& flush) {
     // maxima of the four groups of 8 scores, then of the chunk: almost no chunk holds a candidate once the bound is warm
     float g[4];
 #pragma unroll
@@ -285,8 +290,8 @@ __device__ __forceinline__ float filter_collect(const uint32_t (&v)[32], int row
 #pragma unroll
             for (int jj = 1; jj < 32; ++jj) s = (j == jj) ? __uint_as_float(v[jj]) : s;
         }
-        stage_s[staged * QT] = s;
-        stage_r[staged * QT] = row_base + j;
+        stage_s[staged * sstride] = s;
+        stage_r[staged * sstride] = row_base + j;
         if (++staged == kStage) flush();
         if (LIST && s > thr) {
             ls[0] = s;
@@ -356,8 +361,8 @@ __device__ __forceinline__ void kth_largest_batch8(const float* __restrict__ cm_
     }
 }
 
-template <int KL, int NT, int MODE>
-__global__ void __launch_bounds__(kThreads, 1)
+template <int KL, int NT, int MODE, int EPI>
+__global__ void __launch_bounds__(kThreadsFor(EPI), 1)
 scan_mma_bf16_kernel(const __grid_constant__ CUtensorMap tmS,
                      const __nv_bfloat16* __restrict__ qbf,   // [b_pad, ld] normalised, zero padded
                      float* __restrict__ gtau,                // [b_pad] shared k-th best per query (-inf initialised)
@@ -368,6 +373,8 @@ scan_mma_bf16_kernel(const __grid_constant__ CUtensorMap tmS,
                      const XShared xs) {                          // exact mode: cooperative bound (see XShared)
     constexpr int B_KB_BYTES = NT * 128;
     constexpr uint32_t A_COL0 = 2 * NT;                         // first TMEM column of the query tile
+    constexpr int kEpi = EPI;                                   // epilogue warps
+    constexpr int QTS = QT * (kEpi / 4);                        // epilogue threads = staging slices
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     unsigned char* sB = smem;                                   // ring of store-tile k-blocks
@@ -390,14 +397,14 @@ scan_mma_bf16_kernel(const __grid_constant__ CUtensorMap tmS,
     const int n_iter = n_local + boot_T;
     auto tile_at = [&](int it) { return group + (it < n_local ? it : it - n_local) * n_groups; };
     // exact mode: bound per query of this tile (refreshed by warp 3), flags
-    float* sbound = reinterpret_cast<float*>(smem + (size_t)stages * B_KB_BYTES + 512 + (size_t)QT * kStage * 8);
+    float* sbound = reinterpret_cast<float*>(smem + (size_t)stages * B_KB_BYTES + 512 + (size_t)2 * QT * kStage * 8);
     int* sflags = reinterpret_cast<int*>(sbound + QT);          // [0] epilogue warps past the boot tiles, [1] bound ready, [2] epilogue warps done
 
     if (warp == 0 && lane == 0) tma_prefetch_desc(&tmS);
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], kIssuers * cl); }
         mbar_init(a_full, 4);
-        for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], kIssuers); mbar_init(&tmem_empty[a], 4); mbar_init(&x_first[a], 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], kIssuers); mbar_init(&tmem_empty[a], kEpi); mbar_init(&x_first[a], 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -519,13 +526,13 @@ scan_mma_bf16_kernel(const __grid_constant__ CUtensorMap tmS,
         const int q_lo = (int)(((long long)group * QT) / n_groups), q_hi = (int)(((long long)(group + 1) * QT) / n_groups);
         if (boot_T > 0) {
             const long long t0 = clock64();
-            while (*reinterpret_cast<volatile int*>(&sflags[0]) < 4 && clock64() - t0 < 8000000) __nanosleep(500);
+            while (*reinterpret_cast<volatile int*>(&sflags[0]) < kEpi && clock64() - t0 < 8000000) __nanosleep(500);
         }
         unsigned sleep_ns = (unsigned)xs.refresh_ns;
-        while (sleep_ns > 0 && q_hi > q_lo && *reinterpret_cast<volatile int*>(&sflags[2]) < 4) {
+        while (sleep_ns > 0 && q_hi > q_lo && *reinterpret_cast<volatile int*>(&sflags[2]) < kEpi) {
             // sleep in 1 us slices: the CTA cannot retire before this warp has seen the epilogue's done flag
-            for (unsigned slept = 0; slept < sleep_ns && *reinterpret_cast<volatile int*>(&sflags[2]) < 4; slept += 1000) __nanosleep(1000);
-            if (*reinterpret_cast<volatile int*>(&sflags[2]) >= 4) break;
+            for (unsigned slept = 0; slept < sleep_ns && *reinterpret_cast<volatile int*>(&sflags[2]) < kEpi; slept += 1000) __nanosleep(1000);
+            if (*reinterpret_cast<volatile int*>(&sflags[2]) >= kEpi) break;
             bool changed = false;
             for (int q0 = q_lo; q0 < q_hi; q0 += 8) {
                 const int ql = q0 + lane < q_hi ? q0 + lane : q_hi - 1;              // lanes 0..7: the batch's queries (clamped)
@@ -545,14 +552,15 @@ scan_mma_bf16_kernel(const __grid_constant__ CUtensorMap tmS,
             }
             sleep_ns = changed ? (unsigned)xs.refresh_ns : (sleep_ns < 16u * (unsigned)xs.refresh_ns ? sleep_ns * 2 : sleep_ns);
         }
-    } else if (warp >= 4) {
-        const int ew = warp - 4;                          // == warp % 4: TMEM lanes [32*ew, 32*ew+32)
+    } else if (warp >= 4 && warp < 4 + kEpi) {
+        const int ew = (warp - 4) & 3;                    // == warp % 4: TMEM lanes [32*ew, 32*ew+32)
+        const int half = (warp - 4) >> 2;                 // 8 epilogue warps: which half of a tile's columns this warp filters
         // TMEM lane ew*32+lane serves query (lane*4 + ew) of the tile: a small batch is spread over all
-        // four epilogue warps
+        // four lane quarters
         const int q = q_tile * QT + lane * 4 + ew;
         const uint32_t lane_base = tmem_base + ((uint32_t)(ew * 32) << 16);
         // ---- query tile -> tensor memory: lane t holds query q, column c holds elements 2c, 2c+1
-        {
+        if (half == 0) {
             const uint4* qrow = reinterpret_cast<const uint4*>(qbf + (size_t)q * ld);
             // 4 k-blocks (32 x 16 B loads) in flight per thread before the first tcgen05.st
             for (int kb0 = 0; kb0 < nkb; kb0 += 4) {
@@ -640,14 +648,13 @@ scan_mma_bf16_kernel(const __grid_constant__ CUtensorMap tmS,
             for (int i = 0; i < KL; ++i) { ls[i] = (LIST && i < k) ? VQ_NEG_INF : INFINITY; lr[i] = VQ_EMPTY_ROW; }
             float eps2 = 2.f * qeps[q];              // -inf once the buffer has overflowed: thr_c = +inf, nothing passes
             const size_t dst = (size_t)q * cap;
-            const int ql = lane * 4 + ew;
-            float* stage_s = reinterpret_cast<float*>(smem + (size_t)stages * B_KB_BYTES + 512) + (ew * 32 + lane);
-            int* stage_r = reinterpret_cast<int*>(smem + (size_t)stages * B_KB_BYTES + 512 + (size_t)QT * kStage * 4) + (ew * 32 + lane);
+            float* stage_s = reinterpret_cast<float*>(smem + (size_t)stages * B_KB_BYTES + 512) + (half * QT + ew * 32 + lane);
+            int* stage_r = reinterpret_cast<int*>(smem + (size_t)stages * B_KB_BYTES + 512 + (size_t)QTS * kStage * 4) + (half * QT + ew * 32 + lane);
             int staged = 0;
             auto flush = [&]() {
                 const int at = atomicAdd(cand_cnt + q, staged);
                 for (int i = 0; i < staged; ++i)
-                    if (at + i < cap) { cand_s[dst + at + i] = stage_s[i * QT]; cand_r[dst + at + i] = stage_r[i * QT]; }
+                    if (at + i < cap) { cand_s[dst + at + i] = stage_s[i * QTS]; cand_r[dst + at + i] = stage_r[i * QTS]; }
                 staged = 0;
                 if (at + kStage > cap) eps2 = VQ_NEG_INF;    // overflow (mass ties): the finish kernel flags the query
             };
@@ -660,7 +667,7 @@ scan_mma_bf16_kernel(const __grid_constant__ CUtensorMap tmS,
             auto publish = [&](int sub, float m) {
 #pragma unroll
                 for (int j = 0; j < kMaxSub; ++j)
-                    if (j == sub && m > smax[j]) { smax[j] = m; *reinterpret_cast<volatile float*>(my_cmax + j) = m; }
+                    if (j == sub && m > smax[j]) { smax[j] = m; atomic_max_float(my_cmax + j, m); }   // (two column halves share a slot)
             };
             float g_next = *reinterpret_cast<volatile float*>(gtau + q);      // static / bootstrap bound, then the refreshed one
             for (int it = 0; it < n_iter; ++it) {
@@ -676,7 +683,7 @@ scan_mma_bf16_kernel(const __grid_constant__ CUtensorMap tmS,
                     tc_fence_after();
                     float m = VQ_NEG_INF;
 #pragma unroll 1
-                    for (int c0 = 0; c0 < NT; c0 += 32) {
+                    for (int c0 = half * (NT / (kEpi / 4)); c0 < (half + 1) * (NT / (kEpi / 4)); c0 += 32) {
                         uint32_t v[32];
                         tmem_ld32(lane_base + (uint32_t)(acc * NT + c0), v);
 #pragma unroll
@@ -692,7 +699,7 @@ scan_mma_bf16_kernel(const __grid_constant__ CUtensorMap tmS,
                         // they published is the first bound of these 32 queries (the threshold bootstrap).
                         __threadfence();
                         __syncwarp();
-                        int* arr = xs.arrived + q_tile * 4 + ew;
+                        int* arr = xs.arrived + q_tile * 8 + (warp - 4);
                         if (lane == 0) atomicAdd(arr, 1);
                         const long long t0 = clock64();
                         while (*reinterpret_cast<volatile int*>(arr) < n_groups && clock64() - t0 < 4000000) __nanosleep(64);
@@ -724,15 +731,19 @@ scan_mma_bf16_kernel(const __grid_constant__ CUtensorMap tmS,
                 tc_fence_after();
                 uint32_t va[32], vb[32];
                 float tmax = VQ_NEG_INF;
-                tmem_ld32_issue(lane_base + (uint32_t)(acc * NT), va);
+                constexpr int cpw = n_chunks / (kEpi / 4);           // chunks of 32 columns this warp filters per tile
+                const int c_lo = half * cpw;
+                tmem_ld32_issue(lane_base + (uint32_t)(acc * NT + c_lo * 32), va);
 #pragma unroll 1
-                for (int c = 0; c < n_chunks; c += 2) {
+                for (int c = 0; c < cpw; c += 2) {
                     tmem_ld_wait(va);
-                    tmem_ld32_issue(lane_base + (uint32_t)(acc * NT + (c + 1) * 32), vb);
-                    tmax = fmaxf(tmax, filter_collect<KL, LIST>(va, row0 + c * 32, valid - c * 32, g_keep, eps2, thr, thr_c, ls, lr, stage_s, stage_r, staged, flush));
-                    tmem_ld_wait(vb);
-                    if (c + 2 < n_chunks) tmem_ld32_issue(lane_base + (uint32_t)(acc * NT + (c + 2) * 32), va);
-                    tmax = fmaxf(tmax, filter_collect<KL, LIST>(vb, row0 + (c + 1) * 32, valid - (c + 1) * 32, g_keep, eps2, thr, thr_c, ls, lr, stage_s, stage_r, staged, flush));
+                    if (c + 1 < cpw) tmem_ld32_issue(lane_base + (uint32_t)(acc * NT + (c_lo + c + 1) * 32), vb);
+                    tmax = fmaxf(tmax, filter_collect<KL, LIST>(va, row0 + (c_lo + c) * 32, valid - (c_lo + c) * 32, g_keep, eps2, thr, thr_c, ls, lr, stage_s, stage_r, QTS, staged, flush));
+                    if (c + 1 < cpw) {
+                        tmem_ld_wait(vb);
+                        if (c + 2 < cpw) tmem_ld32_issue(lane_base + (uint32_t)(acc * NT + (c_lo + c + 2) * 32), va);
+                        tmax = fmaxf(tmax, filter_collect<KL, LIST>(vb, row0 + (c_lo + c + 1) * 32, valid - (c_lo + c + 1) * 32, g_keep, eps2, thr, thr_c, ls, lr, stage_s, stage_r, QTS, staged, flush));
+                    }
                 }
                 tc_fence_before();
                 __syncwarp();
@@ -863,7 +874,7 @@ prep_queries_bf16_kernel(const float* __restrict__ src, int b, int dim, int src_
     if (row >= b_pad) return;
     if (cmax) {
         for (int c = lane; c < cmax_v; c += 32) cmax[(size_t)row * cmax_v + c] = VQ_NEG_INF;
-        if (lane == 0 && row < 4 * n_qt) arrived[row] = 0;
+        if (lane == 0 && row < 8 * n_qt) arrived[row] = 0;
     }
     __nv_bfloat16* o = dst + (size_t)row * ld;
     // padding queries (zero rows of the last query tile) must neither keep nor gather anything: bound +inf
@@ -1045,7 +1056,7 @@ MmaPlan plan(int64_t n, int ld, int b, int k) {
     // each other, a prefix of the store would only know the first few videos
     p.boot_mul = p.boot_tiles ? (int)((n / p.nt) / p.boot_tiles) : 1;
     if (p.boot_mul < 1) p.boot_mul = 1;
-    p.smem = 1024 + (size_t)p.stages * stage_bytes + 512 + (size_t)QT * kStage * 8 + (size_t)QT * 4 + 64;
+    p.smem = 1024 + (size_t)p.stages * stage_bytes + 512 + (size_t)2 * QT * kStage * 8 + (size_t)QT * 4 + 64;
     // candidate capacity is sized for the largest group count any batch <= b can get (the HNSW builder
     // reuses one workspace for a shrinking last batch)
     const int max_groups = sms > p.n_qt ? sms : p.n_qt;
@@ -1081,10 +1092,10 @@ MmaWs carve(const MmaPlan& p, void* ws_v) {
     return w;
 }
 
-template <int KL, int NT, int MODE>
+template <int KL, int NT, int MODE, int EPI = epi_warps(KL, MODE)>
 cudaError_t launch_mma(const MmaPlan& p, const CUtensorMap& tmS, const __nv_bfloat16* qbf, const MmaWs& w, int n, int ld, int k,
                        int dbg, cudaStream_t stream) {
-    auto kern = scan_mma_bf16_kernel<KL, NT, MODE>;
+    auto kern = scan_mma_bf16_kernel<KL, NT, MODE, EPI>;
     constexpr bool BOOT = MODE == kModeBoot;
     static std::atomic<unsigned long long> attr_done{0};   // per instantiation, one bit per device
     if (vq_first_use_on_device(&attr_done)) {
@@ -1094,7 +1105,7 @@ cudaError_t launch_mma(const MmaPlan& p, const CUtensorMap& tmS, const __nv_bflo
     }
     const int grid = BOOT ? p.boot_groups * p.n_qt : p.grid;
     const int cl = (MODE == kModeList || MODE == kModeExact) ? p.cl : 1;
-    return vq_launch_cluster(BOOT ? 1 : 3, cl, kern, dim3(grid), dim3(kThreads), p.smem, stream, tmS, qbf, w.gtau, n, ld, p.nkb, p.n_qt,
+    return vq_launch_cluster(BOOT ? 1 : 3, cl, kern, dim3(grid), dim3(kThreadsFor(EPI)), p.smem, stream, tmS, qbf, w.gtau, n, ld, p.nkb, p.n_qt,
                              k, p.stages, p.grp_log2, cl, BOOT ? p.boot_mul : 1, p.b_pad, BOOT ? w.boot_max : w.cand_s, w.cand_r, w.cnt, p.cap, dbg,
                              (const float*)w.qeps, w.xs);
 }
@@ -1134,13 +1145,19 @@ int run_scan(const MmaPlan& p, const void* store, int64_t n, int ld, const __nv_
     }
     vq_prof_begin(stream);
     if (exact) {
-        if (p.nt == 128)
-            e = k == 10 ? launch_mma<10, 128, kModeExact>(p, tmM, qbf, w, (int)n, ld, k, dbg, stream)      // the contract's k: no sentinel slots to bubble through
+        if (p.nt == 128) {
+            // 8 epilogue warps pay when the gather slow path runs for many of the tile's 128 queries; a batch of a few
+            // queries is bound by the store stream and the four extra warps only add to launch and drain (measured: b <= 128
+            // is 1-5 us slower with them, b >= 256 8-12 % faster)
+            static const int epi_env = getenv("VQ_EXACT_EPI") ? atoi(getenv("VQ_EXACT_EPI")) : 0;
+            const bool epi4 = epi_env ? epi_env == 4 : b <= 128;
+            e = k == 10 ? (epi4 ? launch_mma<10, 128, kModeExact, 4>(p, tmM, qbf, w, (int)n, ld, k, dbg, stream)
+                                : launch_mma<10, 128, kModeExact>(p, tmM, qbf, w, (int)n, ld, k, dbg, stream))      // the contract's k: no sentinel slots to bubble through
               : k <= 16 ? launch_mma<16, 128, kModeExact>(p, tmM, qbf, w, (int)n, ld, k, dbg, stream)
               : k <= 32 ? launch_mma<32, 128, kModeExact>(p, tmM, qbf, w, (int)n, ld, k, dbg, stream)
               : k <= 64 ? launch_mma<64, 128, kModeExact>(p, tmM, qbf, w, (int)n, ld, k, dbg, stream)
                         : launch_mma<1, 128, kModeExact>(p, tmM, qbf, w, (int)n, ld, k, dbg, stream);
-        else
+        } else
             e = k <= 16 ? launch_mma<16, 64, kModeExact>(p, tmM, qbf, w, (int)n, ld, k, dbg, stream)
               : k <= 32 ? launch_mma<32, 64, kModeExact>(p, tmM, qbf, w, (int)n, ld, k, dbg, stream)
               : k <= 64 ? launch_mma<64, 64, kModeExact>(p, tmM, qbf, w, (int)n, ld, k, dbg, stream)
@@ -1442,7 +1459,7 @@ ExactPlan plan_exact(int64_t n, int ld, int b, int k) {
     p.off_qbf = o;     o += align256((size_t)p.b_pad * ld * 2);
     x.off_eps = o;     o += align256((size_t)p.b_pad * 4);
     x.off_cmax = o;    o += align256((size_t)p.b_pad * sms * kMaxSub * 4 / (p.n_qt > 0 ? p.n_qt : 1) + 1024);
-    x.off_arrived = o; o += align256((size_t)p.n_qt * 4 * 4);
+    x.off_arrived = o; o += align256((size_t)p.n_qt * 8 * 4);
     p.total = o;
     return x;
 }
