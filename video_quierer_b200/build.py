@@ -27,6 +27,7 @@ NVCC_FLAGS = [
     "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC,-O3,-Wall,-Wno-unused-function",
     "--expt-relaxed-constexpr",
+    *os.environ.get("VQ_NVCC_EXTRA", "").split(),     # developer builds, e.g. -DVQ_SCAN_TRACE
 ]
 
 

@@ -66,7 +66,6 @@ constexpr int kThreadsFor(int epi) { return (4 + epi) * 32; }
 constexpr int kMaxK = 64;
 constexpr int kModeList = 0, kModeBoot = 1, kModeCollect = 2, kModeExact = 3;   // epilogue of scan_mma_bf16_kernel
 constexpr int kStage = 8;               // collect mode: candidates a thread stages in shared memory per global atomic
-constexpr int kIssuers = 2;            // MMA-issuing warps (warps 1 and 2), alternating k-blocks
 constexpr int kMaxBootTiles = 256;     // sample tiles of the threshold bootstrap (8 per lane in boot_select)
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -107,6 +106,32 @@ __device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
                  ::"r"(smem_u32(bar)), "h"(mask) : "memory");
 }
+// ---- cta_group::2: the CTA pair of a cluster issues ONE M = 256 MMA per step.  Each CTA holds its own 128 queries in tensor
+// memory and HALF of the store tile (64 rows) in shared memory, so a store tile crosses the L2 -> SM fabric once per 256
+// queries instead of once per 128 (the fabric, ~6300 B/clk chip-wide, is what bounds the 1-CTA kernel: see DESIGN.md).
+__device__ __forceinline__ uint32_t mapa_rank(uint32_t cta_addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(cta_addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    // default semantics (release at CTA scope), as for a local arrive: what the waiting issuer depends on — the tcgen05.ld /
+    // TMA completions before this arrive — is ordered by the tcgen05 fences and the barrier itself.  A .release.cluster
+    // here made every arrive wait for the thread's outstanding global stores and atomics (~1000s of cycles per tile).
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void umma_commit_cg2(uint64_t* bar) {     // arrives on the same barrier of BOTH CTAs
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void umma_bf16_ts_cg2(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+        "}" ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
 __device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
 __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
@@ -139,8 +164,8 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
     return d;
 }
 // kind::f16 instruction descriptor: bf16 x bf16 -> fp32, both operands K-major, M = 128, N = nt
-__device__ __forceinline__ uint32_t umma_idesc_bf16(int nt) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(nt >> 3) << 17) | ((uint32_t)(QT >> 4) << 24);
+__device__ __forceinline__ uint32_t umma_idesc_bf16(int nt, int m = QT) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(nt >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 // D[tmem] (+)= A[tmem] * B[smem]   (A operand resident in tensor memory)
 __device__ __forceinline__ void umma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
@@ -361,7 +386,14 @@ __device__ __forceinline__ void kth_largest_batch8(const float* __restrict__ cm_
     }
 }
 
-template <int KL, int NT, int MODE, int EPI>
+#ifdef VQ_SCAN_TRACE
+// developer build: clock64 stamps of CTA 0's pipeline events over four consecutive tiles (printed when the kernel ends)
+__device__ long long g_tr[4 * 16];
+#define TR(itv, slot) do { if (lane == 0 && blockIdx.x == 0 && (itv) >= 200 && (itv) < 204) g_tr[((itv) - 200) * 16 + (slot)] = clock64(); } while (0)
+#else
+#define TR(itv, slot) do { } while (0)
+#endif
+template <int KL, int NT, int MODE, int EPI, bool CG2>
 __global__ void __launch_bounds__(kThreadsFor(EPI), 1)
 scan_mma_bf16_kernel(const __grid_constant__ CUtensorMap tmS,
                      const __nv_bfloat16* __restrict__ qbf,   // [b_pad, ld] normalised, zero padded
@@ -371,25 +403,26 @@ scan_mma_bf16_kernel(const __grid_constant__ CUtensorMap tmS,
                      int* __restrict__ cand_r, int* __restrict__ cand_cnt, int cap, int dbg,
                      const float* __restrict__ qeps,              // [b_pad] per-query score-error bound (exact mode)
                      const XShared xs) {                          // exact mode: cooperative bound (see XShared)
-    constexpr int B_KB_BYTES = NT * 128;
+    constexpr int B_KB_BYTES = NT * 128;                        // one k-block of a store tile
+    constexpr int B_ST_BYTES = CG2 ? B_KB_BYTES / 2 : B_KB_BYTES;   // ... and what one ring slot of this CTA holds of it
     constexpr uint32_t A_COL0 = 2 * NT;                         // first TMEM column of the query tile
     constexpr int kEpi = EPI;                                   // epilogue warps
     constexpr int QTS = QT * (kEpi / 4);                        // epilogue threads = staging slices
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     unsigned char* sB = smem;                                   // ring of store-tile k-blocks
-    uint64_t* full = reinterpret_cast<uint64_t*>(sB + (size_t)stages * B_KB_BYTES);
+    const size_t ring_bytes = (size_t)stages * B_ST_BYTES;
+    uint64_t* full = reinterpret_cast<uint64_t*>(sB + ring_bytes);
     uint64_t* empty = full + stages;
     uint64_t* a_full = empty + stages;
     uint64_t* tmem_full = a_full + 1;      // [2]
     uint64_t* tmem_empty = tmem_full + 2;  // [2]
-    uint64_t* x_first = tmem_empty + 2;    // [2] issuer 0 has issued the overwriting MMA of the tile
+    uint64_t* x_first = tmem_empty + 2;    // [2] turn[r]: the other issuer has issued the tile before issuer r's next one
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(x_first + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int q_tile = blockIdx.x % n_qt, group = blockIdx.x / n_qt, n_groups = gridDim.x / n_qt;
     const int n_tiles = (n + NT - 1) / NT;
-    const int grp_mask = (1 << grp_log2) - 1;          // ring slots are released 2^grp_log2 at a time
     // This CTA's tiles: group, group + n_groups, ...  Exact mode scans its first boot_T tiles twice: first for
     // their maxima only (threshold bootstrap inside the kernel), again at the very end with the bound in place.
     const int n_local = group < n_tiles ? (n_tiles - group + n_groups - 1) / n_groups : 0;
@@ -397,20 +430,27 @@ scan_mma_bf16_kernel(const __grid_constant__ CUtensorMap tmS,
     const int n_iter = n_local + boot_T;
     auto tile_at = [&](int it) { return group + (it < n_local ? it : it - n_local) * n_groups; };
     // exact mode: bound per query of this tile (refreshed by warp 3), flags
-    float* sbound = reinterpret_cast<float*>(smem + (size_t)stages * B_KB_BYTES + 512 + (size_t)2 * QT * kStage * 8);
+    float* sbound = reinterpret_cast<float*>(smem + ring_bytes + 512 + (size_t)2 * QT * kStage * 8);
     int* sflags = reinterpret_cast<int*>(sbound + QT);          // [0] epilogue warps past the boot tiles, [1] bound ready, [2] epilogue warps done
 
     if (warp == 0 && lane == 0) tma_prefetch_desc(&tmS);
     if (warp == 1 && lane == 0) {
-        for (int s = 0; s < stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], kIssuers * cl); }
-        mbar_init(a_full, 4);
-        for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], kIssuers); mbar_init(&tmem_empty[a], kEpi); mbar_init(&x_first[a], 1); }
+        // cta_group::2: only the leader's issuers commit (to both CTAs); the leader's a_full / tmem_empty count both CTAs' warps
+        // (one full / empty barrier per ring GROUP; a group is committed by the one issuer that owns its tile)
+        for (int s = 0; s < stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], CG2 ? 1 : cl); }
+        mbar_init(a_full, CG2 ? 8 : 4);
+        for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], CG2 ? 2 * kEpi : kEpi); mbar_init(&x_first[a], 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     if (warp == 2) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "r"((uint32_t)TMEM_COLS) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if (CG2) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "r"((uint32_t)TMEM_COLS) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "r"((uint32_t)TMEM_COLS) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
     }
     tc_fence_before();
     if (cl > 1) cluster_sync_all(); else __syncthreads();     // the peer's barriers are live before anything lands on them
@@ -430,39 +470,70 @@ scan_mma_bf16_kernel(const __grid_constant__ CUtensorMap tmS,
     // in uniform registers) and elect one lane only for the asynchronous instruction itself: a loop
     // executed by a single lane makes ptxas wrap every UTCHMMA in an ELECT / R2UR waterfall
     // (~25 dependent instructions, measured 131 cycles per MMA instead of 64).
+    //
+    // The ring is handed over in GROUPS of gs = 2^grp_log2 k-blocks (gs divides nkb; 64 KB per group at dim 512: half a tile
+    // with 1-CTA MMAs, a whole tile for a CTA pair): one expect_tx and gs loads per group on the producer side, ONE barrier
+    // wait, 4 * gs back-to-back MMAs and one commit on the issuer side.  With a wait, a fence, an election and a commit per
+    // k-block the issue loop itself was the bound (~100 cycles per MMA, with or without loads and MMAs switched off).
+    const int gs = 1 << grp_log2;
     if (warp == 0) {
         int stage = 0; uint32_t phase = 0;
         const uint32_t sB_addr = smem_u32(sB), full_addr = smem_u32(full);
         for (int it_p = 0; it_p < n_iter; ++it_p) {
             const int tile = tile_at(it_p);
-            for (int kb = 0; kb < nkb; ++kb) {
-                if ((stage & grp_mask) == 0) mbar_wait(&empty[stage >> grp_log2], phase ^ 1);   // whole group free
+            for (int kb0 = 0; kb0 < nkb; kb0 += gs) {
+                const int grp = stage >> grp_log2;
+                mbar_wait(&empty[grp], phase ^ 1);                         // the whole group is free
                 if (elect_one()) {
-                    if (dbg & 2) { mbar_arrive(&full[stage]); }
-                    else {
-                        mbar_expect_tx(&full[stage], B_KB_BYTES);          // the whole box: own part + the peer's multicast
-                        if (cl > 1)
-                            tma_load_2d_mc(sB_addr + (uint32_t)stage * B_KB_BYTES + cl_rank * (B_KB_BYTES / 2), &tmS,
-                                           full_addr + (uint32_t)stage * 8, kb * KB_ELEMS, tile * NT + (int)cl_rank * (NT / 2), cl_mask);
-                        else
-                            tma_load_2d_addr(sB_addr + (uint32_t)stage * B_KB_BYTES, &tmS, full_addr + (uint32_t)stage * 8, kb * KB_ELEMS,
-                                             tile * tile_mul * NT);   // boot pass: sample tile j is store tile j * tile_mul
+                    if (dbg & 2) { mbar_arrive(&full[grp]); }
+                    else if (CG2) {
+                        // each CTA keeps its own half of every k-block (plain loads on its own barrier; the peer's relay warp
+                        // forwards the completion to the leader: .cta_group::2 loads counted on the leader's barrier streamed
+                        // at half the rate, 0.72 ms per 1M-row pass against 0.46 ms)
+                        mbar_expect_tx(&full[grp], (uint32_t)gs * B_ST_BYTES);
+                        for (int j = 0; j < gs; ++j)
+                            tma_load_2d_addr(sB_addr + (uint32_t)(stage + j) * B_ST_BYTES, &tmS, full_addr + (uint32_t)grp * 8,
+                                             (kb0 + j) * KB_ELEMS, tile * NT + (int)cl_rank * (NT / 2));
+                    } else {
+                        mbar_expect_tx(&full[grp], (uint32_t)gs * B_KB_BYTES);  // whole boxes: own part + the peer's multicast
+                        for (int j = 0; j < gs; ++j) {
+                            if (cl > 1)
+                                tma_load_2d_mc(sB_addr + (uint32_t)(stage + j) * B_KB_BYTES + cl_rank * (B_KB_BYTES / 2), &tmS,
+                                               full_addr + (uint32_t)grp * 8, (kb0 + j) * KB_ELEMS, tile * NT + (int)cl_rank * (NT / 2), cl_mask);
+                            else
+                                tma_load_2d_addr(sB_addr + (uint32_t)(stage + j) * B_KB_BYTES, &tmS, full_addr + (uint32_t)grp * 8,
+                                                 (kb0 + j) * KB_ELEMS, tile * tile_mul * NT);   // boot pass: sample tile j is store tile j * tile_mul
+                        }
                     }
                 }
                 __syncwarp();
-                if (++stage == stages) { stage = 0; phase ^= 1; }
+                stage += gs;
+                if (stage == stages) { stage = 0; phase ^= 1; }
             }
         }
-    } else if (warp == 1 || warp == 2) {
-        // Two issuing warps on two SM sub-partitions alternate the k-blocks of every tile (role 0: even,
-        // role 1: odd).  A UTCHMMA holds its warp's issue slot until the tensor pipe accepts it, so with
-        // one issuer the barrier waits and descriptor arithmetic between k-blocks leave the pipe idle
-        // (measured 89-117 cycles/MMA); with two, one warp's bookkeeping hides behind the other's MMAs
-        // (74 cycles/MMA in tools/mmabench.cu).  tcgen05.commit tracks the MMAs of the executing thread
-        // only, so BOTH issuers commit at every release point and the barriers count kIssuers arrivals.
+    } else if (CG2 && cl_rank != 0 && warp == 1) {
+        // relay (peer CTA of a pair): "my half of group g has landed" -> the leader's pfull[g]
+        const uint32_t pfull_leader = mapa_rank(smem_u32(full + stages / 2), 0);
+        int stage = 0; uint32_t phase = 0;
+        for (int it_r = 0; it_r < n_iter; ++it_r) {
+            for (int kb0 = 0; kb0 < nkb; kb0 += gs) {
+                const int grp = stage >> grp_log2;
+                mbar_wait(&full[grp], phase);
+                if (lane == 0) mbar_arrive_cluster(pfull_leader + (uint32_t)grp * 8);
+                __syncwarp();
+                stage += gs;
+                if (stage == stages) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if ((warp == 1 || warp == 2) && !(CG2 && cl_rank != 0)) {
+        // Two issuing warps on two SM sub-partitions own alternate tiles (issuer r: accumulator r), so the waits, the fence
+        // and the descriptor arithmetic of one tile hide behind the other issuer's MMAs.  The tensor pipe runs MMAs in issue
+        // order: issuer r starts a tile only after the other one has issued ALL MMAs of the tile before it (turn[]), so that
+        // tile t completes — and its epilogue starts — while tile t + 1 is still being multiplied.
         const int role = warp - 1;
-        const uint32_t idesc = umma_idesc_bf16(NT);
+        const uint32_t idesc = umma_idesc_bf16(NT, CG2 ? 2 * QT : QT);
         const uint32_t sB_addr = smem_u32(sB);
+        uint64_t* turn = x_first;
         mbar_wait(a_full, 0);                          // query tile is in tensor memory
         tc_fence_after();
         int stage = 0; uint32_t phase = 0; int it = 0;
@@ -470,42 +541,55 @@ scan_mma_bf16_kernel(const __grid_constant__ CUtensorMap tmS,
         if (dbg & 128) { dbg_c0 = clock64(); asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(dbg_t0)); }
         for (; it < n_iter; ++it) {
             const int acc = it & 1;
-            const uint32_t acc_phase = (it >> 1) & 1;
-            mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
-            tc_fence_after();
-            if (role == 1) {        // the MMA that OVERWRITES the accumulator (k-block 0) must be ordered first
-                mbar_wait(&x_first[acc], acc_phase);
+            const bool mine = acc == role;
+            const int nth = it >> 1;                   // this issuer's nth tile
+            if (mine) {
+                TR(it, 0);
+                mbar_wait(&tmem_empty[acc], (uint32_t)(nth & 1) ^ 1);
+                TR(it, 1);
+                // The tile before this one is in the pipe.  This wait also comes BEFORE the ring waits for a reason: an
+                // issuer skips the other one's tiles, and a parity wait two phases ahead of its barrier passes at once.
+                if (it > 0) mbar_wait(&turn[role], (uint32_t)((role == 1 ? nth : nth - 1) & 1));
                 tc_fence_after();
+                TR(it, 2);
             }
             const uint32_t d_tmem = tmem_base + (uint32_t)acc * NT;
-            for (int kb = 0; kb < nkb; ++kb) {
-                if ((kb & 1) == role) {
-                    mbar_wait(&full[stage], phase);
+            for (int kb0 = 0; kb0 < nkb; kb0 += gs) {
+                const int grp = stage >> grp_log2;
+                if (mine) {
+                    mbar_wait(&full[grp], phase);
+                    if (CG2) mbar_wait(&full[stages / 2 + grp], phase);      // pfull: the peer's half (see the relay warp)
                     tc_fence_after();
-                    if (elect_one() && !(dbg & 1)) {
-                        const uint64_t bd0 = umma_desc_sw128(sB_addr + (uint32_t)stage * B_KB_BYTES);
-                        const uint32_t a_tmem = tmem_base + A_COL0 + (uint32_t)kb * (KB_ELEMS / 2);
-#pragma unroll
-                        for (int k4 = 0; k4 < KB_ELEMS / 16; ++k4)   // +32 bytes per K=16 step = +2 in the (addr >> 4) field
-                            umma_bf16_ts(d_tmem, a_tmem + k4 * 8, bd0 + (uint64_t)(k4 * 2), idesc, (kb | k4) != 0 ? 1u : 0u);
-                    }
-                    __syncwarp();
-                    if (kb == 0) {                     // only role 0 gets here
-                        tc_fence_before();
-                        if (elect_one()) mbar_arrive(&x_first[acc]);
-                        __syncwarp();
-                    }
-                }
-                // ring slots are handed back 2^grp_log2 at a time; the accumulator is published after the last k-block
-                const bool rel = (stage & grp_mask) == grp_mask, last = kb == nkb - 1;
-                if (rel || last) {
+                    TR(it, kb0 == 0 ? 3 : 5);
                     if (elect_one()) {
-                        if (rel) { if (cl > 1) umma_commit_mc(&empty[stage >> grp_log2], cl_mask); else umma_commit(&empty[stage >> grp_log2]); }
-                        if (last) umma_commit(&tmem_full[acc]);
+                        if (!(dbg & 1)) {
+                            for (int j = 0; j < gs; ++j) {
+                                const uint64_t bd0 = umma_desc_sw128(sB_addr + (uint32_t)(stage + j) * B_ST_BYTES);
+                                const uint32_t a_tmem = tmem_base + A_COL0 + (uint32_t)(kb0 + j) * (KB_ELEMS / 2);
+#pragma unroll
+                                for (int k4 = 0; k4 < KB_ELEMS / 16; ++k4) {   // +32 bytes per K=16 step = +2 in the (addr >> 4) field
+                                    const uint32_t accum = ((kb0 + j) | k4) != 0 ? 1u : 0u;
+                                    if (CG2) umma_bf16_ts_cg2(d_tmem, a_tmem + k4 * 8, bd0 + (uint64_t)(k4 * 2), idesc, accum);
+                                    else umma_bf16_ts(d_tmem, a_tmem + k4 * 8, bd0 + (uint64_t)(k4 * 2), idesc, accum);
+                                }
+                            }
+                        }
+                        // the group goes back to the producer(s), the accumulator to the epilogue after the last k-block
+                        const bool last = kb0 + gs == nkb;
+                        if (CG2) {
+                            umma_commit_cg2(&empty[grp]);
+                            if (last) umma_commit_cg2(&tmem_full[acc]);
+                        } else {
+                            if (cl > 1) umma_commit_mc(&empty[grp], cl_mask); else umma_commit(&empty[grp]);
+                            if (last) umma_commit(&tmem_full[acc]);
+                        }
+                        if (last) mbar_arrive(&turn[role ^ 1]);
                     }
                     __syncwarp();
+                    TR(it, kb0 == 0 ? 4 : 6);
                 }
-                if (++stage == stages) { stage = 0; phase ^= 1; }
+                stage += gs;
+                if (stage == stages) { stage = 0; phase ^= 1; }
             }
         }
         if ((dbg & 128) && blockIdx.x == 0 && lane == 0 && role == 0) {
@@ -559,6 +643,9 @@ scan_mma_bf16_kernel(const __grid_constant__ CUtensorMap tmS,
         // four lane quarters
         const int q = q_tile * QT + lane * 4 + ew;
         const uint32_t lane_base = tmem_base + ((uint32_t)(ew * 32) << 16);
+        // an accumulator is handed back to the issuers — of the pair's leader when the pair shares its MMAs
+        const uint32_t tmem_empty_leader = CG2 ? mapa_rank(smem_u32(tmem_empty), 0) : 0u;
+        auto release_acc = [&](int a) { if (CG2) mbar_arrive_cluster(tmem_empty_leader + (uint32_t)a * 8); else mbar_arrive(&tmem_empty[a]); };
         // ---- query tile -> tensor memory: lane t holds query q, column c holds elements 2c, 2c+1
         if (half == 0) {
             const uint4* qrow = reinterpret_cast<const uint4*>(qbf + (size_t)q * ld);
@@ -582,7 +669,7 @@ scan_mma_bf16_kernel(const __grid_constant__ CUtensorMap tmS,
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(a_full);
+            if (lane == 0) { if (CG2) mbar_arrive_cluster(mapa_rank(smem_u32(a_full), 0)); else mbar_arrive(a_full); }
         }
         if (MODE == kModeCollect) {
             // collect pass: EVERY row whose score reaches the query's fixed threshold is appended to the
@@ -592,8 +679,8 @@ scan_mma_bf16_kernel(const __grid_constant__ CUtensorMap tmS,
             // candidates are staged kStage at a time in this thread's slice of shared memory and flushed
             // with ONE atomicAdd: waiting for a global atomic per candidate (an L2 round trip inside the
             // tile loop, hit by some lane in almost every 32-score chunk) cost as much as the MMAs
-            float* stage_s = reinterpret_cast<float*>(smem + (size_t)stages * B_KB_BYTES + 512) + (size_t)(ew * 32 + lane) * kStage;
-            int* stage_r = reinterpret_cast<int*>(smem + (size_t)stages * B_KB_BYTES + 512 + (size_t)QT * kStage * 4) + (size_t)(ew * 32 + lane) * kStage;
+            float* stage_s = reinterpret_cast<float*>(smem + ring_bytes + 512) + (size_t)(ew * 32 + lane) * kStage;
+            int* stage_r = reinterpret_cast<int*>(smem + ring_bytes + 512 + (size_t)QT * kStage * 4) + (size_t)(ew * 32 + lane) * kStage;
             int staged = 0;
             auto flush = [&]() {
                 const int at = atomicAdd(cand_cnt + q, staged);
@@ -631,7 +718,7 @@ scan_mma_bf16_kernel(const __grid_constant__ CUtensorMap tmS,
                 }
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+                if (lane == 0) release_acc(acc);
             }
             if (staged) flush();
         } else if (MODE == kModeExact) {
@@ -648,8 +735,8 @@ scan_mma_bf16_kernel(const __grid_constant__ CUtensorMap tmS,
             for (int i = 0; i < KL; ++i) { ls[i] = (LIST && i < k) ? VQ_NEG_INF : INFINITY; lr[i] = VQ_EMPTY_ROW; }
             float eps2 = 2.f * qeps[q];              // -inf once the buffer has overflowed: thr_c = +inf, nothing passes
             const size_t dst = (size_t)q * cap;
-            float* stage_s = reinterpret_cast<float*>(smem + (size_t)stages * B_KB_BYTES + 512) + (half * QT + ew * 32 + lane);
-            int* stage_r = reinterpret_cast<int*>(smem + (size_t)stages * B_KB_BYTES + 512 + (size_t)QTS * kStage * 4) + (half * QT + ew * 32 + lane);
+            float* stage_s = reinterpret_cast<float*>(smem + ring_bytes + 512) + (half * QT + ew * 32 + lane);
+            int* stage_r = reinterpret_cast<int*>(smem + ring_bytes + 512 + (size_t)QTS * kStage * 4) + (half * QT + ew * 32 + lane);
             int staged = 0;
             auto flush = [&]() {
                 const int at = atomicAdd(cand_cnt + q, staged);
@@ -691,7 +778,7 @@ scan_mma_bf16_kernel(const __grid_constant__ CUtensorMap tmS,
                     }
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+                    if (lane == 0) release_acc(acc);
                     publish(it % ms, m);
                     if (it == boot_T - 1) {
                         // The maxima of this warp's 32 queries are out.  Arrive on the (query tile, epilogue warp)
@@ -727,15 +814,17 @@ scan_mma_bf16_kernel(const __grid_constant__ CUtensorMap tmS,
                 const float g_keep = (g == VQ_NEG_INF) ? g : nextafterf(g, VQ_NEG_INF);
                 float thr = LIST ? fmaxf(ls[0], g_keep) : g_keep;
                 float thr_c = thr - eps2;
+                if (ew == 0) TR(it, 8 + 4 * half);
                 mbar_wait(&tmem_full[acc], acc_phase);
                 tc_fence_after();
+                if (ew == 0) TR(it, 9 + 4 * half);
                 uint32_t va[32], vb[32];
                 float tmax = VQ_NEG_INF;
                 constexpr int cpw = n_chunks / (kEpi / 4);           // chunks of 32 columns this warp filters per tile
                 const int c_lo = half * cpw;
-                tmem_ld32_issue(lane_base + (uint32_t)(acc * NT + c_lo * 32), va);
+                if (!(dbg & 4)) tmem_ld32_issue(lane_base + (uint32_t)(acc * NT + c_lo * 32), va);
 #pragma unroll 1
-                for (int c = 0; c < cpw; c += 2) {
+                for (int c = (dbg & 4) ? cpw : 0; c < cpw; c += 2) {
                     tmem_ld_wait(va);
                     if (c + 1 < cpw) tmem_ld32_issue(lane_base + (uint32_t)(acc * NT + (c_lo + c + 1) * 32), vb);
                     tmax = fmaxf(tmax, filter_collect<KL, LIST>(va, row0 + (c_lo + c) * 32, valid - (c_lo + c) * 32, g_keep, eps2, thr, thr_c, ls, lr, stage_s, stage_r, QTS, staged, flush));
@@ -747,10 +836,11 @@ scan_mma_bf16_kernel(const __grid_constant__ CUtensorMap tmS,
                 }
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+                if (ew == 0) TR(it, 10 + 4 * half);
+                if (lane == 0) release_acc(acc);
                 // first pass over a full tile: its maximum feeds the cooperative bound (a partial tile's maximum would
                 // include the zero scores of the padding rows; re-scanned tiles were counted in their first pass)
-                if (it < n_local && valid == NT) publish(it % ms, tmax);
+                if (it < n_local && valid == NT && !(dbg & 8)) publish(it % ms, tmax);
             }
             if (staged) flush();
             __syncwarp();
@@ -774,7 +864,7 @@ scan_mma_bf16_kernel(const __grid_constant__ CUtensorMap tmS,
                 }
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+                if (lane == 0) release_acc(acc);
                 cand_s[(size_t)tile * b_pad + q] = m;
             }
         } else {
@@ -821,7 +911,7 @@ scan_mma_bf16_kernel(const __grid_constant__ CUtensorMap tmS,
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+            if (lane == 0) release_acc(acc);
             if (ls[0] > published) {                      // list full and improved: share the new k-th best
                 published = ls[0];
                 atomic_max_float(gtau + q, published);
@@ -850,9 +940,19 @@ scan_mma_bf16_kernel(const __grid_constant__ CUtensorMap tmS,
     }
     tc_fence_before();
     if (cl > 1) cluster_sync_all(); else __syncthreads();     // no CTA leaves while its peer may still write into it
+#ifdef VQ_SCAN_TRACE
+    if (threadIdx.x == 0 && blockIdx.x == 0 && n_iter > 204) {
+        for (int t = 0; t < 4; ++t) {
+            printf("[scan trace] tile %d:", 200 + t);
+            for (int i = 0; i < 15; ++i) printf(" %d:%lld", i, g_tr[t * 16 + i] ? g_tr[t * 16 + i] - g_tr[1] : 0);
+            printf("\n");
+        }
+    }
+#endif
     if (warp == 2) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS) : "memory");
+        if (CG2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS) : "memory");
+        else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS) : "memory");
     }
 }
 
@@ -1028,11 +1128,13 @@ MmaPlan plan(int64_t n, int ld, int b, int k) {
     p.grid = p.groups * p.n_qt;
     const size_t stage_bytes = (size_t)(p.nt ? p.nt : 128) * 128;
     int st = (int)((200 * 1024) / stage_bytes);
-    // Release granularity of the ring: 4 slots per tcgen05.commit.  Finer release (1 or 2 slots, i.e. up
-    // to 11 loads in flight) was measured and does not speed up the memory-bound single-query-tile case
-    // (0.1945 / 0.1925 / 0.1905 ms at 1 / 2 / 4 slots, batch 32), and costs 9 % at batch 1024.
+    // The ring is filled, consumed and released in groups of up to 4 k-blocks (one barrier wait and one commit per group,
+    // see the kernel); the group size must divide the k-blocks of a tile.
     static const int grp_env = getenv("VQ_MMA_GROUP") ? atoi(getenv("VQ_MMA_GROUP")) : -1;
-    p.grp_log2 = grp_env >= 0 ? grp_env : 2;
+    p.grp_log2 = grp_env >= 0 && grp_env <= 2 ? grp_env : 2;
+    while (p.grp_log2 > 0 && p.nkb % (1 << p.grp_log2) != 0) --p.grp_log2;
+    static const int st_env = getenv("VQ_MMA_STAGES") ? atoi(getenv("VQ_MMA_STAGES")) : 0;      // experiments: a shallower ring
+    if (st_env > 0 && st_env < st) st = st_env;
     p.stages = (st > 12 ? 12 : st) >> p.grp_log2 << p.grp_log2;
     // an even number of query tiles: two CTAs with neighbouring query tiles form a cluster and share every
     // store tile (each loads half a box and multicasts it), halving the L2 -> SM traffic per FLOP
@@ -1092,10 +1194,10 @@ MmaWs carve(const MmaPlan& p, void* ws_v) {
     return w;
 }
 
-template <int KL, int NT, int MODE, int EPI = epi_warps(KL, MODE)>
+template <int KL, int NT, int MODE, int EPI = epi_warps(KL, MODE), bool CG2 = false>
 cudaError_t launch_mma(const MmaPlan& p, const CUtensorMap& tmS, const __nv_bfloat16* qbf, const MmaWs& w, int n, int ld, int k,
                        int dbg, cudaStream_t stream) {
-    auto kern = scan_mma_bf16_kernel<KL, NT, MODE, EPI>;
+    auto kern = scan_mma_bf16_kernel<KL, NT, MODE, EPI, CG2>;
     constexpr bool BOOT = MODE == kModeBoot;
     static std::atomic<unsigned long long> attr_done{0};   // per instantiation, one bit per device
     if (vq_first_use_on_device(&attr_done)) {
@@ -1106,7 +1208,7 @@ cudaError_t launch_mma(const MmaPlan& p, const CUtensorMap& tmS, const __nv_bflo
     const int grid = BOOT ? p.boot_groups * p.n_qt : p.grid;
     const int cl = (MODE == kModeList || MODE == kModeExact) ? p.cl : 1;
     return vq_launch_cluster(BOOT ? 1 : 3, cl, kern, dim3(grid), dim3(kThreadsFor(EPI)), p.smem, stream, tmS, qbf, w.gtau, n, ld, p.nkb, p.n_qt,
-                             k, p.stages, p.grp_log2, cl, BOOT ? p.boot_mul : 1, p.b_pad, BOOT ? w.boot_max : w.cand_s, w.cand_r, w.cnt, p.cap, dbg,
+                             k, CG2 ? 2 * p.stages : p.stages, (CG2 && p.nkb % (2 << p.grp_log2) == 0) ? p.grp_log2 + 1 : p.grp_log2, cl, BOOT ? p.boot_mul : 1, p.b_pad, BOOT ? w.boot_max : w.cand_s, w.cand_r, w.cnt, p.cap, dbg,
                              (const float*)w.qeps, w.xs);
 }
 
@@ -1151,6 +1253,15 @@ int run_scan(const MmaPlan& p, const void* store, int64_t n, int ld, const __nv_
             // is 1-5 us slower with them, b >= 256 8-12 % faster)
             static const int epi_env = getenv("VQ_EXACT_EPI") ? atoi(getenv("VQ_EXACT_EPI")) : 0;
             const bool epi4 = epi_env ? epi_env == 4 : b <= 128;
+            // CTA pairs issue cta_group::2 MMAs (one store tile per 256 queries through the L2 -> SM fabric) wherever two query
+            // tiles share a cluster and the 8-warp epilogue keeps up; VQ_MMA_CG2=0 falls back to multicast + 1-CTA MMAs
+            static const int cg2_env = getenv("VQ_MMA_CG2") ? atoi(getenv("VQ_MMA_CG2")) : 1;
+            const bool cg2 = cg2_env && p.cl == 2 && !epi4 && k <= 32;
+            if (cg2)
+                e = k == 10 ? launch_mma<10, 128, kModeExact, 8, true>(p, tmM, qbf, w, (int)n, ld, k, dbg, stream)
+                  : k <= 16 ? launch_mma<16, 128, kModeExact, 8, true>(p, tmM, qbf, w, (int)n, ld, k, dbg, stream)
+                            : launch_mma<32, 128, kModeExact, 8, true>(p, tmM, qbf, w, (int)n, ld, k, dbg, stream);
+            else
             e = k == 10 ? (epi4 ? launch_mma<10, 128, kModeExact, 4>(p, tmM, qbf, w, (int)n, ld, k, dbg, stream)
                                 : launch_mma<10, 128, kModeExact>(p, tmM, qbf, w, (int)n, ld, k, dbg, stream))      // the contract's k: no sentinel slots to bubble through
               : k <= 16 ? launch_mma<16, 128, kModeExact>(p, tmM, qbf, w, (int)n, ld, k, dbg, stream)
