@@ -187,6 +187,20 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32
           "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
         : "memory");
 }
+// fire-and-forget maximum (no value returned: the warp never waits for the L2 round trip)
+__device__ __forceinline__ void red_max_float(float* addr, float v) {
+    if (v >= 0.f) asm volatile("red.relaxed.gpu.global.max.s32 [%0], %1;" ::"l"(addr), "r"(__float_as_int(v)) : "memory");
+    else asm volatile("red.relaxed.gpu.global.min.u32 [%0], %1;" ::"l"(addr), "r"(__float_as_uint(v)) : "memory");
+}
+// Bound of the NEXT tile, loaded a whole tile ahead.  `after` is a value the caller has just computed from the previous bound:
+// naming it as an operand keeps the load behind the last use of the register the result is carried in — with a plain volatile
+// load ptxas hoisted the load, had to copy the result into the loop-carried register right away, and every tile stalled
+// on the L2 round trip it was meant to hide (~430 cycles).
+__device__ __forceinline__ float ld_bound_after(const float* p, float after) {
+    float v;
+    asm volatile("ld.relaxed.gpu.global.f32 %0, [%1];" : "=f"(v) : "l"(p), "f"(after) : "memory");
+    return v;
+}
 __device__ __forceinline__ void atomic_max_float(float* addr, float v) {
     if (v >= 0.f) atomicMax(reinterpret_cast<int*>(addr), __float_as_int(v));
     else atomicMin(reinterpret_cast<unsigned*>(addr), __float_as_uint(v));
@@ -545,12 +559,9 @@ scan_mma_bf16_kernel(const __grid_constant__ CUtensorMap tmS,
             const int nth = it >> 1;                   // this issuer's nth tile
             if (mine) {
                 TR(it, 0);
-                mbar_wait(&tmem_empty[acc], (uint32_t)(nth & 1) ^ 1);
-                TR(it, 1);
-                // The tile before this one is in the pipe.  This wait also comes BEFORE the ring waits for a reason: an
-                // issuer skips the other one's tiles, and a parity wait two phases ahead of its barrier passes at once.
+                // The tile before this one is in the pipe.  This wait comes BEFORE the ring waits for a reason: an issuer
+                // skips the other one's tiles, and a parity wait two phases ahead of its barrier passes at once.
                 if (it > 0) mbar_wait(&turn[role], (uint32_t)((role == 1 ? nth : nth - 1) & 1));
-                tc_fence_after();
                 TR(it, 2);
             }
             const uint32_t d_tmem = tmem_base + (uint32_t)acc * NT;
@@ -559,7 +570,11 @@ scan_mma_bf16_kernel(const __grid_constant__ CUtensorMap tmS,
                 if (mine) {
                     mbar_wait(&full[grp], phase);
                     if (CG2) mbar_wait(&full[stages / 2 + grp], phase);      // pfull: the peer's half (see the relay warp)
+                    // the accumulator last: the epilogue's release -> first MMA of this tile is the chain that has to fit
+                    // into the other tile's MMAs
+                    if (kb0 == 0) mbar_wait(&tmem_empty[acc], (uint32_t)(nth & 1) ^ 1);
                     tc_fence_after();
+                    if (kb0 == 0) TR(it, 1);
                     TR(it, kb0 == 0 ? 3 : 5);
                     if (elect_one()) {
                         if (!(dbg & 1)) {
@@ -754,8 +769,9 @@ scan_mma_bf16_kernel(const __grid_constant__ CUtensorMap tmS,
             auto publish = [&](int sub, float m) {
 #pragma unroll
                 for (int j = 0; j < kMaxSub; ++j)
-                    if (j == sub && m > smax[j]) { smax[j] = m; atomic_max_float(my_cmax + j, m); }   // (two column halves share a slot)
+                    if (j == sub && m > smax[j]) { smax[j] = m; red_max_float(my_cmax + j, m); }   // (two column halves share a slot)
             };
+            int sub_it = 0;                                                   // it % ms, kept incrementally
             float g_next = *reinterpret_cast<volatile float*>(gtau + q);      // static / bootstrap bound, then the refreshed one
             for (int it = 0; it < n_iter; ++it) {
                 const int acc = it & 1;
@@ -779,7 +795,8 @@ scan_mma_bf16_kernel(const __grid_constant__ CUtensorMap tmS,
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) release_acc(acc);
-                    publish(it % ms, m);
+                    publish(sub_it, m);
+                    if (++sub_it == ms) sub_it = 0;
                     if (it == boot_T - 1) {
                         // The maxima of this warp's 32 queries are out.  Arrive on the (query tile, epilogue warp)
                         // counter and wait — bounded — for the same warp of every other CTA: the k-th largest of what
@@ -810,8 +827,8 @@ scan_mma_bf16_kernel(const __grid_constant__ CUtensorMap tmS,
                     continue;
                 }
                 const float g = g_next;                                        // loaded one tile ago: no L2 round trip here
-                g_next = *reinterpret_cast<volatile float*>(gtau + q);
                 const float g_keep = (g == VQ_NEG_INF) ? g : nextafterf(g, VQ_NEG_INF);
+                g_next = ld_bound_after(gtau + q, g_keep);
                 float thr = LIST ? fmaxf(ls[0], g_keep) : g_keep;
                 float thr_c = thr - eps2;
                 if (ew == 0) TR(it, 8 + 4 * half);
@@ -822,6 +839,22 @@ scan_mma_bf16_kernel(const __grid_constant__ CUtensorMap tmS,
                 float tmax = VQ_NEG_INF;
                 constexpr int cpw = n_chunks / (kEpi / 4);           // chunks of 32 columns this warp filters per tile
                 const int c_lo = half * cpw;
+                if (cpw <= 2) {
+                    // the warp's whole share of the tile fits the two register buffers: copy it out and hand the accumulator
+                    // back to the issuers BEFORE filtering (the release -> next MMA chain was on the critical path)
+                    tmem_ld32_issue(lane_base + (uint32_t)(acc * NT + c_lo * 32), va);
+                    if (cpw == 2) tmem_ld32_issue(lane_base + (uint32_t)(acc * NT + (c_lo + 1) * 32), vb);
+                    tmem_ld_wait(va);
+                    if (cpw == 2) tmem_ld_wait(vb);
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) release_acc(acc);
+                    if (!(dbg & 4)) {
+                        tmax = filter_collect<KL, LIST>(va, row0 + c_lo * 32, valid - c_lo * 32, g_keep, eps2, thr, thr_c, ls, lr, stage_s, stage_r, QTS, staged, flush);
+                        if (cpw == 2)
+                            tmax = fmaxf(tmax, filter_collect<KL, LIST>(vb, row0 + (c_lo + 1) * 32, valid - (c_lo + 1) * 32, g_keep, eps2, thr, thr_c, ls, lr, stage_s, stage_r, QTS, staged, flush));
+                    }
+                } else {
                 if (!(dbg & 4)) tmem_ld32_issue(lane_base + (uint32_t)(acc * NT + c_lo * 32), va);
 #pragma unroll 1
                 for (int c = (dbg & 4) ? cpw : 0; c < cpw; c += 2) {
@@ -836,11 +869,13 @@ scan_mma_bf16_kernel(const __grid_constant__ CUtensorMap tmS,
                 }
                 tc_fence_before();
                 __syncwarp();
-                if (ew == 0) TR(it, 10 + 4 * half);
                 if (lane == 0) release_acc(acc);
+                }
+                if (ew == 0) TR(it, 10 + 4 * half);
                 // first pass over a full tile: its maximum feeds the cooperative bound (a partial tile's maximum would
                 // include the zero scores of the padding rows; re-scanned tiles were counted in their first pass)
-                if (it < n_local && valid == NT && !(dbg & 8)) publish(it % ms, tmax);
+                if (it < n_local && valid == NT && !(dbg & 8)) publish(sub_it, tmax);
+                if (it < n_local && ++sub_it == ms) sub_it = 0;
             }
             if (staged) flush();
             __syncwarp();
