@@ -24,6 +24,9 @@ constexpr int kWarps = kThreads / 32;
 constexpr int kXMaxLarge = 2048;         // rows re-scored per query at most (k_sel > 64: the large-k route)
 constexpr int kXMaxSmall = 1024;         // ... for k <= 64 (measured: <= 140 on clustered 1M-row stores): 12 KB less shared memory, 4 instead of 3 CTAs per SM
 constexpr int kSelStop = 64;             // the bisection stops once this few keys (>= k_sel) are left
+constexpr int kSortCapSmem = 1024;       // bf16-score keys kept in shared memory; a query that gathered more reads the rest from
+                                         // its gather buffer (L2): 22 KB per CTA = 8 CTAs per SM, a batch of 1024 in ONE wave
+                                         // (with all `cap` = 4096 keys in shared memory: 46 KB, 4 CTAs per SM, two waves)
 
 // exact fp32 scores of rows[0..cnt) -> 64-bit (exact score key, row) keys; one warp per row, 4 rows of a
 // warp in flight so that their HBM latencies overlap
@@ -79,6 +82,10 @@ exact_finish_kernel(const float* __restrict__ cand_s, const int* __restrict__ ca
 
     const int total = cand_cnt[q];
     const int n = total < cap ? total : cap;
+    const size_t cbase = (size_t)q * cap;
+    auto key_at = [&](int i) -> unsigned long long {
+        return i < sort_cap ? keys[i] : (((unsigned long long)vq_score_key(cand_s[cbase + i]) << 32) | (unsigned)cand_r[cbase + i]);
+    };
     if (tid == 0) { key_min = 0xffffffffu; key_max = 0u; x_cnt = 0; lb_key = 0xffffffffu; }
     __syncthreads();
     // ---- load (the last warp meanwhile normalises the query in fp32, same arithmetic as ingest_rows_kernel)
@@ -98,7 +105,7 @@ exact_finish_kernel(const float* __restrict__ cand_s, const int* __restrict__ ca
         unsigned mn = 0xffffffffu, mx = 0u;
         for (int i = tid; i < n; i += kThreads) {
             const unsigned kh = vq_score_key(cand_s[base + i]);
-            keys[i] = ((unsigned long long)kh << 32) | (unsigned)cand_r[base + i];
+            if (i < sort_cap) keys[i] = ((unsigned long long)kh << 32) | (unsigned)cand_r[base + i];
             mn = kh < mn ? kh : mn;
             mx = kh > mx ? kh : mx;
         }
@@ -121,7 +128,7 @@ exact_finish_kernel(const float* __restrict__ cand_s, const int* __restrict__ ca
         while (lo < hi && cnt_hi > stop) {
             const unsigned mid = lo + ((hi - lo) >> 1);
             int c = 0;
-            for (int i = tid; i < n; i += kThreads) c += ((unsigned)(keys[i] >> 32) <= mid) ? 1 : 0;
+            for (int i = tid; i < n; i += kThreads) c += ((unsigned)(key_at(i) >> 32) <= mid) ? 1 : 0;
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
             if (lane == 0) part[it & 1][warp] = c;
@@ -134,7 +141,7 @@ exact_finish_kernel(const float* __restrict__ cand_s, const int* __restrict__ ca
         }
     }
     for (int i = tid; i < n; i += kThreads) {
-        const unsigned long long key = keys[i];
+        const unsigned long long key = key_at(i);
         if ((unsigned)(key >> 32) <= hi) {
             const int at = atomicAdd(&x_cnt, 1);
             if (at < kXMax) xrow[at] = (int)(unsigned)key;
@@ -160,7 +167,7 @@ exact_finish_kernel(const float* __restrict__ cand_s, const int* __restrict__ ca
     if (n > n_a && x_cnt_a <= kXMax) {
         const unsigned t_key = lb_key == 0xffffffffu ? 0xffffffffu : vq_score_key(vq_key_score(lb_key) - qeps[q]);
         for (int i = tid; i < n; i += kThreads) {
-            const unsigned long long key = keys[i];
+            const unsigned long long key = key_at(i);
             const unsigned kh = (unsigned)(key >> 32);
             if (kh > hi && kh <= t_key) {
                 const int at = atomicAdd(&x_cnt, 1);
@@ -205,7 +212,7 @@ int vq_exact_finish_launch(const float* cand_s, const int* cand_r, const int* ca
         vq_set_error("exact_finish: need k_out <= k_sel <= %d (k_sel=%d k_out=%d)", kXMax / 2, k_sel, k_out);
         return VQ_EUNSUPPORTED;
     }
-    const int sort_cap = cap;
+    const int sort_cap = cap < kSortCapSmem ? cap : kSortCapSmem;
     const size_t smem = (size_t)sort_cap * 8 + (size_t)kXMax * 12 + (size_t)ld * 4 + 64;
     if (smem > 200 * 1024) {
         vq_set_error("exact_finish: %d candidate slots per query do not fit shared memory", cap);

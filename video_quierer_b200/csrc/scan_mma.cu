@@ -357,7 +357,8 @@ __device__ __forceinline__ float filter_collect(const uint32_t (&v)[32], int row
 //                                 — every entry is the score of a row no other entry covers, so the k-th largest
 //                                 entry of a query's row is a lower bound of its k-th best score over the store
 //   arrived [n_qt][4]             CTAs of a query tile whose epilogue warp w has published the maxima of its first boot_T tiles
-struct XShared { float* cmax; int* arrived; int ms; int boot_T; int refresh_ns; };   // refresh_ns: first sleep of the refresher (0 = no periodic refresh)
+struct XShared { float* cmax; int* arrived; int ms; int boot_T; int refresh_ns;      // refresh_ns: first sleep of the refresher (0 = no periodic refresh)
+                 const float* boot_max; int boot_ext_T; };                        // sample-pass maxima [b_pad][boot_ext_T] the scan selects its first bound from (0: gtau holds it)
 constexpr int kMaxSub = 8;              // sub-streams per CTA at most
 
 // Lower bounds of the k-th largest of the V published maxima of 8 queries at once (warp-cooperative; all lanes
@@ -772,7 +773,28 @@ scan_mma_bf16_kernel(const __grid_constant__ CUtensorMap tmS,
                     if (j == sub && m > smax[j]) { smax[j] = m; red_max_float(my_cmax + j, m); }   // (two column halves share a slot)
             };
             int sub_it = 0;                                                   // it % ms, kept incrementally
-            float g_next = *reinterpret_cast<volatile float*>(gtau + q);      // static / bootstrap bound, then the refreshed one
+            float g_next = *reinterpret_cast<volatile float*>(gtau + q);      // static bound (+inf: padding query), then the refreshed one
+            // First bound = the k-th largest of the sample pass's tile maxima of the query (k distinct rows reach it).  Selected
+            // HERE, while the first tiles are being loaded and multiplied, instead of by a kernel of its own between the sample
+            // pass and the scan: sample pass -> select -> scan was the serial chain a step could not overlap with its
+            // neighbours (12 us of ~155 on a 125k-row shard).  The halves of a quarter split its four batches of 8 queries.
+            float g0 = VQ_NEG_INF;
+            if (xs.boot_ext_T > 0) {
+                const unsigned real = __ballot_sync(0xffffffffu, g_next != INFINITY);      // bit j: lane j's query is not padding
+                const float* bm = xs.boot_max + (size_t)(q_tile * QT) * xs.boot_ext_T;
+                const int bq_lo = kEpi == 8 ? 2 * half : 0, bq_hi = kEpi == 8 ? 2 * half + 2 : 4;
+                for (int bq = bq_lo; bq < bq_hi; ++bq) {
+                    if (((real >> (8 * bq)) & 0xffu) == 0) continue;
+                    float kth[8];
+                    kth_largest_batch8(bm, xs.boot_ext_T, k, lane, (8 * bq) * 4 + ew, 4, kth);
+                    float mine = kth[0];
+#pragma unroll
+                    for (int u = 1; u < 8; ++u) mine = (lane == u) ? kth[u] : mine;
+                    if (lane < 8) sbound[(8 * bq + lane) * 4 + ew] = mine;
+                }
+                asm volatile("bar.sync 1, %0;" ::"r"(kEpi * 32) : "memory");           // the epilogue warps only
+                if (g_next != INFINITY) g0 = sbound[lane * 4 + ew];
+            }
             for (int it = 0; it < n_iter; ++it) {
                 const int acc = it & 1;
                 const uint32_t acc_phase = (it >> 1) & 1;
@@ -826,7 +848,7 @@ scan_mma_bf16_kernel(const __grid_constant__ CUtensorMap tmS,
                     }
                     continue;
                 }
-                const float g = g_next;                                        // loaded one tile ago: no L2 round trip here
+                const float g = fmaxf(g_next, g0);                             // loaded one tile ago: no L2 round trip here
                 const float g_keep = (g == VQ_NEG_INF) ? g : nextafterf(g, VQ_NEG_INF);
                 g_next = ld_bound_after(gtau + q, g_keep);
                 float thr = LIST ? fmaxf(ls[0], g_keep) : g_keep;
@@ -900,7 +922,8 @@ scan_mma_bf16_kernel(const __grid_constant__ CUtensorMap tmS,
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) release_acc(acc);
-                cand_s[(size_t)tile * b_pad + q] = m;
+                // (cap > 0: query-major [b_pad][cap] — the layout the exact scan selects its first bound from)
+                if (cap > 0) cand_s[(size_t)q * cap + tile] = m; else cand_s[(size_t)tile * b_pad + q] = m;
             }
         } else {
         // top-k list of this thread's query, in registers, WORST first: slots [0,k) are live and
@@ -1142,6 +1165,7 @@ inline size_t align256(size_t v) { return (v + 255) / 256 * 256; }
 struct MmaPlan {
     int nkb, nt, n_qt, b_pad, groups, grid, stages, grp_log2, cl;
     int boot_tiles, boot_groups, boot_mul;       // threshold bootstrap (0 = off); sample tile j = store tile j * boot_mul
+    int boot_qmajor = 0;                         // sample maxima stored [b_pad][boot_tiles] and selected by the scan itself (exact mode)
     int cap;                                     // candidate slots per query (= groups * k, cannot overflow)
     size_t smem;
     // workspace layout
@@ -1217,7 +1241,7 @@ MmaWs carve(const MmaPlan& p, void* ws_v) {
     unsigned char* ws = (unsigned char*)ws_v;
     MmaWs w;
     w.qeps = nullptr;
-    w.xs = XShared{nullptr, nullptr, 1, 0, 0};
+    w.xs = XShared{nullptr, nullptr, 1, 0, 0, nullptr, 0};
     w.gtau = (float*)(ws + p.off_tau);
     w.cnt = (int*)(ws + p.off_cnt);
     w.cand_s = (float*)(ws + p.off_cand_s);
@@ -1225,7 +1249,7 @@ MmaWs carve(const MmaPlan& p, void* ws_v) {
     w.boot_max = (float*)(ws + p.off_boot);
     w.qbf = (__nv_bfloat16*)(ws + p.off_qbf);
     w.qeps = nullptr;
-    w.xs = XShared{nullptr, nullptr, 1, 0, 0};
+    w.xs = XShared{nullptr, nullptr, 1, 0, 0, nullptr, 0};
     return w;
 }
 
@@ -1242,8 +1266,18 @@ cudaError_t launch_mma(const MmaPlan& p, const CUtensorMap& tmS, const __nv_bflo
     }
     const int grid = BOOT ? p.boot_groups * p.n_qt : p.grid;
     const int cl = (MODE == kModeList || MODE == kModeExact) ? p.cl : 1;
-    return vq_launch_cluster(BOOT ? 1 : 3, cl, kern, dim3(grid), dim3(kThreadsFor(EPI)), p.smem, stream, tmS, qbf, w.gtau, n, ld, p.nkb, p.n_qt,
-                             k, CG2 ? 2 * p.stages : p.stages, (CG2 && p.nkb % (2 << p.grp_log2) == 0) ? p.grp_log2 + 1 : p.grp_log2, cl, BOOT ? p.boot_mul : 1, p.b_pad, BOOT ? w.boot_max : w.cand_s, w.cand_r, w.cnt, p.cap, dbg,
+    // The sample pass runs a handful of tiles per CTA: two ring groups are enough, and with ~130 KB of shared memory instead of
+    // 215 KB its CTAs share their SMs with the exact_finish CTAs of the step before (the two kernels become runnable at the
+    // same moment — when the scan between them retires — and used to run one after the other).
+    static const int boot_ring_env = getenv("VQ_BOOT_RING") ? atoi(getenv("VQ_BOOT_RING")) : 2;
+    int stages = CG2 ? 2 * p.stages : p.stages;
+    size_t smem = p.smem;
+    if (BOOT && boot_ring_env > 0 && (boot_ring_env << p.grp_log2) < p.stages) {
+        stages = boot_ring_env << p.grp_log2;
+        smem -= (size_t)(p.stages - stages) * NT * 128;
+    }
+    return vq_launch_cluster(BOOT ? 1 : 3, cl, kern, dim3(grid), dim3(kThreadsFor(EPI)), smem, stream, tmS, qbf, w.gtau, n, ld, p.nkb, p.n_qt,
+                             k, stages, (CG2 && p.nkb % (2 << p.grp_log2) == 0) ? p.grp_log2 + 1 : p.grp_log2, cl, BOOT ? p.boot_mul : 1, p.b_pad, BOOT ? w.boot_max : w.cand_s, w.cand_r, w.cnt, BOOT ? (p.boot_qmajor ? p.boot_tiles : 0) : p.cap, dbg,
                              (const float*)w.qeps, w.xs);
 }
 
@@ -1267,13 +1301,16 @@ int run_scan(const MmaPlan& p, const void* store, int64_t n, int ld, const __nv_
             vq_set_error("launch of scan_mma_bf16_kernel<boot> failed: %s", cudaGetErrorString(e));
             return VQ_ECUDA;
         }
-        e = vq_launch(2, boot_select_kernel, dim3((p.b_pad + 7) / 8), dim3(256), 0, stream, (const float*)w.boot_max, p.boot_tiles,
-                      b, p.b_pad, k, w.gtau);
-        if (e != cudaSuccess) {
-            vq_set_error("launch of boot_select_kernel failed: %s", cudaGetErrorString(e));
-            return VQ_ECUDA;
+        *launches = 2;
+        if (!p.boot_qmajor) {
+            e = vq_launch(2, boot_select_kernel, dim3((p.b_pad + 7) / 8), dim3(256), 0, stream, (const float*)w.boot_max, p.boot_tiles,
+                          b, p.b_pad, k, w.gtau);
+            if (e != cudaSuccess) {
+                vq_set_error("launch of boot_select_kernel failed: %s", cudaGetErrorString(e));
+                return VQ_ECUDA;
+            }
+            *launches = 3;
         }
-        *launches = 3;
     }
     CUtensorMap tmM = tmS;                       // main pass: half-height boxes when two CTAs share a tile
     if (p.cl > 1 && !get_map_bf16(&tmM, store, (uint64_t)n, (uint64_t)ld, (uint32_t)(p.nt / p.cl))) {
@@ -1446,7 +1483,7 @@ int vq_scan_mma_collect(const void* store_bf16, const float* store_f32, int64_t 
     unsigned char* ws = (unsigned char*)ws_v;
     MmaWs w;
     w.qeps = nullptr;
-    w.xs = XShared{nullptr, nullptr, 1, 0, 0};
+    w.xs = XShared{nullptr, nullptr, 1, 0, 0, nullptr, 0};
     w.gtau = (float*)(ws + p.off_tau);
     w.cnt = (int*)(ws + p.off_cnt);
     const size_t cand_bytes = align256((size_t)p.b_pad * cap * 4);
@@ -1565,6 +1602,7 @@ ExactPlan plan_exact(int64_t n, int ld, int b, int k) {
         if (bs > full_tiles / 2) bs = (int)(full_tiles / 2);
         if (bs >= k && cap < n8 && boot_env != 0) {
             p.boot_tiles = bs;
+            p.boot_qmajor = k <= 16 ? 1 : 0;   // (the in-scan selection keeps two values per lane: not enough for a larger k — boot_select_kernel ranks all)
             p.boot_groups = bs < p.groups ? bs : p.groups;
             p.boot_mul = (int)(full_tiles / bs);
             if (p.boot_mul < 1) p.boot_mul = 1;
@@ -1649,7 +1687,8 @@ int vq_scan_mma_exact(const void* store_bf16, const float* store_f32, int64_t n,
     }
     MmaWs w = carve(p, ws_v);
     w.qeps = (float*)((unsigned char*)ws_v + x.off_eps);
-    w.xs = XShared{(float*)((unsigned char*)ws_v + x.off_cmax), (int*)((unsigned char*)ws_v + x.off_arrived), x.ms, x.boot_T, x.refresh_ns};
+    w.xs = XShared{(float*)((unsigned char*)ws_v + x.off_cmax), (int*)((unsigned char*)ws_v + x.off_arrived), x.ms, x.boot_T, x.refresh_ns,
+                   p.boot_qmajor ? (const float*)w.boot_max : nullptr, p.boot_qmajor ? p.boot_tiles : 0};
     if (vq_launch(0, prep_queries_bf16_kernel, dim3((p.b_pad + 7) / 8), dim3(256), 0, stream, queries, b, dim, dim, w.qbf, ld,
                   p.b_pad, query_norm, w.gtau, w.cnt, (const float*)nullptr, bounds, w.qeps, w.xs.cmax, p.groups * w.xs.ms, w.xs.arrived, p.n_qt, 0.f) != cudaSuccess) {
         vq_set_error("launch of prep_queries_bf16_kernel failed: %s", cudaGetErrorString(cudaGetLastError()));
