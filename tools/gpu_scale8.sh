@@ -5,8 +5,7 @@ run() { n=$1; shift; timeout 600 python -m torch.distributed.run --nnodes=1 --np
 run 8 --steps 30 --warmup 3 > gpurun_out/${tag}_scale_n8.json 2> gpurun_out/${tag}_scale_n8.err; echo "n8 rc=$?"
 run 8 --config 5 --steps 5 --warmup 3 --no-sweep > gpurun_out/${tag}_c5_n8.json 2> gpurun_out/${tag}_c5_n8.err; echo "c5 rc=$?"
 run 8 --config 4 --steps 10 --warmup 3 --no-sweep > gpurun_out/${tag}_c4_n8.json 2> gpurun_out/${tag}_c4_n8.err; echo "c4 rc=$?"
-run 4 --steps 30 --warmup 3 --no-sweep > gpurun_out/${tag}_scale_n4b.json 2> gpurun_out/${tag}_scale_n4b.err; echo "n4 rc=$?"
-for f in scale_n8 c5_n8 c4_n8 scale_n4b; do echo "== $f"; tail -1 gpurun_out/${tag}_$f.err | cut -c1-300; python - <<PY
+for f in scale_n8 c5_n8 c4_n8; do echo "== $f"; tail -1 gpurun_out/${tag}_$f.err | cut -c1-300; python - <<PY
 import json
 try:
     d = json.load(open("gpurun_out/${tag}_$f.json"))
