@@ -562,12 +562,13 @@ def run_ours(args):
         # all-gather runs 3x slower per step than the same replays with a shallow queue)
         nccl_inside = world > 1 and lanes[0].searcher._peer is None
         sync_every = int(os.environ.get("VQ_BENCH_SYNC_EVERY", "0")) or (4 if nccl_inside else 1 << 30)
-        # Peer route, N > 1: the host keeps at most `cap` steps (two per lane) enqueued ahead of the GPU.
+        # Peer route, N > 1: the host keeps at most `cap` steps (one per lane) enqueued ahead of the GPU.
         # With the whole run enqueued at once the lanes of different ranks drift apart — rank A ahead on
         # lane 0, rank B ahead on lane 1 — and every exchange then waits for a different straggler (seen on
-        # 8 GPUs: 3.8 M QPS free-running in a run whose host-gated e2e loop reached 4.4 M).  A serving
-        # process bounds its queue the same way.
-        cap = int(os.environ.get("VQ_BENCH_INFLIGHT", "0")) or (2 * depth if (world > 1 and not nccl_inside) else 0)
+        # 8 GPUs: 3.8 M QPS free-running in a run whose host-gated e2e loop reached 4.4 M; same session,
+        # final kernel: 3.85 / 4.39 / 4.47 M QPS at 6 / 4 / 3 steps ahead, 2 GPUs: 2.07 / 2.19 M at 6 / 3 —
+        # tools/inflight8.sh, tools/inflight2.sh).  A serving process bounds its queue the same way.
+        cap = int(os.environ.get("VQ_BENCH_INFLIGHT", "0")) or (depth if (world > 1 and not nccl_inside) else 0)
 
         def timed_steps(n_steps):
             done_evs = []

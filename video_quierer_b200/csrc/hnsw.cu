@@ -197,6 +197,35 @@ __device__ __forceinline__ float row_dot_8lanes(const unsigned char* row, const 
     return acc;
 }
 
+// bf16 rows are half as long: FOUR lanes per row take the same 16 loads per lane, so a warp gathers 8 rows per round trip
+// instead of 4 with the same registers in flight (the search is bound by the number of dependent round trips per hop).
+__device__ __forceinline__ float row_dot_4lanes_bf16(const unsigned char* row, const float* q, int ld, int l4) {
+    const int steps = ld / 32;                   // 16-byte pieces per lane (8 bf16 each, 4 lanes)
+    constexpr int kMLP = 16;
+    float acc = 0.f;
+    for (int j0 = 0; j0 < steps; j0 += kMLP) {
+        uint4 x[kMLP];
+#pragma unroll
+        for (int u = 0; u < kMLP; ++u)
+            if (j0 + u < steps) x[u] = vq_ldg_stream(row + ((size_t)(j0 + u) * 4 + l4) * 16);
+#pragma unroll
+        for (int u = 0; u < kMLP; ++u) {
+            if (j0 + u < steps) {
+                const float* qq = q + ((j0 + u) * 4 + l4) * 8;
+                const float4 q0 = *reinterpret_cast<const float4*>(qq);
+                const float4 q1 = *reinterpret_cast<const float4*>(qq + 4);
+                acc = fmaf(vq_bf16lo(x[u].x), q0.x, acc); acc = fmaf(vq_bf16hi(x[u].x), q0.y, acc);
+                acc = fmaf(vq_bf16lo(x[u].y), q0.z, acc); acc = fmaf(vq_bf16hi(x[u].y), q0.w, acc);
+                acc = fmaf(vq_bf16lo(x[u].z), q1.x, acc); acc = fmaf(vq_bf16hi(x[u].z), q1.y, acc);
+                acc = fmaf(vq_bf16lo(x[u].w), q1.z, acc); acc = fmaf(vq_bf16hi(x[u].w), q1.w, acc);
+            }
+        }
+    }
+    acc += __shfl_xor_sync(kFull, acc, 1);
+    acc += __shfl_xor_sync(kFull, acc, 2);
+    return acc;
+}
+
 template <bool BF16, int S>        // S > 0: result list in registers (ef <= 32*S); S == 0: in shared memory
 __global__ void __launch_bounds__(128)
 hnsw_search_kernel(const void* __restrict__ store_v, int ld,
@@ -322,12 +351,21 @@ hnsw_search_kernel(const void* __restrict__ store_v, int ld,
                 logged = (logged + nnew <= kLogCap) ? logged + nnew : kLogCap + 1;   // > cap => full clear next time
                 if (visited_cnt > cap - cap / 8) overflow = 1;
                 __syncwarp();
-                // gather + distance, 4 rows per step (8 lanes each)
-                for (int i0 = 0; i0 < nnew; i0 += 4) {
-                    const int mine = i0 + grp;
-                    const int node = w.nbr[mine < nnew ? mine : nnew - 1];
-                    const float dot = row_dot_8lanes<BF16>(store + (size_t)node * row_bytes, w.q, ld, l8);
-                    if (l8 == 0 && mine < nnew) w.nd[mine] = 1.0f - dot;
+                // gather + distance: 4 rows per step (8 lanes each); bf16 rows (ld a multiple of 32): 8 rows per step, 4 lanes each
+                if (BF16 && (ld & 31) == 0) {
+                    for (int i0 = 0; i0 < nnew; i0 += 8) {
+                        const int mine = i0 + (lane >> 2);
+                        const int node = w.nbr[mine < nnew ? mine : nnew - 1];
+                        const float dot = row_dot_4lanes_bf16(store + (size_t)node * row_bytes, w.q, ld, lane & 3);
+                        if ((lane & 3) == 0 && mine < nnew) w.nd[mine] = 1.0f - dot;
+                    }
+                } else {
+                    for (int i0 = 0; i0 < nnew; i0 += 4) {
+                        const int mine = i0 + grp;
+                        const int node = w.nbr[mine < nnew ? mine : nnew - 1];
+                        const float dot = row_dot_8lanes<BF16>(store + (size_t)node * row_bytes, w.q, ld, l8);
+                        if (l8 == 0 && mine < nnew) w.nd[mine] = 1.0f - dot;
+                    }
                 }
                 evals += nnew;
                 __syncwarp();
