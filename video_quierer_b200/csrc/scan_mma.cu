@@ -17,20 +17,26 @@
 //
 // TMEM (512 columns): [0, 2*NT) two fp32 accumulators (MMA of tile i+1 overlaps the epilogue of
 // tile i), [2*NT, 2*NT + ld/2) the resident query tile.
-// Warp roles (256 threads, 1 CTA / SM):
-//   warp 0   TMA producer  : store tiles k-block by k-block through a `stages`-deep mbarrier ring
-//   warp 1   MMA issuer    : one thread, 4 x tcgen05.mma (K = 16) per k-block, tcgen05.commit
-//                            frees the smem slot / publishes the accumulator
-//   warp 2   TMEM allocator
-//   warps 4-7 epilogue     : load the query tile into TMEM, then per tile tcgen05.ld 32x32b.x32,
-//                            branch-free threshold filter, register insertion
+// Warp roles (256 or 384 threads, 1 CTA / SM):
+//   warp 0    TMA producer : store tiles through a ring that is filled, consumed and released in GROUPS of
+//                            k-blocks (64 KB at dim 512): one expect_tx + the group's loads per group
+//   warps 1,2 MMA issuers  : own alternate tiles (issuer r: accumulator r); per group ONE barrier wait,
+//                            4 * gs back-to-back tcgen05.mma (K = 16) and one tcgen05.commit; a `turn`
+//                            barrier keeps the tiles in issue order (tile t completes while t+1 runs)
+//   warp 2    also the TMEM allocator; warp 3: bound refresher (exact mode)
+//   warps 4-7 (4-11 in the exact mode above 128 queries) epilogue: load the query tile into TMEM, then per
+//                            tile tcgen05.ld 32x32b.x32, accumulator release, threshold filter, insertion
 // Grid: persistent, gridDim = groups * n_qt; CTA c serves query tile c % n_qt and the store tiles
-// c / n_qt, + groups, ... ; it writes one k-entry list per query, `topk_merge` reduces them.
+// c / n_qt, + groups, ... .
+// CTA pairs (exact mode, even number of query tiles; template flag CG2): the two CTAs of a cluster hold
+// neighbouring query tiles and issue ONE tcgen05.mma.cta_group::2 (M = 256) per step — each keeps its own
+// queries in its TMEM and HALF of every store tile in its shared memory (see the helpers below).
 //
-// Measured design rules (tools/mmabench.cu, B200): a lone tcgen05.mma M128 N128 K16 retires every
-// 64 cycles, but every tcgen05.commit drains the tensor pipe (~160 cycles): one commit per 4 MMAs
-// gives 105-120 cycles/MMA.  Ring slots are therefore released in GROUPS of 2^grp_log2 k-blocks (one
-// commit per 16 MMAs) while TMA completion stays per k-block.
+// Measured design rules (tools/mmabench.cu, tools/issue_rate.sh, tools/scan_trace.sh; B200): a lone
+// tcgen05.mma M128 N128 K16 retires every 64 cycles.  A barrier wait + fence + election + commit per
+// k-block made the ISSUE LOOP the bound (~100 cycles per MMA even with loads and MMAs switched off);
+// with one wait and one commit per group and the hand-offs described in the kernel the traced steady
+// state is one 128 x 128 x 512 tile per 2045 cycles = 64.0 cycles per MMA.
 //
 // Threshold bootstrap: the per-query insertion cost is ~k*(1+ln(rows per CTA / k)) serial list
 // insertions per CTA.  For large stores a BOOT pass of the same kernel first scores a sample of
