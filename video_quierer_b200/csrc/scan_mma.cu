@@ -67,7 +67,7 @@ constexpr int TMEM_COLS = 512;          // whole tensor memory: 2 accumulators +
 // Epilogue warps: 4 (one per quarter of the 128 TMEM lanes) or, in the exact mode with lists of <= 32 entries, 8 — warps w and
 // w + 4 serve the same 32 queries and split the columns (store rows) of every tile, halving the per-tile critical path of the
 // epilogue, which is as long as the tile's MMAs as soon as the gather slow path runs (12 warps x 168 registers still fit).
-constexpr int epi_warps(int kl, int mode) { return (mode == 3 && kl <= 32) ? 8 : 4; }
+[[maybe_unused]] constexpr int epi_warps(int kl, int mode) { return (mode == 3 && kl <= 32) ? 8 : 4; }
 constexpr int kThreadsFor(int epi) { return (4 + epi) * 32; }
 constexpr int kMaxK = 64;
 constexpr int kModeList = 0, kModeBoot = 1, kModeCollect = 2, kModeExact = 3;   // epilogue of scan_mma_bf16_kernel
