@@ -61,3 +61,22 @@ def test_reference_arm_uses_the_vendored_reference_when_present():
     src = "/root/reference/video_search_overhaul.py"
     if os.path.exists(src):
         assert open(src, "rb").read() == open(os.path.join(ref_dir, "video_search_overhaul.py"), "rb").read()
+
+
+def test_traffic_table_keys_match_the_capture_names():
+    """profiles/r02_traffic.json (what bench.py reports as roofline.traffic) is keyed by tools/ncu_summarise.py from the
+    capture file names: the keys bench.py looks up must be the ones the summariser writes, and the committed table must
+    carry the shapes the driver's runs use (1M rows at N = 1, its 2- / 4- / 8-way shards)."""
+    import json
+    spec2 = importlib.util.spec_from_file_location("ncu_summarise", os.path.join(ROOT, "tools", "ncu_summarise.py"))
+    summ = importlib.util.module_from_spec(spec2)
+    spec2.loader.exec_module(summ)
+    assert summ.traffic_key("r02b_scan_exact_b1024_clip") == ("scan_mma_bf16_kernel", "rows1000000_b1024_clip")
+    assert summ.traffic_key("r02b_scan_exact_b1024_gauss") == ("scan_mma_bf16_kernel", "rows1000000_b1024_gauss")
+    assert summ.traffic_key("r02b_scan_exact_b32_clip") == ("scan_mma_bf16_kernel", "rows1000000_ble128_clip")
+    assert summ.traffic_key("r02b_scan_exact_b1024_shard125k") == ("scan_mma_bf16_kernel", "rows125000_b1024_clip")
+    assert summ.traffic_key("r02b_exact_finish_b1024_clip") == ("exact_finish_kernel", "rows1000000_b1024_clip")
+    tab = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))["scan_mma_bf16_kernel"]
+    for rows in (1_000_000, 500_000, 250_000, 125_000):
+        t = tab["rows%d_b1024_clip" % rows]
+        assert 1.0 <= t / (rows * 512 * 2) < 1.35           # DRAM traffic of the scan: the algorithmic bytes + gather buffers
