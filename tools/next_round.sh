@@ -1,15 +1,26 @@
 # First measurements of the next round, cheapest first.  Run under gpurun.
 set -x
 T="python -m torch.distributed.run --nnodes=1 --master-addr 127.0.0.1"
-# 1. (8 GPUs) does the two-per-lane queue bound remove the 3.8-5.1 M spread?  three runs each
-for cap in 6 0x; do
-  for i in 1 2 3; do
-    VQ_BENCH_INFLIGHT=${cap/0x/100000} $T --nproc-per-node 8 --master-port 2960$i bench.py --gpus 8 --steps 400 --warmup 5 --no-sweep \
-      > gpurun_out/n8_cap${cap}_$i.json 2> gpurun_out/n8_cap${cap}_$i.err
-  done
+B="--steps 30 --warmup 3 --no-hnsw --no-cpu --no-api --no-sweep"
+# 1. (1 GPU) the N = 8 shard alone: where the 0.157 ms step goes.  Launch list (serialised) + the pipelined step with the
+#    sample pass forced onto fewer tiles (does a smaller sample shorten the sample pass -> scan chain more than it costs in gather?)
+python bench.py $B --rows 125000 > gpurun_out/r125_default.json 2> gpurun_out/r125_default.err
+for sub in 4 8; do VQ_EXACT_SUB=$sub python bench.py $B --rows 125000 > gpurun_out/r125_sub$sub.json 2> gpurun_out/r125_sub$sub.err; done
+# 2. (1 GPU) the pipeline events of the pair kernel on a SHORT scan (54 tiles per CTA): how long until the first tile's
+#    epilogue runs, how long the tail is (tools/scan_trace.sh needs the tracing build)
+VQ_NVCC_EXTRA=-DVQ_SCAN_TRACE python -m video_quierer_b200.build --force && bash tools/scan_trace.sh "0 1" > gpurun_out/trace_1m.log 2>&1
+python -m video_quierer_b200.build --force
+# 3. (2 GPUs, cheap) host queue depth and the exchange: value vs e2e at 1 / 2 / 3 steps ahead
+for cap in 1 2 3; do
+  VQ_BENCH_INFLIGHT=$cap $T --nproc-per-node 2 --master-port 2981$cap bench.py --gpus 2 $B --sustain 0 \
+    > gpurun_out/n2_cap$cap.json 2> gpurun_out/n2_cap$cap.err
 done
-# 2. (1 GPU) the N = 8 shard alone: floor of the step with 3 lanes (scan + bootstrap)
-python bench.py --rows 125000 --steps 400 --warmup 5 --no-hnsw --no-cpu > gpurun_out/r125_n1.json 2> gpurun_out/r125_n1.err
-# 3. (1 GPU) ncu of the CURRENT exchange kernels (line protocol), one simulated rank
-VQ_PEER_TIMEOUT_MS=500 ncu --set full --clock-control none --import-source on -k regex:peer_exchange_merge -s 4 -c 1 -f \
-  -o gpurun_out/r02_peer_exchange_b1024 python tools/peer_probe.py --batch 1024 --k 10 --iters 5 > gpurun_out/ncu_peer2.log 2>&1
+# 4. (8 GPUs) three runs of the contract line: the run-to-run spread at N = 8 was 3.85-4.98 M QPS this round
+for i in 1 2 3; do
+  $T --nproc-per-node 8 --master-port 2960$i bench.py --gpus 8 --steps 30 --warmup 3 --no-sweep --no-hnsw --no-cpu --no-api \
+    > gpurun_out/n8_run$i.json 2> gpurun_out/n8_run$i.err
+done
+# 5. (1 GPU) HNSW: ncu of the search kernel at ef 128 (the bound is per-hop bookkeeping on shared memory)
+python tools/bench_hnsw.py --efs 128 > /dev/null 2>&1 && \
+ncu --set full --clock-control none --import-source on -k regex:hnsw_search_kernel -s 1 -c 1 -f -o gpurun_out/r03_hnsw_ef128 \
+  python tools/bench_hnsw.py --efs 128 > gpurun_out/ncu_hnsw.log 2>&1
