@@ -963,8 +963,10 @@ def main():
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--exchange", default="auto", choices=["auto", "peer", "collective"],
                     help="N > 1: fused NVLink peer-memory push+merge kernel (auto/peer) or NCCL all-gather + merge")
-    ap.add_argument("--pipeline", type=int, default=3,
-                    help="search steps in flight (each on its own stream with its own workspace / exchange windows)")
+    ap.add_argument("--pipeline", type=int, default=0,
+                    help="search steps in flight (each on its own stream with its own workspace / exchange windows); default 4 on "
+                         "one GPU (the end-to-end loop with host buffers: 1.22 / 1.30 / 1.29 M QPS at 3 / 4 / 6, the device-resident "
+                         "loop does not care: tools/pipeline_ab.sh), 3 with an exchange in the step (measured at N = 2 / 4 / 8)")
     ap.add_argument("--sustain", type=float, default=2.0, help="seconds of extra device-resident steps after the contract region (0 = off)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-api", action="store_true", help="skip the e2e_api leg (drop-in facade, dicts out)")
@@ -980,6 +982,8 @@ def main():
                     help="exact: bf16 tensor scan + exact fp32 re-score (default); fp32: FMA scan of the fp32 store")
     ap.add_argument("--rows", type=int, default=0, help="store rows (experiments only: overrides the config's)")
     args = ap.parse_args()
+    if args.pipeline <= 0:
+        args.pipeline = 4 if int(os.environ.get('WORLD_SIZE', '1')) == 1 else 3
     cfg = CONFIGS[args.config]
     g = globals()
     g["N_ROWS"], g["DIM"], g["K_TOP"], g["LABEL"] = args.rows or cfg["rows"], cfg["dim"], cfg["k"], cfg["label"]
