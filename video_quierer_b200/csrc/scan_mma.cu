@@ -438,8 +438,8 @@ scan_mma_bf16_kernel(const __grid_constant__ CUtensorMap tmS,
     uint64_t* a_full = empty + stages;
     uint64_t* tmem_full = a_full + 1;      // [2]
     uint64_t* tmem_empty = tmem_full + 2;  // [2]
-    uint64_t* x_first = tmem_empty + 2;    // [2] turn[r]: the other issuer has issued the tile before issuer r's next one
-    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(x_first + 2);
+    uint64_t* turn = tmem_empty + 2;       // [2] turn[r]: the other issuer has issued the tile before issuer r's next one
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(turn + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int q_tile = blockIdx.x % n_qt, group = blockIdx.x / n_qt, n_groups = gridDim.x / n_qt;
@@ -460,7 +460,7 @@ scan_mma_bf16_kernel(const __grid_constant__ CUtensorMap tmS,
         // (one full / empty barrier per ring GROUP; a group is committed by the one issuer that owns its tile)
         for (int s = 0; s < stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], CG2 ? 1 : cl); }
         mbar_init(a_full, CG2 ? 8 : 4);
-        for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], CG2 ? 2 * kEpi : kEpi); mbar_init(&x_first[a], 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], CG2 ? 2 * kEpi : kEpi); mbar_init(&turn[a], 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -554,7 +554,6 @@ scan_mma_bf16_kernel(const __grid_constant__ CUtensorMap tmS,
         const int role = warp - 1;
         const uint32_t idesc = umma_idesc_bf16(NT, CG2 ? 2 * QT : QT);
         const uint32_t sB_addr = smem_u32(sB);
-        uint64_t* turn = x_first;
         mbar_wait(a_full, 0);                          // query tile is in tensor memory
         tc_fence_after();
         int stage = 0; uint32_t phase = 0; int it = 0;
